@@ -1,0 +1,566 @@
+// fpt_api.cu — context management and the extern "C" boundary of libfpt_b200.so (include/fpt_b200.h).
+// Host code only: argument checks, buffer staging for FPT_MEM_HOST calls, kernel launches.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fpt_internal.h"
+
+using namespace fpt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(FPT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// grow-only device scratch buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct fpt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // models
+    double *d_bias = nullptr;
+    double bias_dflt = 1e-6;
+    int bias_uniform = 0;
+    bool has_bias = false;
+    double *d_dm = nullptr;
+    int n_models = 0;
+    double2 *d_lut = nullptr;
+    int lut_e = 0, lut_o = 0;
+    int *d_status = nullptr;
+    int64_t launches = 0;
+    size_t score_smem_prepared = 0;
+    // scratch
+    DevBuf plan, scratch;
+    DevBuf h_in[8], h_out[8];  // staging for FPT_MEM_HOST calls
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        want = dev;
+    }
+    ~DeviceGuard() {
+        if (prev != want) cudaSetDevice(prev);
+    }
+    int want;
+};
+
+int check_status(fpt_ctx *ctx, const char *what) {
+    int st = 0;
+    CU(cudaMemcpyAsync(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (st != 0) {
+        CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+        return fail(FPT_ERR_RANGE, "%s: a cut count exceeds the exact-integer range of this window geometry", what);
+    }
+    return FPT_OK;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int fpt_abi_version(void) { return FPT_ABI_VERSION; }
+
+const char *fpt_last_error(void) { return g_err.c_str(); }
+
+int fpt_ctx_create(int device, fpt_ctx **out) {
+    if (!out) return fail(FPT_ERR_ARG, "fpt_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(FPT_ERR_CUDA, "fpt_ctx_create: no CUDA device available (%s)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(FPT_ERR_ARG, "fpt_ctx_create: device %d out of range [0,%d)", device, n);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(FPT_ERR_CUDA, "fpt_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    fpt_ctx *c = new fpt_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(cudaMalloc(&c->d_bias, 4096 * sizeof(double)));
+    CU(cudaMalloc(&c->d_status, sizeof(int)));
+    CU(cudaMemset(c->d_status, 0, sizeof(int)));
+    *out = c;
+    return FPT_OK;
+}
+
+int fpt_ctx_destroy(fpt_ctx *ctx) {
+    if (!ctx) return FPT_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_bias);
+    cudaFree(ctx->d_dm);
+    cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_status);
+    ctx->plan.release();
+    ctx->scratch.release();
+    for (auto &b : ctx->h_in) b.release();
+    for (auto &b : ctx->h_out) b.release();
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return FPT_OK;
+}
+
+int fpt_ctx_set_stream(fpt_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_ctx_set_stream: ctx is NULL");
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return FPT_OK;
+}
+
+int fpt_ctx_sync(fpt_ctx *ctx) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_ctx_sync: ctx is NULL");
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return FPT_OK;
+}
+
+int64_t fpt_ctx_launch_count(const fpt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fpt_bias_upload(fpt_ctx *ctx, const double *table4096, double dflt, int uniform) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_bias_upload: ctx is NULL");
+    if (!uniform && !table4096) return fail(FPT_ERR_ARG, "fpt_bias_upload: table is NULL");
+    DeviceGuard g(ctx->device);
+    // Device layout: little-endian k-mer index (first base in the two low bits), so that a window of
+    // packed 2-bit codes is the index without any bit shuffling.
+    std::vector<double> le(4096, 1.0);
+    if (!uniform) {
+        for (unsigned be = 0; be < 4096; ++be) {
+            unsigned l = 0;
+            for (int j = 0; j < 6; ++j) {
+                unsigned code = (be >> (2 * (5 - j))) & 3u;  // j-th base of the 6-mer
+                l |= code << (2 * j);
+            }
+            le[l] = table4096[be];
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->d_bias, le.data(), 4096 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->bias_dflt = uniform ? 1.0 : dflt;
+    ctx->bias_uniform = uniform ? 1 : 0;
+    ctx->has_bias = true;
+    return FPT_OK;
+}
+
+int fpt_dm_upload(fpt_ctx *ctx, const double *mu_params, const double *r_params, int n_models, int lut_exp,
+                  int lut_obs) {
+    if (!ctx || !mu_params || !r_params) return fail(FPT_ERR_ARG, "fpt_dm_upload: NULL argument");
+    if (n_models < 1) return fail(FPT_ERR_ARG, "fpt_dm_upload: n_models must be >= 1");
+    if (lut_exp < 0 || lut_obs < 0 || (long long)lut_exp * lut_obs > (1LL << 26))
+        return fail(FPT_ERR_ARG, "fpt_dm_upload: table of %d x %d entries is not supported", lut_exp, lut_obs);
+    DeviceGuard g(ctx->device);
+    std::vector<double> host((size_t)n_models * kModelDoubles);
+    for (int i = 0; i < n_models; ++i) {
+        memcpy(&host[(size_t)i * kModelDoubles], mu_params + (size_t)i * 9, 9 * sizeof(double));
+        memcpy(&host[(size_t)i * kModelDoubles + 9], r_params + (size_t)i * 15, 15 * sizeof(double));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_dm);
+    ctx->d_dm = nullptr;
+    cudaFree(ctx->d_lut);
+    ctx->d_lut = nullptr;
+    ctx->lut_e = ctx->lut_o = 0;
+    CU(cudaMalloc(&ctx->d_dm, host.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->d_dm, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_models = n_models;
+    if (lut_exp > 0 && lut_obs > 0) {
+        CU(cudaMalloc(&ctx->d_lut, (size_t)lut_exp * lut_obs * sizeof(double2)));
+        CU(launch_lut_build(ctx->stream, ctx->d_dm, ctx->d_lut, lut_exp, lut_obs));
+        ctx->launches++;
+        ctx->lut_e = lut_exp;
+        ctx->lut_o = lut_obs;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return FPT_OK;
+}
+
+int fpt_pack_sequence(const char *seq, int64_t n, uint32_t *seq2, uint32_t *nmask) {
+    if (n < 0 || (n > 0 && (!seq || !seq2 || !nmask))) return fail(FPT_ERR_ARG, "fpt_pack_sequence: bad argument");
+    int64_t nw2 = (n + 15) / 16, nwm = (n + 31) / 32;
+    memset(seq2, 0, (size_t)nw2 * sizeof(uint32_t));
+    memset(nmask, 0, (size_t)nwm * sizeof(uint32_t));
+    static signed char lut[256];
+    static bool init = false;
+    if (!init) {
+        memset(lut, -1, sizeof lut);
+        lut[(int)'A'] = lut[(int)'a'] = 0;
+        lut[(int)'C'] = lut[(int)'c'] = 1;
+        lut[(int)'G'] = lut[(int)'g'] = 2;
+        lut[(int)'T'] = lut[(int)'t'] = 3;
+        init = true;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        int c = lut[(unsigned char)seq[i]];
+        if (c < 0)
+            nmask[i >> 5] |= 1u << (i & 31);
+        else
+            seq2[i >> 4] |= (uint32_t)c << (2 * (i & 15));
+    }
+    return FPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
+    const int hw = a->half_win_width, shw = a->smoothing_half_win_width;
+    const int wsm = 2 * shw + 1;
+    const int ktrim = shw > 0 ? (int)((double)wsm * a->smoothing_clip) : 0;  // smoothing.h:112
+    int wh_max = 0;
+    ScoreParams p;
+    memset(&p, 0, sizeof p);
+    for (int s = 0; s < a->n_scales; ++s) {
+        int h = a->win_half_width[s];
+        p.whw[s] = h;
+        p.sqrt_k[s] = std::sqrt((double)(2 * h + 1));  // windowing.h:63
+        if (h > wh_max) wh_max = h;
+    }
+    if (!a->winp_out) wh_max = 0;
+    p.seq2 = a->seq2; p.nmask = a->nmask; p.cuts_p = a->cuts_plus; p.cuts_m = a->cuts_minus;
+    p.n_track = a->n_track;
+    p.iv_start = reinterpret_cast<const long long *>(a->iv_start);
+    p.out_off = reinterpret_cast<const long long *>(a->out_off);
+    p.n_iv = a->n_iv; p.total = a->total;
+    p.tile = kComputeMax - 2 * wh_max;
+    p.n_tiles = (a->total + p.tile - 1) / p.tile;
+    p.hw = hw; p.shw = shw; p.ktrim = ktrim;
+    p.combine = a->combine_strands ? 1 : 0;
+    p.n_scales = a->winp_out ? a->n_scales : 0;
+    p.wh_max = wh_max;
+    p.bias = ctx->d_bias; p.dflt = ctx->bias_dflt; p.uniform = ctx->bias_uniform;
+    p.dm = ctx->d_dm; p.lut = ctx->d_lut; p.lut_e = ctx->lut_e; p.lut_o = ctx->lut_o;
+    p.exp_out = a->exp_out; p.obs_out = a->obs_out; p.win_out = a->win_out;
+    p.pval_out = a->pval_out; p.winp_out = a->winp_out;
+    p.hist = reinterpret_cast<unsigned long long *>(a->hist);
+    p.hist_d0 = a->hist_d0; p.hist_d1 = a->hist_d1;
+    // exact 32-bit integer window arithmetic needs (2*hw)*(2*shw+1)*max_cut < 2^32
+    p.max_cut = (unsigned)(0xFFFFFFFFull / ((unsigned long long)(2 * hw) * (unsigned long long)wsm));
+    p.status = ctx->d_status;
+    p.p_cap = kComputeMax + kMaxRegions * (2 * hw + 1);
+    if (p.n_tiles == 0) return FPT_OK;
+    if (p.n_tiles > 0x7FFFFFFFLL) return fail(FPT_ERR_ARG, "fpt_score: too many tiles");
+
+    CU(ctx->plan.need((size_t)p.n_tiles * sizeof(int)));
+    p.tile_first_iv = ctx->plan.as<int>();
+    CU(launch_plan(ctx->stream, p.out_off, p.n_iv, p.total, p.tile, p.n_tiles, ctx->plan.as<int>()));
+    ctx->launches++;
+    size_t smem = score_smem_bytes(hw, p.uniform != 0);
+    if (smem > ctx->score_smem_prepared) {
+        CU(score_kernel_prepare(smem));
+        ctx->score_smem_prepared = smem;
+    }
+    int per_sm = score_kernel_blocks_per_sm(smem);
+    if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: kernel does not fit on an SM (smem %zu)", smem);
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    CU(launch_score(ctx->stream, p, (int)grid));
+    ctx->launches++;
+    return FPT_OK;
+}
+
+int fpt_score(fpt_ctx *ctx, const fpt_score_args *a, int mem) {
+    if (!ctx || !a) return fail(FPT_ERR_ARG, "fpt_score: NULL argument");
+    if (!ctx->has_bias) return fail(FPT_ERR_STATE, "fpt_score: no bias model uploaded (fpt_bias_upload)");
+    const int hw = a->half_win_width, shw = a->smoothing_half_win_width;
+    if (hw < 1 || hw > kMaxHalfWin) return fail(FPT_ERR_ARG, "fpt_score: half_win_width %d not in [1,%d]", hw, kMaxHalfWin);
+    if (shw < 0 || shw > kMaxSmoothHalfWin)
+        return fail(FPT_ERR_ARG, "fpt_score: smoothing_half_win_width %d not in [0,%d]", shw, kMaxSmoothHalfWin);
+    if (shw > 0) {
+        int wsm = 2 * shw + 1;
+        int k = (int)((double)wsm * a->smoothing_clip);
+        if (!(a->smoothing_clip >= 0.0) || 2 * k >= wsm)
+            return fail(FPT_ERR_ARG, "fpt_score: smoothing_clip %g trims the whole window", a->smoothing_clip);
+    }
+    if (a->n_scales < 0 || a->n_scales > FPT_MAX_SCALES) return fail(FPT_ERR_ARG, "fpt_score: n_scales %d not in [0,%d]", a->n_scales, FPT_MAX_SCALES);
+    for (int s = 0; s < a->n_scales; ++s)
+        if (a->win_half_width[s] < 0 || a->win_half_width[s] > kMaxScaleHalfWin)
+            return fail(FPT_ERR_ARG, "fpt_score: window half-width %d not in [0,%d]", a->win_half_width[s], kMaxScaleHalfWin);
+    if (a->n_iv < 0 || a->total < 0 || a->n_track < 0) return fail(FPT_ERR_ARG, "fpt_score: negative size");
+    if (a->n_iv > 0x7FFFFFF0LL) return fail(FPT_ERR_ARG, "fpt_score: too many intervals");
+    const bool want_p = a->pval_out || (a->winp_out && a->n_scales > 0);
+    if (!a->combine_strands && (a->pval_out || a->winp_out || a->hist))
+        return fail(FPT_ERR_ARG, "fpt_score: p-values/windows/histogram need combine_strands=1");
+    if (want_p && !ctx->d_dm) return fail(FPT_ERR_STATE, "fpt_score: no dispersion model uploaded (fpt_dm_upload)");
+    if (a->hist && (a->hist_d0 <= 0 || a->hist_d1 <= 0)) return fail(FPT_ERR_ARG, "fpt_score: bad histogram shape");
+    if (!ctx->bias_uniform && a->total > 0 && (!a->seq2 || !a->nmask)) return fail(FPT_ERR_ARG, "fpt_score: sequence is NULL");
+    if (a->total > 0 && (!a->cuts_plus || !a->cuts_minus || !a->iv_start || !a->out_off))
+        return fail(FPT_ERR_ARG, "fpt_score: NULL input array");
+    DeviceGuard g(ctx->device);
+    if (a->total == 0 || a->n_iv == 0) return FPT_OK;
+
+    if (mem == FPT_MEM_DEVICE) return score_device(ctx, a);
+    if (mem != FPT_MEM_HOST) return fail(FPT_ERR_ARG, "fpt_score: bad mem flag %d", mem);
+
+    // ---- host buffers: stage in, run, stage out ---------------------------------------------------
+    if (a->out_off[a->n_iv] != a->total) return fail(FPT_ERR_ARG, "fpt_score: total != out_off[n_iv]");
+    fpt_score_args d = *a;
+    const size_t nt = (size_t)a->n_track, tot = (size_t)a->total, niv = (size_t)a->n_iv;
+    const size_t w2 = (nt + 15) / 16 * 4, wm = (nt + 31) / 32 * 4;
+    cudaStream_t st = ctx->stream;
+    auto up = [&](DevBuf &b, const void *src, size_t bytes, const void **dst) -> cudaError_t {
+        if (!src) { *dst = nullptr; return cudaSuccess; }
+        cudaError_t e = b.need(bytes ? bytes : 4);
+        if (e != cudaSuccess) return e;
+        *dst = b.p;
+        return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st);
+    };
+    CU(up(ctx->h_in[0], a->seq2, w2, (const void **)&d.seq2));
+    CU(up(ctx->h_in[1], a->nmask, wm, (const void **)&d.nmask));
+    CU(up(ctx->h_in[2], a->cuts_plus, nt * 4, (const void **)&d.cuts_plus));
+    CU(up(ctx->h_in[3], a->cuts_minus, nt * 4, (const void **)&d.cuts_minus));
+    CU(up(ctx->h_in[4], a->iv_start, niv * 8, (const void **)&d.iv_start));
+    CU(up(ctx->h_in[5], a->out_off, (niv + 1) * 8, (const void **)&d.out_off));
+    const size_t mult = a->combine_strands ? 1 : 2;
+    struct OutSpec { double *host; double **dev; size_t n; };
+    OutSpec outs[5] = {{a->exp_out, &d.exp_out, tot * mult},
+                       {a->obs_out, &d.obs_out, tot * mult},
+                       {a->win_out, &d.win_out, tot * mult},
+                       {a->pval_out, &d.pval_out, tot},
+                       {a->winp_out, &d.winp_out, tot * (size_t)a->n_scales}};
+    for (int i = 0; i < 5; ++i) {
+        *outs[i].dev = nullptr;
+        if (!outs[i].host || outs[i].n == 0) continue;
+        CU(ctx->h_out[i].need(outs[i].n * sizeof(double)));
+        *outs[i].dev = ctx->h_out[i].as<double>();
+    }
+    if (a->hist) {
+        size_t hb = (size_t)a->hist_d0 * a->hist_d1 * sizeof(int64_t);
+        CU(ctx->h_out[5].need(hb));
+        d.hist = ctx->h_out[5].as<int64_t>();
+        CU(cudaMemcpyAsync(d.hist, a->hist, hb, cudaMemcpyHostToDevice, st));
+    }
+    int rc = score_device(ctx, &d);
+    if (rc != FPT_OK) return rc;
+    for (int i = 0; i < 5; ++i)
+        if (*outs[i].dev) CU(cudaMemcpyAsync(outs[i].host, *outs[i].dev, outs[i].n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (a->hist)
+        CU(cudaMemcpyAsync(a->hist, d.hist, (size_t)a->hist_d0 * a->hist_d1 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    return check_status(ctx, "fpt_score");
+}
+
+/* Reads and clears the range-error flag of the last asynchronous FPT_MEM_DEVICE calls (synchronises). */
+int fpt_ctx_check(fpt_ctx *ctx) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_ctx_check: ctx is NULL");
+    DeviceGuard g(ctx->device);
+    return check_status(ctx, "fpt_ctx_check");
+}
+
+int fpt_nb_values(fpt_ctx *ctx, const double *exp, const double *obs, int64_t n, int what, int model_index,
+                  int64_t row_len, int model_stride, double *out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_nb_values: ctx is NULL");
+    if (!ctx->d_dm) return fail(FPT_ERR_STATE, "fpt_nb_values: no dispersion model uploaded (fpt_dm_upload)");
+    if (n < 0 || what < 0 || what > 2) return fail(FPT_ERR_ARG, "fpt_nb_values: bad argument");
+    if (n == 0) return FPT_OK;
+    if (!exp || !obs || !out) return fail(FPT_ERR_ARG, "fpt_nb_values: NULL array");
+    long long last_model = model_index + (row_len > 0 ? ((n - 1) / row_len) * (long long)model_stride : 0);
+    if (model_index < 0 || last_model >= ctx->n_models || last_model < 0)
+        return fail(FPT_ERR_ARG, "fpt_nb_values: model index out of range (%d models uploaded)", ctx->n_models);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_nb_values(st, ctx->d_dm, exp, obs, n, what, model_index, row_len, model_stride, out));
+        ctx->launches++;
+        return FPT_OK;
+    }
+    size_t bytes = (size_t)n * sizeof(double);
+    CU(ctx->h_in[0].need(bytes)); CU(ctx->h_in[1].need(bytes)); CU(ctx->h_out[0].need(bytes));
+    CU(cudaMemcpyAsync(ctx->h_in[0].p, exp, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_in[1].p, obs, bytes, cudaMemcpyHostToDevice, st));
+    CU(launch_nb_values(st, ctx->d_dm, ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(), n, what, model_index,
+                        row_len, model_stride, ctx->h_out[0].as<double>()));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+int fpt_window(fpt_ctx *ctx, const double *x, const double *w, int64_t n, const int64_t *seg_off, int64_t n_seg,
+               int hw, int op, double *out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_window: ctx is NULL");
+    if (n < 0 || hw < 0 || op < 0 || op > 4) return fail(FPT_ERR_ARG, "fpt_window: bad argument");
+    if (n == 0) return FPT_OK;
+    if (!x || !out || (op == FPT_WIN_WSTOUFFER && !w)) return fail(FPT_ERR_ARG, "fpt_window: NULL array");
+    if (seg_off && n_seg < 1) return fail(FPT_ERR_ARG, "fpt_window: n_seg must be >= 1 with seg_off");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    size_t bytes = (size_t)n * sizeof(double);
+    CU(ctx->scratch.need(bytes));
+    const bool maps = (op >= FPT_WIN_FISHER);
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_window(st, x, w, n, reinterpret_cast<const long long *>(seg_off), n_seg, hw, op,
+                         ctx->scratch.as<double>(), out));
+        ctx->launches += maps ? 2 : 1;
+        return FPT_OK;
+    }
+    CU(ctx->h_in[0].need(bytes)); CU(ctx->h_out[0].need(bytes));
+    CU(cudaMemcpyAsync(ctx->h_in[0].p, x, bytes, cudaMemcpyHostToDevice, st));
+    const double *dw = nullptr;
+    if (op == FPT_WIN_WSTOUFFER) {
+        CU(ctx->h_in[1].need(bytes));
+        CU(cudaMemcpyAsync(ctx->h_in[1].p, w, bytes, cudaMemcpyHostToDevice, st));
+        dw = ctx->h_in[1].as<double>();
+    }
+    const long long *dseg = nullptr;
+    if (seg_off) {
+        CU(ctx->h_in[2].need((size_t)(n_seg + 1) * 8));
+        CU(cudaMemcpyAsync(ctx->h_in[2].p, seg_off, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+        dseg = ctx->h_in[2].as<long long>();
+    }
+    CU(launch_window(st, ctx->h_in[0].as<double>(), dw, n, dseg, n_seg, hw, op, ctx->scratch.as<double>(),
+                     ctx->h_out[0].as<double>()));
+    ctx->launches += maps ? 2 : 1;
+    CU(cudaMemcpyAsync(out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+int fpt_hist2d(fpt_ctx *ctx, const double *exp, const double *obs, int64_t n, int64_t *hist, int d0, int d1,
+               int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_hist2d: ctx is NULL");
+    if (n < 0 || d0 <= 0 || d1 <= 0 || !hist) return fail(FPT_ERR_ARG, "fpt_hist2d: bad argument");
+    if (n == 0) return FPT_OK;
+    if (!exp || !obs) return fail(FPT_ERR_ARG, "fpt_hist2d: NULL array");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_hist2d(st, exp, obs, n, reinterpret_cast<unsigned long long *>(hist), d0, d1));
+        ctx->launches++;
+        return FPT_OK;
+    }
+    size_t bytes = (size_t)n * sizeof(double), hb = (size_t)d0 * d1 * sizeof(int64_t);
+    CU(ctx->h_in[0].need(bytes)); CU(ctx->h_in[1].need(bytes)); CU(ctx->h_out[0].need(hb));
+    CU(cudaMemcpyAsync(ctx->h_in[0].p, exp, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_in[1].p, obs, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_out[0].p, hist, hb, cudaMemcpyHostToDevice, st));
+    CU(launch_hist2d(st, ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(), n,
+                     ctx->h_out[0].as<unsigned long long>(), d0, d1));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(hist, ctx->h_out[0].p, hb, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+int fpt_posterior(fpt_ctx *ctx, const double *obs, const double *exp, const double *fdr, const double *w,
+                  const double *betas, int n_samples, int64_t m, const int64_t *seg_off, int64_t n_seg,
+                  double fdr_cutoff, int win_hw, double *out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_posterior: ctx is NULL");
+    if (n_samples < 1 || m < 0 || win_hw < 0) return fail(FPT_ERR_ARG, "fpt_posterior: bad argument");
+    if (!ctx->d_dm || ctx->n_models < n_samples)
+        return fail(FPT_ERR_STATE, "fpt_posterior: %d dispersion models uploaded, %d samples", ctx->n_models, n_samples);
+    if (m == 0) return FPT_OK;
+    if (!obs || !exp || !fdr || !w || !betas || !out) return fail(FPT_ERR_ARG, "fpt_posterior: NULL array");
+    if (seg_off && n_seg < 1) return fail(FPT_ERR_ARG, "fpt_posterior: n_seg must be >= 1 with seg_off");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    size_t n = (size_t)n_samples * (size_t)m, bytes = n * sizeof(double);
+    CU(ctx->scratch.need((2 * (size_t)m + 2 * n) * sizeof(double)));
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_posterior(st, ctx->d_dm, obs, exp, fdr, w, betas, n_samples, m,
+                            reinterpret_cast<const long long *>(seg_off), n_seg, fdr_cutoff, win_hw,
+                            ctx->scratch.as<double>(), out));
+        ctx->launches += 3;
+        return FPT_OK;
+    }
+    const double *src[4] = {obs, exp, fdr, w};
+    for (int i = 0; i < 4; ++i) {
+        CU(ctx->h_in[i].need(bytes));
+        CU(cudaMemcpyAsync(ctx->h_in[i].p, src[i], bytes, cudaMemcpyHostToDevice, st));
+    }
+    CU(ctx->h_in[4].need((size_t)n_samples * 2 * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->h_in[4].p, betas, (size_t)n_samples * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const long long *dseg = nullptr;
+    if (seg_off) {
+        CU(ctx->h_in[5].need((size_t)(n_seg + 1) * 8));
+        CU(cudaMemcpyAsync(ctx->h_in[5].p, seg_off, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+        dseg = ctx->h_in[5].as<long long>();
+    }
+    CU(ctx->h_out[0].need(bytes));
+    CU(launch_posterior(st, ctx->d_dm, ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(), ctx->h_in[2].as<double>(),
+                        ctx->h_in[3].as<double>(), ctx->h_in[4].as<double>(), n_samples, m, dseg, n_seg, fdr_cutoff,
+                        win_hw, ctx->scratch.as<double>(), ctx->h_out[0].as<double>()));
+    ctx->launches += 3;
+    CU(cudaMemcpyAsync(out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+int fpt_special(fpt_ctx *ctx, int fn, const double *a, const double *b, const double *x, int64_t n, double *out) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_special: ctx is NULL");
+    if (fn < 0 || fn > 7 || n < 0) return fail(FPT_ERR_ARG, "fpt_special: bad argument");
+    if (n == 0) return FPT_OK;
+    if (!a || !out) return fail(FPT_ERR_ARG, "fpt_special: NULL array");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    size_t bytes = (size_t)n * sizeof(double);
+    const double *src[3] = {a, b ? b : a, x ? x : a};
+    for (int i = 0; i < 3; ++i) {
+        CU(ctx->h_in[i].need(bytes));
+        CU(cudaMemcpyAsync(ctx->h_in[i].p, src[i], bytes, cudaMemcpyHostToDevice, st));
+    }
+    CU(ctx->h_out[0].need(bytes));
+    CU(launch_special(st, fn, ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(), ctx->h_in[2].as<double>(), n,
+                      ctx->h_out[0].as<double>()));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

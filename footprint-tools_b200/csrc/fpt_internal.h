@@ -1,0 +1,72 @@
+// fpt_internal.h — shared declarations between the translation units of libfpt_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fpt_b200.h"
+
+namespace fpt {
+
+constexpr int kModelDoubles = 24;  // 9 mu params + 15 r params (dispersion.pyx:117-125)
+
+// Fused-kernel geometry. One CTA = kThreads threads works on sub-tiles of at
+// most kComputeMax scored positions staged into at most kStageCap shared-memory slots.
+constexpr int kThreads = 512;
+constexpr int kRounds = 2;                        // scored positions per thread per sub-tile
+constexpr int kComputeMax = kThreads * kRounds;   // 1024
+constexpr int kStageCap = kThreads * 4;           // 2048 staged slots (4 per thread)
+constexpr int kMaxRegions = 12;                   // interval pieces per sub-tile
+constexpr int kMaxHalfWin = 16;                   // half_win_width limit
+constexpr int kMaxSmoothHalfWin = 100;            // smoothing_half_win_width limit
+constexpr int kMaxScaleHalfWin = 32;              // Stouffer half-width limit
+
+struct ScoreParams {
+    const uint32_t *seq2, *nmask, *cuts_p, *cuts_m;
+    long long n_track;
+    const long long *iv_start, *out_off;
+    long long n_iv, total;
+    const int *tile_first_iv;
+    long long n_tiles;
+    int tile;  // scored positions per tile
+    int hw, shw, ktrim;
+    int combine;
+    int n_scales;
+    int whw[FPT_MAX_SCALES];
+    double sqrt_k[FPT_MAX_SCALES];
+    int wh_max;
+    const double *bias;  // 4096 doubles, little-endian k-mer index (first base in the low bits)
+    double dflt;
+    int uniform;
+    const double *dm;  // 24 doubles (model 0)
+    const double2 *lut;
+    int lut_e, lut_o;
+    double *exp_out, *obs_out, *win_out, *pval_out, *winp_out;
+    unsigned long long *hist;
+    int hist_d0, hist_d1;
+    unsigned int max_cut;
+    int *status;
+    int p_cap;  // capacity of each bias-propensity staging array
+};
+
+size_t score_smem_bytes(int hw, bool uniform);
+cudaError_t launch_plan(cudaStream_t st, const long long *out_off, long long n_iv, long long total, int tile,
+                        long long n_tiles, int *tile_first_iv);
+cudaError_t launch_score(cudaStream_t st, const ScoreParams &p, int grid);
+cudaError_t score_kernel_prepare(size_t smem);
+int score_kernel_blocks_per_sm(size_t smem);
+
+cudaError_t launch_lut_build(cudaStream_t st, const double *dm, double2 *lut, int lut_e, int lut_o);
+cudaError_t launch_nb_values(cudaStream_t st, const double *dm, const double *e, const double *o, long long n,
+                             int what, int model_index, long long row_len, int model_stride, double *out);
+cudaError_t launch_window(cudaStream_t st, const double *x, const double *w, long long n, const long long *seg_off,
+                          long long n_seg, int hw, int op, double *scratch, double *out);
+cudaError_t launch_hist2d(cudaStream_t st, const double *e, const double *o, long long n, unsigned long long *hist,
+                          int d0, int d1);
+cudaError_t launch_posterior(cudaStream_t st, const double *dm, const double *obs, const double *exp,
+                             const double *fdr, const double *w, const double *betas, int n_samples, long long m,
+                             const long long *seg_off, long long n_seg, double cutoff, int win_hw, double *scratch,
+                             double *out);
+cudaError_t launch_special(cudaStream_t st, int fn, const double *a, const double *b, const double *x, long long n,
+                           double *out);
+
+}  // namespace fpt

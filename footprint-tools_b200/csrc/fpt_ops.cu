@@ -1,0 +1,317 @@
+// fpt_ops.cu — the stand-alone operators of the scoring path (sm_100a): negative-binomial
+// evaluations, window reducers, learn_dm histogram, multi-sample posterior, the (exp,obs) table
+// builder and scalar probes of the special functions. The fused kernel in fpt_score.cu uses the
+// same device functions (fpt_math.cuh), so both give the same bits.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "fpt_internal.h"
+#include "fpt_math.cuh"
+
+namespace fpt {
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+inline unsigned grid_for(long long n, int threads, int max_blocks = 148 * 16) {
+    long long b = (n + threads - 1) / threads;
+    if (b > max_blocks) b = max_blocks;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+// ---- (exp,obs) table: p = nbinom.cdf(obs, r/(r+mu), r), z = ndtri(1-p) ------------------------
+// (modeling/dispersion.pyx:291-316 evaluated once per distinct integer pair)
+__global__ void lut_build_kernel(const double *__restrict__ dm, double2 *__restrict__ lut, int lut_e, int lut_o) {
+    __shared__ double par[kModelDoubles];
+    if (threadIdx.x < kModelDoubles) par[threadIdx.x] = dm[threadIdx.x];
+    __syncthreads();
+    long long n = (long long)lut_e * lut_o;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int e = (int)(i / lut_o), o = (int)(i % lut_o);
+        double r = fit_r(par + 9, (double)e), mu = fit_mu(par, (double)e);
+        double p = nb_cdf(o, nb_prob(r, mu), r);
+        lut[i] = make_double2(p, ndtri_fn(1.0 - p));
+    }
+}
+
+// ---- dispersion_model.p_values / pmf_values / log_pmf_values (dispersion.pyx:170-316) --------
+__global__ void nb_values_kernel(const double *__restrict__ dm, const double *__restrict__ ex,
+                                 const double *__restrict__ ob, long long n, int what, int model_index,
+                                 long long row_len, int model_stride, double *__restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long mi = model_index + (row_len > 0 ? (i / row_len) * model_stride : 0);
+        const double *par = dm + mi * kModelDoubles;
+        double e = ex[i], o = ob[i];
+        double r = fit_r(par + 9, e), mu = fit_mu(par, e);
+        int k = (int)o;  // <int>obs[i]: truncation toward zero
+        double p = nb_prob(r, mu);
+        double v;
+        if (what == FPT_NB_CDF) v = nb_cdf(k, p, r);
+        else {
+            v = nb_logpmf(k, p, r);
+            if (what == FPT_NB_PMF) v = exp(v);
+        }
+        out[i] = v;
+    }
+}
+
+// ---- window reducers (stats/windowing.h:11-123, stats/windowing.pyx:34-58,132-158) ------------
+// pass 1: per-element transform into scratch (ndtri(1-x) for Stouffer, log(x) for Fisher)
+__global__ void window_map_kernel(const double *__restrict__ x, long long n, int op, double *__restrict__ t) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (op == FPT_WIN_STOUFFER || op == FPT_WIN_WSTOUFFER) v = ndtri_fn(1.0 - v);
+        else if (op == FPT_WIN_FISHER) v = log(v);
+        t[i] = v;
+    }
+}
+
+__device__ __forceinline__ long long segment_of(const long long *__restrict__ seg_off, long long n_seg, long long i) {
+    long long a = 0, b = n_seg;
+    while (b - a > 1) {
+        long long m = (a + b) >> 1;
+        if (__ldg(seg_off + m) <= i) a = m; else b = m;
+    }
+    return a;
+}
+
+// pass 2: left-to-right reduction over [i-hw, i+hw] inside the element's segment
+__global__ void window_reduce_kernel(const double *__restrict__ t, const double *__restrict__ w, long long n,
+                                     const long long *__restrict__ seg_off, long long n_seg, int hw, int op,
+                                     double *__restrict__ out) {
+    const int k = 2 * hw + 1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long s0 = 0, s1 = n;
+        if (seg_off) {
+            long long s = segment_of(seg_off, n_seg, i);
+            s0 = __ldg(seg_off + s);
+            s1 = __ldg(seg_off + s + 1);
+        }
+        double res = 1.0;
+        if (i - s0 >= hw && i < s1 - hw) {
+            const double *v = t + (i - hw);
+            if (op == FPT_WIN_SUM) {
+                double s = 0.0;
+                for (int j = 0; j < k; ++j) s = __dadd_rn(s, v[j]);
+                res = s;
+            } else if (op == FPT_WIN_PRODUCT) {
+                double s = 1.0;
+                for (int j = 0; j < k; ++j) s = __dmul_rn(s, v[j]);
+                res = s;
+            } else if (op == FPT_WIN_FISHER) {
+                double s = 0.0;
+                for (int j = 0; j < k; ++j) s = __dadd_rn(s, v[j]);
+                s *= -2.0;
+                res = chdtrc_fn((double)2.0 * k, s);
+            } else if (op == FPT_WIN_STOUFFER) {
+                double s = 0.0;
+                for (int j = 0; j < k; ++j) s = __dadd_rn(s, v[j]);
+                res = ndtr_fn(-__ddiv_rn(s, sqrt((double)k)));
+            } else {
+                const double *ww = w + (i - hw);
+                double s = 0.0, sw = 0.0;
+                for (int j = 0; j < k; ++j) {
+                    s = __dadd_rn(s, __dmul_rn(ww[j], v[j]));
+                    sw = __dadd_rn(sw, __dmul_rn(ww[j], ww[j]));
+                }
+                res = ndtr_fn(-__ddiv_rn(s, sqrt(sw)));
+            }
+        }
+        out[i] = res;
+    }
+}
+
+// ---- learn_dm histogram (cli/learn_dm.py:276-287) --------------------------------------------
+// Python semantics: int() truncates toward zero, negative indices wrap around once, anything still
+// out of range raises IndexError and is skipped.
+__global__ void hist2d_kernel(const double *__restrict__ ex, const double *__restrict__ ob, long long n,
+                              unsigned long long *__restrict__ hist, int d0, int d1) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double e = ex[i], o = ob[i];
+        if (!(fabs(e) < 2147483647.0) || !(fabs(o) < 2147483647.0)) continue;  // NaN/inf/huge -> python raises
+        long long ei = (long long)e, oi = (long long)o;
+        if (ei < 0) ei += d0;
+        if (oi < 0) oi += d1;
+        if (ei < 0 || ei >= d0 || oi < 0 || oi >= d1) continue;
+        atomicAdd(hist + ei * d1 + oi, 1ULL);
+    }
+}
+
+// ---- multi-sample posterior (stats/posterior.py:12-149, cli/post.py:114-122) -----------------
+// pass 1, one thread per column: prior (posterior.py:32-36) and delta (posterior.py:69-88);
+// samples are accumulated in order, as numpy's axis-0 reduction does.
+__global__ void posterior_column_kernel(const double *__restrict__ obs, const double *__restrict__ ex,
+                                        const double *__restrict__ fdr, const double *__restrict__ w,
+                                        const double *__restrict__ betas, int ns, long long m, double cutoff,
+                                        double *__restrict__ pr, double *__restrict__ delta) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+        double k = 0.0, n = 0.0, num = 0.0, den = 0.0;
+        for (int i = 0; i < ns; ++i) {
+            size_t ix = (size_t)i * m + j;
+            double f = fdr[ix];
+            if (f <= cutoff) k += 1.0;
+            n = __dadd_rn(n, w[ix]);
+            double kk = obs[ix], e = ex[ix];
+            double nn = e > kk ? e : kk;  // np.max(np.vstack([exp, obs]), axis=0)
+            if (e != e || kk != kk) nn = CUDART_NAN;
+            double a = __dadd_rn(kk, betas[2 * i]), b = __dadd_rn(__dadd_rn(nn, -kk), betas[2 * i + 1]);
+            // scipy.stats.beta.stats(a, b, moments="mv"): mean a/(a+b), var ab/((a+b)^2 (a+b+1))
+            double ab = __dadd_rn(a, b);
+            double mu = __ddiv_rn(a, ab);
+            double var = __ddiv_rn(__dmul_rn(a, b), __dmul_rn(__dmul_rn(ab, ab), __dadd_rn(ab, 1.0)));
+            if (!(a > 0.0) || !(b > 0.0)) { mu = CUDART_NAN; var = CUDART_NAN; }
+            double ws = __ddiv_rn(1.0, sqrt(var));
+            if (f > cutoff) ws = 0.0;
+            num = __dadd_rn(num, __dmul_rn(ws, mu));
+            den = __dadd_rn(den, ws);
+        }
+        double a = n - k + 0.5, b = k + 0.5;
+        pr[j] = __ddiv_rn(a, __dadd_rn(a, b));
+        double d = __ddiv_rn(num, den);
+        delta[j] = (d != d) ? 1.0 : d;
+    }
+}
+
+// pass 2, one thread per (sample, column): log-pmf with and without the protection factor
+// (posterior.py:115-119 -> dispersion.pyx:170-196)
+__global__ void posterior_logpmf_kernel(const double *__restrict__ dm, const double *__restrict__ obs,
+                                        const double *__restrict__ ex, const double *__restrict__ delta, int ns,
+                                        long long m, double *__restrict__ lp_on, double *__restrict__ lp_off) {
+    long long n = (long long)ns * m;
+    for (long long ix = blockIdx.x * (long long)blockDim.x + threadIdx.x; ix < n; ix += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(ix / m);
+        long long j = ix - (long long)i * m;
+        const double *par = dm + (size_t)i * kModelDoubles;
+        int k = (int)obs[ix];
+        double e_off = ex[ix];
+        double e_on = __dmul_rn(e_off, delta[j]);
+        double r1 = fit_r(par + 9, e_on), m1 = fit_mu(par, e_on);
+        lp_on[ix] = nb_logpmf(k, nb_prob(r1, m1), r1);
+        double r0 = fit_r(par + 9, e_off), m0 = fit_mu(par, e_off);
+        lp_off[ix] = nb_logpmf(k, nb_prob(r0, m0), r0);
+    }
+}
+
+__device__ __forceinline__ double logaddexp_fn(double x, double y) {  // numpy npy_logaddexp
+    if (x == y) return x + 0.693147180559945309417232121458176568;
+    double t = x - y;
+    if (t > 0) return x + log1p(exp(-t));
+    if (t <= 0) return y + log1p(exp(t));
+    return t;  // NaN
+}
+
+// pass 3: windowed log-likelihoods (windowing.sum, edges 1.0), posterior (posterior.py:142-149) and
+// the caller's post-processing (post.py:121-126): -posterior, clipped at 0, transposed.
+__global__ void posterior_combine_kernel(const double *__restrict__ lp_on, const double *__restrict__ lp_off,
+                                         const double *__restrict__ pr, const double *__restrict__ w, int ns,
+                                         long long m, const long long *__restrict__ seg_off, long long n_seg,
+                                         int hw, double *__restrict__ out) {
+    long long n = (long long)ns * m;
+    for (long long ix = blockIdx.x * (long long)blockDim.x + threadIdx.x; ix < n; ix += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(ix / m);
+        long long j = ix - (long long)i * m;
+        long long s0 = 0, s1 = m;
+        if (seg_off) {
+            long long s = segment_of(seg_off, n_seg, j);
+            s0 = __ldg(seg_off + s);
+            s1 = __ldg(seg_off + s + 1);
+        }
+        double ll_on = 1.0, ll_off = 1.0;
+        if (j - s0 >= hw && j < s1 - hw) {
+            double a = 0.0, b = 0.0;
+            for (int d = -hw; d <= hw; ++d) {
+                a = __dadd_rn(a, lp_on[ix + d]);
+                b = __dadd_rn(b, lp_off[ix + d]);
+            }
+            ll_on = a;
+            ll_off = b;
+        }
+        double prior = (w[ix] == 0.0) ? 1.0 : pr[j];
+        double prior_on = log(1.0 - prior), prior_off = log(prior);
+        double p_off = prior_off + ll_off, p_on = prior_on + ll_on;
+        double post = -(p_off - logaddexp_fn(p_on, p_off));
+        if (post <= 0.0) post = 0.0;
+        out[(size_t)j * ns + i] = post;
+    }
+}
+
+// ---- scalar probes -----------------------------------------------------------------------------
+__global__ void special_kernel(int fn, const double *__restrict__ a, const double *__restrict__ b,
+                               const double *__restrict__ x, long long n, double *__restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double v;
+        switch (fn) {
+        case 0: v = incbet_fn(a[i], b[i], x[i]); break;
+        case 1: v = gamma_fn(a[i]); break;
+        case 2: v = lgam_fn(a[i]); break;
+        case 3: v = ndtr_fn(a[i]); break;
+        case 4: v = ndtri_fn(a[i]); break;
+        case 5: v = igamc_fn(a[i], b[i]); break;
+        case 6: v = chdtrc_fn(a[i], b[i]); break;
+        default: v = log1p_fn(a[i]); break;
+        }
+        out[i] = v;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_lut_build(cudaStream_t st, const double *dm, double2 *lut, int lut_e, int lut_o) {
+    long long n = (long long)lut_e * lut_o;
+    if (n <= 0) return cudaSuccess;
+    lut_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(dm, lut, lut_e, lut_o);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nb_values(cudaStream_t st, const double *dm, const double *e, const double *o, long long n,
+                             int what, int model_index, long long row_len, int model_stride, double *out) {
+    if (n <= 0) return cudaSuccess;
+    nb_values_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(dm, e, o, n, what, model_index, row_len,
+                                                                    model_stride, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_window(cudaStream_t st, const double *x, const double *w, long long n, const long long *seg_off,
+                          long long n_seg, int hw, int op, double *scratch, double *out) {
+    if (n <= 0) return cudaSuccess;
+    const double *t = x;
+    if (op == FPT_WIN_FISHER || op == FPT_WIN_STOUFFER || op == FPT_WIN_WSTOUFFER) {
+        window_map_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(x, n, op, scratch);
+        t = scratch;
+    }
+    window_reduce_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(t, w, n, seg_off, n_seg, hw, op, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hist2d(cudaStream_t st, const double *e, const double *o, long long n, unsigned long long *hist,
+                          int d0, int d1) {
+    if (n <= 0) return cudaSuccess;
+    hist2d_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(e, o, n, hist, d0, d1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_posterior(cudaStream_t st, const double *dm, const double *obs, const double *exp,
+                             const double *fdr, const double *w, const double *betas, int n_samples, long long m,
+                             const long long *seg_off, long long n_seg, double cutoff, int win_hw, double *scratch,
+                             double *out) {
+    if (m <= 0 || n_samples <= 0) return cudaSuccess;
+    long long n = (long long)n_samples * m;
+    double *pr = scratch, *delta = scratch + m, *lp_on = scratch + 2 * m, *lp_off = lp_on + n;
+    posterior_column_kernel<<<grid_for(m, 128), 128, 0, st>>>(obs, exp, fdr, w, betas, n_samples, m, cutoff, pr, delta);
+    posterior_logpmf_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(dm, obs, exp, delta, n_samples, m, lp_on,
+                                                                           lp_off);
+    posterior_combine_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(lp_on, lp_off, pr, w, n_samples, m,
+                                                                            seg_off, n_seg, win_hw, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_special(cudaStream_t st, int fn, const double *a, const double *b, const double *x, long long n,
+                           double *out) {
+    if (n <= 0) return cudaSuccess;
+    special_kernel<<<grid_for(n, 128), 128, 0, st>>>(fn, a, b, x, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace fpt

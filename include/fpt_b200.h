@@ -1,0 +1,179 @@
+/* fpt_b200.h — C ABI of libfpt_b200.so, the B200 (sm_100a) implementation of the footprint-tools
+ * per-nucleotide scoring path.
+ *
+ * This is the drop-in boundary: every entry point replaces a native call the
+ * reference makes through Cython `cdef extern` (paths relative to /root/reference), batched over
+ * many intervals. No C++ types, no exceptions, caller owns every buffer. All functions return 0 on
+ * success or a negative FPT_ERR_* code; fpt_last_error() gives the message. Math-domain cases are
+ * not errors: they produce the same sentinel values (0, 1, NaN, +-inf) as the reference's Cephes.
+ *
+ * Memory spaces: each compute call takes `mem` = FPT_MEM_DEVICE (every array argument is a device
+ * pointer on the context's GPU; the call is asynchronous on the context's stream) or FPT_MEM_HOST
+ * (every array argument is a host pointer; the library copies in, runs the same kernels, copies
+ * out and synchronises — this is the path the reference-facing Python modules use).
+ *
+ * Track layout (device-resident, sized for 180 GB of HBM3e — a whole genome plus its two cut
+ * tracks is ~26 GB): a "track" is a coordinate space of n_track bases holding
+ *   seq2   : 2-bit codes A=0 C=1 G=2 T=3, 16 bases per uint32 word, base i in bits 2*(i%16)..+1
+ *   nmask  : 1 bit per base, 32 bases per uint32 word, set when the base is not A/C/G/T
+ *   cuts_plus / cuts_minus : uint32 cut counts per base and strand
+ * Intervals are (iv_start[k], length) pairs in track coordinates; out_off[k] is the offset of
+ * interval k in every output array (out_off[n_iv] = total scored bases). Reads that fall outside
+ * [0, n_track) see zero cuts and an N base.
+ */
+#ifndef FPT_B200_H
+#define FPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPT_ABI_VERSION 1
+
+/* error codes */
+#define FPT_OK 0
+#define FPT_ERR_ARG (-1)    /* bad argument */
+#define FPT_ERR_CUDA (-2)   /* CUDA runtime failure (no device, launch failure, out of memory) */
+#define FPT_ERR_RANGE (-3)  /* a cut count exceeds the supported range for this window geometry */
+#define FPT_ERR_STATE (-4)  /* model not uploaded */
+
+#define FPT_MEM_DEVICE 0
+#define FPT_MEM_HOST 1
+
+/* window reducers, footprint_tools/stats/windowing.h:11-102 */
+#define FPT_WIN_SUM 0
+#define FPT_WIN_PRODUCT 1
+#define FPT_WIN_FISHER 2
+#define FPT_WIN_STOUFFER 3
+#define FPT_WIN_WSTOUFFER 4
+
+/* negative-binomial evaluations, footprint_tools/modeling/dispersion.pyx:170-316 */
+#define FPT_NB_CDF 0
+#define FPT_NB_PMF 1
+#define FPT_NB_LOGPMF 2
+
+#define FPT_MAX_SCALES 8
+
+typedef struct fpt_ctx fpt_ctx;
+
+int fpt_abi_version(void);
+const char *fpt_last_error(void);
+
+/* One context per (process, GPU). Calls on a context are stream-ordered, not concurrent. */
+int fpt_ctx_create(int device, fpt_ctx **out);
+int fpt_ctx_destroy(fpt_ctx *ctx);
+/* Use an external cudaStream_t (e.g. torch's current stream); NULL restores the context's own. */
+int fpt_ctx_set_stream(fpt_ctx *ctx, void *cuda_stream);
+int fpt_ctx_sync(fpt_ctx *ctx);
+/* Reads and clears the deferred range-error flag of earlier asynchronous FPT_MEM_DEVICE calls
+ * (synchronises the stream). Returns FPT_ERR_RANGE if a cut count was too large. */
+int fpt_ctx_check(fpt_ctx *ctx);
+/* Number of this library's kernel launches issued on the context so far. */
+int64_t fpt_ctx_launch_count(const fpt_ctx *ctx);
+
+/* ---- models ------------------------------------------------------------------------------- */
+
+/* Replaces bias_model.__getitem__/kmer_model.probs (footprint_tools/modeling/bias.py:16-17,88-111)
+ * and the minus-strand reverse_complement (modeling/predict.pyx:47-61,153): table4096 (HOST) is
+ * indexed by the 6-mer read 5'->3' with A=0,C=1,G=2,T=3, first base most significant; `dflt` is
+ * returned for any 6-mer containing a non-ACGT base (1e-6 for k-mer models). uniform != 0 gives
+ * bias.uniform_model (bias.py:114-122): every position 1.0 regardless of sequence. */
+int fpt_bias_upload(fpt_ctx *ctx, const double *table4096, double dflt, int uniform);
+
+/* Replaces dispersion_model.fit_mu/fit_r parameter storage (modeling/dispersion.pyx:117-163).
+ * n_models >= 1 consecutive models; mu_params is n_models x 9, r_params n_models x 15 (HOST), in
+ * the reference's layout [breaks, intercepts, slopes]. Also (re)builds, for model 0, the device
+ * table p[e][o] = nbinom.cdf(o, r/(r+mu), r), z[e][o] = ndtri(1 - p) for e < lut_exp, o < lut_obs
+ * with the same device code the direct evaluation uses (bit-identical by construction).
+ * lut_exp = lut_obs = 0 disables the table (every base is evaluated directly). */
+int fpt_dm_upload(fpt_ctx *ctx, const double *mu_params, const double *r_params, int n_models, int lut_exp,
+                  int lut_obs);
+
+/* ---- host-side packing (format conversion only; no scoring arithmetic) ------------------- */
+
+/* seq: n characters (any case); seq2 must hold (n+15)/16 words, nmask (n+31)/32 words (HOST). */
+int fpt_pack_sequence(const char *seq, int64_t n, uint32_t *seq2, uint32_t *nmask);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+
+typedef struct fpt_score_args {
+    /* track */
+    const uint32_t *seq2;
+    const uint32_t *nmask;
+    const uint32_t *cuts_plus;
+    const uint32_t *cuts_minus;
+    int64_t n_track;
+    /* intervals */
+    const int64_t *iv_start; /* n_iv */
+    const int64_t *out_off;  /* n_iv + 1 */
+    int64_t n_iv;
+    int64_t total; /* == out_off[n_iv]; passed so that device-resident offsets need no read-back */
+    /* geometry: prediction(half_win_width, smoothing_half_win_width, smoothing_clip),
+     * footprint_tools/modeling/predict.pyx:85-114 */
+    int half_win_width;
+    int smoothing_half_win_width;
+    double smoothing_clip;
+    /* 1: strand-combined outputs as in cli/detect.py:121-122 (plus[t+1] + minus[t]).
+     * 0: per-strand outputs at the same coordinate (prediction.compute's dict entries). */
+    int combine_strands;
+    /* Stouffer window half-widths (cli/detect.py:84 uses {3}) */
+    int n_scales;
+    int win_half_width[FPT_MAX_SCALES];
+    /* outputs; any may be NULL. combine_strands=1: exp/obs/pval are `total` doubles, winp is
+     * n_scales x total. combine_strands=0: exp/obs/win are 2 x total (plus then minus), pval and
+     * winp must be NULL. */
+    double *exp_out;
+    double *obs_out;
+    double *win_out;
+    double *pval_out;
+    double *winp_out;
+    /* optional learn_dm histogram (cli/learn_dm.py:276-287): hist[int(exp)][int(obs)] += 1 for
+     * exp < hist_d0, obs < hist_d1, accumulated into (not zeroed). NULL to skip. */
+    int64_t *hist;
+    int hist_d0, hist_d1;
+} fpt_score_args;
+
+/* Fused scoring of a batch of intervals: 6-mer bias lookup -> window sums -> trimmed-mean
+ * smoothing -> expected counts -> strand combine -> NB p-values -> multi-scale Stouffer windows.
+ * Replaces, per interval: fast_predict (modeling/predict.h:23-74) incl. windowed_trimmed_mean
+ * (modeling/smoothing.h:107-132), the crop/combine of predict.pyx:157-161 + detect.py:121-122,
+ * dispersion_model.p_values (modeling/dispersion.pyx:291-316 -> hcephes_incbet) and
+ * fast_windowing_func(fast_stouffers_z) (stats/windowing.h:53-84). */
+int fpt_score(fpt_ctx *ctx, const fpt_score_args *args, int mem);
+
+/* dispersion_model.p_values / pmf_values / log_pmf_values (modeling/dispersion.pyx:170-316):
+ * elementwise over n (exp, obs) pairs with model `model_index` (+ model_stride * (i / row_len)
+ * when row_len > 0, for the one-model-per-sample layout of stats/posterior.py:115-119). */
+int fpt_nb_values(fpt_ctx *ctx, const double *exp, const double *obs, int64_t n, int what, int model_index,
+                  int64_t row_len, int model_stride, double *out, int mem);
+
+/* windowing.sum/product/fishers_combined/stouffers_z/weighted_stouffers_z
+ * (stats/windowing.pyx:60-178 -> stats/windowing.h:11-123) over n_seg independent segments
+ * x[seg_off[s] .. seg_off[s+1]); positions closer than hw to a segment end are 1.0.
+ * w is only read for FPT_WIN_WSTOUFFER. seg_off == NULL means one segment of n values. */
+int fpt_window(fpt_ctx *ctx, const double *x, const double *w, int64_t n, const int64_t *seg_off, int64_t n_seg,
+               int hw, int op, double *out, int mem);
+
+/* learn_dm histogram on already-computed (exp, obs) (cli/learn_dm.py:276-287). */
+int fpt_hist2d(fpt_ctx *ctx, const double *exp, const double *obs, int64_t n, int64_t *hist, int d0, int d1,
+               int mem);
+
+/* Multi-sample posterior (stats/posterior.py:12-149 + cli/post.py:114-122) over n_seg intervals of
+ * an (n_samples x m) row-major layout (seg_off over the m columns, NULL = one interval):
+ * prior -> delta -> windowed (hw = win_hw) log-likelihoods on/off -> -(posterior) clipped at 0.
+ * betas is n_samples x 2; model s is used for sample s (models uploaded with fpt_dm_upload).
+ * out is m x n_samples (row-major), i.e. already transposed as post.py:126 returns it. */
+int fpt_posterior(fpt_ctx *ctx, const double *obs, const double *exp, const double *fdr, const double *w,
+                  const double *betas, int n_samples, int64_t m, const int64_t *seg_off, int64_t n_seg,
+                  double fdr_cutoff, int win_hw, double *out, int mem);
+
+/* Scalar probes of the device special functions (used by the parity tests; HOST arrays).
+ * fn: 0 incbet(a,b,x) 1 gamma(a) 2 lgam(a) 3 ndtr(a) 4 ndtri(a) 5 igamc(a,b) 6 chdtrc(a,b) 7 log1p(a) */
+int fpt_special(fpt_ctx *ctx, int fn, const double *a, const double *b, const double *x, int64_t n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPT_B200_H */
