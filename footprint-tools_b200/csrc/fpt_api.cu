@@ -109,6 +109,26 @@ int check_status(fpt_ctx *ctx, const char *what) {
 
 }  // namespace
 
+// Generic host staging: copy `nin` inputs up, run, copy one output down.
+template <class F>
+static int staged_call(fpt_ctx *ctx, int nin, const void *const *src, const size_t *src_bytes, void *dst,
+                       size_t dst_bytes, int n_launch, F &&run) {
+    cudaStream_t st = ctx->stream;
+    const void *dev[8] = {nullptr};
+    for (int i = 0; i < nin; ++i) {
+        if (!src[i]) continue;
+        CU(ctx->h_in[i].need(src_bytes[i] ? src_bytes[i] : 8));
+        CU(cudaMemcpyAsync(ctx->h_in[i].p, src[i], src_bytes[i], cudaMemcpyHostToDevice, st));
+        dev[i] = ctx->h_in[i].p;
+    }
+    CU(ctx->h_out[0].need(dst_bytes ? dst_bytes : 8));
+    CU(run(dev, ctx->h_out[0].p));
+    ctx->launches += n_launch;
+    CU(cudaMemcpyAsync(dst, ctx->h_out[0].p, dst_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
 #pragma GCC visibility push(default)
 extern "C" {
 
@@ -514,7 +534,7 @@ int fpt_posterior(fpt_ctx *ctx, const double *obs, const double *exp, const doub
         CU(launch_posterior(st, ctx->d_dm, obs, exp, fdr, w, betas, n_samples, m,
                             reinterpret_cast<const long long *>(seg_off), n_seg, fdr_cutoff, win_hw,
                             ctx->scratch.as<double>(), out));
-        ctx->launches += 3;
+        ctx->launches += 4;
         return FPT_OK;
     }
     const double *src[4] = {obs, exp, fdr, w};
@@ -534,15 +554,107 @@ int fpt_posterior(fpt_ctx *ctx, const double *obs, const double *exp, const doub
     CU(launch_posterior(st, ctx->d_dm, ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(), ctx->h_in[2].as<double>(),
                         ctx->h_in[3].as<double>(), ctx->h_in[4].as<double>(), n_samples, m, dseg, n_seg, fdr_cutoff,
                         win_hw, ctx->scratch.as<double>(), ctx->h_out[0].as<double>()));
-    ctx->launches += 3;
+    ctx->launches += 4;
     CU(cudaMemcpyAsync(out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+int fpt_posterior_prior(fpt_ctx *ctx, const double *fdr, const double *w, int n_samples, int64_t m, double cutoff,
+                        double pseudocount, double *out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_posterior_prior: ctx is NULL");
+    if (n_samples < 1 || m < 0) return fail(FPT_ERR_ARG, "fpt_posterior_prior: bad argument");
+    if (m == 0) return FPT_OK;
+    if (!fdr || !w || !out) return fail(FPT_ERR_ARG, "fpt_posterior_prior: NULL array");
+    DeviceGuard g(ctx->device);
+    CU(ctx->scratch.need((size_t)m * sizeof(double)));
+    double *pr = ctx->scratch.as<double>();
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_posterior_prior(ctx->stream, fdr, w, n_samples, m, cutoff, pseudocount, pr, out));
+        ctx->launches += 2;
+        return FPT_OK;
+    }
+    size_t bytes = (size_t)n_samples * (size_t)m * sizeof(double);
+    const void *src[2] = {fdr, w};
+    size_t sb[2] = {bytes, bytes};
+    return staged_call(ctx, 2, src, sb, out, bytes, 2, [&](const void **d, void *o) {
+        return launch_posterior_prior(ctx->stream, (const double *)d[0], (const double *)d[1], n_samples, m, cutoff,
+                                      pseudocount, pr, (double *)o);
+    });
+}
+
+int fpt_posterior_delta(fpt_ctx *ctx, const double *obs, const double *exp, const double *fdr, const double *betas,
+                        int n_samples, int64_t m, double cutoff, double *out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_posterior_delta: ctx is NULL");
+    if (n_samples < 1 || m < 0) return fail(FPT_ERR_ARG, "fpt_posterior_delta: bad argument");
+    if (m == 0) return FPT_OK;
+    if (!obs || !exp || !fdr || !betas || !out) return fail(FPT_ERR_ARG, "fpt_posterior_delta: NULL array");
+    DeviceGuard g(ctx->device);
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_posterior_delta(ctx->stream, obs, exp, fdr, betas, n_samples, m, cutoff, out));
+        ctx->launches += 1;
+        return FPT_OK;
+    }
+    size_t bytes = (size_t)n_samples * (size_t)m * sizeof(double);
+    const void *src[4] = {obs, exp, fdr, betas};
+    size_t sb[4] = {bytes, bytes, bytes, (size_t)n_samples * 2 * sizeof(double)};
+    return staged_call(ctx, 4, src, sb, out, (size_t)m * sizeof(double), 1, [&](const void **d, void *o) {
+        return launch_posterior_delta(ctx->stream, (const double *)d[0], (const double *)d[1], (const double *)d[2],
+                                      (const double *)d[3], n_samples, m, cutoff, (double *)o);
+    });
+}
+
+int fpt_posterior_logpost(fpt_ctx *ctx, const double *prior, const double *ll_on, const double *ll_off, int64_t n,
+                          double *out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_posterior_logpost: ctx is NULL");
+    if (n < 0) return fail(FPT_ERR_ARG, "fpt_posterior_logpost: bad argument");
+    if (n == 0) return FPT_OK;
+    if (!prior || !ll_on || !ll_off || !out) return fail(FPT_ERR_ARG, "fpt_posterior_logpost: NULL array");
+    DeviceGuard g(ctx->device);
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_posterior_formula(ctx->stream, prior, ll_on, ll_off, n, out));
+        ctx->launches += 1;
+        return FPT_OK;
+    }
+    size_t bytes = (size_t)n * sizeof(double);
+    const void *src[3] = {prior, ll_on, ll_off};
+    size_t sb[3] = {bytes, bytes, bytes};
+    return staged_call(ctx, 3, src, sb, out, bytes, 1, [&](const void **d, void *o) {
+        return launch_posterior_formula(ctx->stream, (const double *)d[0], (const double *)d[1], (const double *)d[2], n,
+                                        (double *)o);
+    });
+}
+
+int fpt_kmer_probs(fpt_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask, int64_t n_bases, int64_t n_out,
+                   double *out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_kmer_probs: ctx is NULL");
+    if (!ctx->has_bias) return fail(FPT_ERR_STATE, "fpt_kmer_probs: no bias model uploaded (fpt_bias_upload)");
+    if (n_bases < 0 || n_out < 0 || n_out > (n_bases > 5 ? n_bases - 5 : 0))
+        return fail(FPT_ERR_ARG, "fpt_kmer_probs: n_out %lld does not fit %lld bases", (long long)n_out, (long long)n_bases);
+    if (n_out == 0) return FPT_OK;
+    if (!seq2 || !nmask || !out) return fail(FPT_ERR_ARG, "fpt_kmer_probs: NULL array");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_kmer_probs(st, seq2, nmask, n_bases, n_out, ctx->d_bias, ctx->bias_dflt, ctx->bias_uniform, out));
+        ctx->launches++;
+        return FPT_OK;
+    }
+    size_t w2 = (size_t)((n_bases + 15) / 16) * 4, wm = (size_t)((n_bases + 31) / 32) * 4;
+    CU(ctx->h_in[0].need(w2)); CU(ctx->h_in[1].need(wm)); CU(ctx->h_out[0].need((size_t)n_out * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->h_in[0].p, seq2, w2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_in[1].p, nmask, wm, cudaMemcpyHostToDevice, st));
+    CU(launch_kmer_probs(st, ctx->h_in[0].as<uint32_t>(), ctx->h_in[1].as<uint32_t>(), n_bases, n_out, ctx->d_bias,
+                         ctx->bias_dflt, ctx->bias_uniform, ctx->h_out[0].as<double>()));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(out, ctx->h_out[0].p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return FPT_OK;
 }
 
 int fpt_special(fpt_ctx *ctx, int fn, const double *a, const double *b, const double *x, int64_t n, double *out) {
     if (!ctx) return fail(FPT_ERR_ARG, "fpt_special: ctx is NULL");
-    if (fn < 0 || fn > 7 || n < 0) return fail(FPT_ERR_ARG, "fpt_special: bad argument");
+    if (fn < 0 || fn > 10 || n < 0) return fail(FPT_ERR_ARG, "fpt_special: bad argument");
     if (n == 0) return FPT_OK;
     if (!a || !out) return fail(FPT_ERR_ARG, "fpt_special: NULL array");
     DeviceGuard g(ctx->device);

@@ -66,6 +66,14 @@ cudaError_t launch_posterior(cudaStream_t st, const double *dm, const double *ob
                              const double *fdr, const double *w, const double *betas, int n_samples, long long m,
                              const long long *seg_off, long long n_seg, double cutoff, int win_hw, double *scratch,
                              double *out);
+cudaError_t launch_posterior_prior(cudaStream_t st, const double *fdr, const double *w, int ns, long long m,
+                                   double cutoff, double pseudo, double *pr_scratch, double *out);
+cudaError_t launch_posterior_delta(cudaStream_t st, const double *obs, const double *exp, const double *fdr,
+                                   const double *betas, int ns, long long m, double cutoff, double *out);
+cudaError_t launch_posterior_formula(cudaStream_t st, const double *prior, const double *ll_on, const double *ll_off,
+                                     long long n, double *out);
+cudaError_t launch_kmer_probs(cudaStream_t st, const uint32_t *seq2, const uint32_t *nmask, long long n_bases,
+                              long long n_out, const double *bias_le, double dflt, int uniform, double *out);
 cudaError_t launch_special(cudaStream_t st, int fn, const double *a, const double *b, const double *x, long long n,
                            double *out);
 

@@ -140,19 +140,30 @@ __global__ void hist2d_kernel(const double *__restrict__ ex, const double *__res
 }
 
 // ---- multi-sample posterior (stats/posterior.py:12-149, cli/post.py:114-122) -----------------
-// pass 1, one thread per column: prior (posterior.py:32-36) and delta (posterior.py:69-88);
+// pass 1a, one thread per column: prior of the unoccupied state (posterior.py:32-36);
 // samples are accumulated in order, as numpy's axis-0 reduction does.
-__global__ void posterior_column_kernel(const double *__restrict__ obs, const double *__restrict__ ex,
-                                        const double *__restrict__ fdr, const double *__restrict__ w,
-                                        const double *__restrict__ betas, int ns, long long m, double cutoff,
-                                        double *__restrict__ pr, double *__restrict__ delta) {
+__global__ void posterior_prior_kernel(const double *__restrict__ fdr, const double *__restrict__ w, int ns,
+                                       long long m, double cutoff, double pseudo, double *__restrict__ pr) {
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
-        double k = 0.0, n = 0.0, num = 0.0, den = 0.0;
+        double k = 0.0, n = 0.0;
         for (int i = 0; i < ns; ++i) {
             size_t ix = (size_t)i * m + j;
-            double f = fdr[ix];
-            if (f <= cutoff) k += 1.0;
+            if (fdr[ix] <= cutoff) k += 1.0;
             n = __dadd_rn(n, w[ix]);
+        }
+        double a = __dadd_rn(__dadd_rn(n, -k), pseudo), b = __dadd_rn(k, pseudo);
+        pr[j] = __ddiv_rn(a, __dadd_rn(a, b));
+    }
+}
+
+// pass 1b, one thread per column: protection factor delta (posterior.py:69-88)
+__global__ void posterior_delta_kernel(const double *__restrict__ obs, const double *__restrict__ ex,
+                                       const double *__restrict__ fdr, const double *__restrict__ betas, int ns,
+                                       long long m, double cutoff, double *__restrict__ delta) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i < ns; ++i) {
+            size_t ix = (size_t)i * m + j;
             double kk = obs[ix], e = ex[ix];
             double nn = e > kk ? e : kk;  // np.max(np.vstack([exp, obs]), axis=0)
             if (e != e || kk != kk) nn = CUDART_NAN;
@@ -163,15 +174,21 @@ __global__ void posterior_column_kernel(const double *__restrict__ obs, const do
             double var = __ddiv_rn(__dmul_rn(a, b), __dmul_rn(__dmul_rn(ab, ab), __dadd_rn(ab, 1.0)));
             if (!(a > 0.0) || !(b > 0.0)) { mu = CUDART_NAN; var = CUDART_NAN; }
             double ws = __ddiv_rn(1.0, sqrt(var));
-            if (f > cutoff) ws = 0.0;
+            if (fdr[ix] > cutoff) ws = 0.0;
             num = __dadd_rn(num, __dmul_rn(ws, mu));
             den = __dadd_rn(den, ws);
         }
-        double a = n - k + 0.5, b = k + 0.5;
-        pr[j] = __ddiv_rn(a, __dadd_rn(a, b));
         double d = __ddiv_rn(num, den);
         delta[j] = (d != d) ? 1.0 : d;
     }
+}
+
+// prior broadcast over samples with the w == 0 override (posterior.py:38-40)
+__global__ void posterior_expand_prior_kernel(const double *__restrict__ pr, const double *__restrict__ w, int ns,
+                                              long long m, double *__restrict__ out) {
+    long long n = (long long)ns * m;
+    for (long long ix = blockIdx.x * (long long)blockDim.x + threadIdx.x; ix < n; ix += (long long)gridDim.x * blockDim.x)
+        out[ix] = (w[ix] == 0.0) ? 1.0 : pr[ix % m];
 }
 
 // pass 2, one thread per (sample, column): log-pmf with and without the protection factor
@@ -200,6 +217,16 @@ __device__ __forceinline__ double logaddexp_fn(double x, double y) {  // numpy n
     if (t > 0) return x + log1p(exp(-t));
     if (t <= 0) return y + log1p(exp(t));
     return t;  // NaN
+}
+
+// posterior.py:142-149 elementwise: (log prior + ll_off) - logaddexp(log(1-prior) + ll_on, log prior + ll_off)
+__global__ void posterior_formula_kernel(const double *__restrict__ prior, const double *__restrict__ ll_on,
+                                         const double *__restrict__ ll_off, long long n, double *__restrict__ out) {
+    for (long long ix = blockIdx.x * (long long)blockDim.x + threadIdx.x; ix < n; ix += (long long)gridDim.x * blockDim.x) {
+        double p = prior[ix];
+        double p_off = log(p) + ll_off[ix], p_on = log(1.0 - p) + ll_on[ix];
+        out[ix] = p_off - logaddexp_fn(p_on, p_off);
+    }
 }
 
 // pass 3: windowed log-likelihoods (windowing.sum, edges 1.0), posterior (posterior.py:142-149) and
@@ -237,6 +264,27 @@ __global__ void posterior_combine_kernel(const double *__restrict__ lp_on, const
     }
 }
 
+// ---- k-mer propensities of a packed sequence (modeling/bias.py:88-111) ------------------------
+__global__ void kmer_probs_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ nmask,
+                                  long long n_bases, long long n_out, const double *__restrict__ bias_le, double dflt,
+                                  int uniform, double *__restrict__ out) {
+    for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n_out; u += (long long)gridDim.x * blockDim.x) {
+        double v = 1.0;
+        if (!uniform) {
+            unsigned idx = 0, bad = 0;
+            for (int j = 0; j < 6; ++j) {
+                long long q = u + j;
+                if (q >= n_bases) { bad = 1; break; }
+                unsigned code = (__ldg(seq2 + (q >> 4)) >> (2 * (q & 15))) & 3u;
+                bad |= (__ldg(nmask + (q >> 5)) >> (q & 31)) & 1u;
+                idx |= code << (2 * j);
+            }
+            v = bad ? dflt : __ldg(bias_le + idx);
+        }
+        out[u] = v;
+    }
+}
+
 // ---- scalar probes -----------------------------------------------------------------------------
 __global__ void special_kernel(int fn, const double *__restrict__ a, const double *__restrict__ b,
                                const double *__restrict__ x, long long n, double *__restrict__ out) {
@@ -250,7 +298,10 @@ __global__ void special_kernel(int fn, const double *__restrict__ a, const doubl
         case 4: v = ndtri_fn(a[i]); break;
         case 5: v = igamc_fn(a[i], b[i]); break;
         case 6: v = chdtrc_fn(a[i], b[i]); break;
-        default: v = log1p_fn(a[i]); break;
+        case 7: v = log1p_fn(a[i]); break;
+        case 8: v = nb_logpmf((int)a[i], b[i], x[i]); break;
+        case 9: v = exp(nb_logpmf((int)a[i], b[i], x[i])); break;
+        default: v = nb_cdf((int)a[i], b[i], x[i]); break;
         }
         out[i] = v;
     }
@@ -299,11 +350,42 @@ cudaError_t launch_posterior(cudaStream_t st, const double *dm, const double *ob
     if (m <= 0 || n_samples <= 0) return cudaSuccess;
     long long n = (long long)n_samples * m;
     double *pr = scratch, *delta = scratch + m, *lp_on = scratch + 2 * m, *lp_off = lp_on + n;
-    posterior_column_kernel<<<grid_for(m, 128), 128, 0, st>>>(obs, exp, fdr, w, betas, n_samples, m, cutoff, pr, delta);
+    posterior_prior_kernel<<<grid_for(m, 128), 128, 0, st>>>(fdr, w, n_samples, m, cutoff, 0.5, pr);
+    posterior_delta_kernel<<<grid_for(m, 128), 128, 0, st>>>(obs, exp, fdr, betas, n_samples, m, cutoff, delta);
     posterior_logpmf_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(dm, obs, exp, delta, n_samples, m, lp_on,
                                                                            lp_off);
     posterior_combine_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(lp_on, lp_off, pr, w, n_samples, m,
                                                                             seg_off, n_seg, win_hw, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_posterior_prior(cudaStream_t st, const double *fdr, const double *w, int ns, long long m,
+                                   double cutoff, double pseudo, double *pr_scratch, double *out) {
+    if (m <= 0 || ns <= 0) return cudaSuccess;
+    posterior_prior_kernel<<<grid_for(m, 128), 128, 0, st>>>(fdr, w, ns, m, cutoff, pseudo, pr_scratch);
+    posterior_expand_prior_kernel<<<grid_for((long long)ns * m, kEwThreads), kEwThreads, 0, st>>>(pr_scratch, w, ns, m, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_posterior_delta(cudaStream_t st, const double *obs, const double *exp, const double *fdr,
+                                   const double *betas, int ns, long long m, double cutoff, double *out) {
+    if (m <= 0 || ns <= 0) return cudaSuccess;
+    posterior_delta_kernel<<<grid_for(m, 128), 128, 0, st>>>(obs, exp, fdr, betas, ns, m, cutoff, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_posterior_formula(cudaStream_t st, const double *prior, const double *ll_on, const double *ll_off,
+                                     long long n, double *out) {
+    if (n <= 0) return cudaSuccess;
+    posterior_formula_kernel<<<grid_for(n, kEwThreads), kEwThreads, 0, st>>>(prior, ll_on, ll_off, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kmer_probs(cudaStream_t st, const uint32_t *seq2, const uint32_t *nmask, long long n_bases,
+                              long long n_out, const double *bias_le, double dflt, int uniform, double *out) {
+    if (n_out <= 0) return cudaSuccess;
+    kmer_probs_kernel<<<grid_for(n_out, kEwThreads), kEwThreads, 0, st>>>(seq2, nmask, n_bases, n_out, bias_le, dflt,
+                                                                         uniform, out);
     return cudaGetLastError();
 }
 

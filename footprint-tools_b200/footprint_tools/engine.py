@@ -1,0 +1,202 @@
+"""Batched entry points of the B200 scoring path (additive to the reference API).
+
+The reference scores one interval per Python call (footprint_tools/cli/detect.py:93-148); here many
+intervals are packed into one *track* (2-bit sequence + N mask + uint32 cut counts per strand, see
+include/fpt_b200.h) and scored by one fused kernel launch. The same call works on host buffers
+(numpy; copies inside) or on device-resident buffers (torch tensors; no copies).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from ._native import MEM_DEVICE, MEM_HOST, ScoreArgs
+
+
+def counts_to_u32(a, what="cut counts"):
+    """float64/integer cut counts -> uint32 (the device format). Counts must be non-negative integers."""
+    a = np.asarray(a)
+    if a.dtype == np.uint32:
+        return np.ascontiguousarray(a)
+    if a.dtype.kind in "iu":
+        if a.size and (a.min() < 0 or a.max() > 0xFFFFFFFF):
+            raise ValueError("%s out of uint32 range" % what)
+        return np.ascontiguousarray(a, dtype=np.uint32)
+    f = np.asarray(a, dtype=np.float64)
+    if f.size and not (np.all(np.isfinite(f)) and np.all(f >= 0) and np.all(f == np.floor(f)) and f.max() <= 0xFFFFFFFF):
+        raise ValueError("%s must be non-negative integers (the B200 path computes on exact integer counts)" % what)
+    return np.ascontiguousarray(f.astype(np.uint32))
+
+
+class IntervalBatch(object):
+    """Host-side packed batch: per-interval padded arrays laid back to back in one track.
+
+    Interval k contributes a block of L_k + 6 track positions: its L_k + 6 sequence characters
+    (fasta.fetch(start - pad - 1 - 3, end + pad + 3), modeling/predict.pyx:138-140) and its L_k cut
+    counts per strand (read_func[padded interval], predict.pyx:136) placed 3 positions in.
+    """
+
+    def __init__(self, seq2, nmask, cuts_plus, cuts_minus, n_track, iv_start, out_off, block_off):
+        self.seq2, self.nmask = seq2, nmask
+        self.cuts_plus, self.cuts_minus = cuts_plus, cuts_minus
+        self.n_track = int(n_track)
+        self.iv_start = np.ascontiguousarray(iv_start, dtype=np.int64)
+        self.out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+        self.block_off = np.ascontiguousarray(block_off, dtype=np.int64)
+
+    @property
+    def n_iv(self):
+        return len(self.iv_start)
+
+    @property
+    def total(self):
+        return int(self.out_off[-1]) if len(self.out_off) else 0
+
+    @staticmethod
+    def from_padded(seqs, cuts_plus, cuts_minus, pad, per_strand=False):
+        """seqs[k]: str of L_k+6; cuts_*[k]: array of L_k, where L_k = len_k + 2*pad + 1.
+
+        per_strand=False: outputs are the len_k strand-combined positions (cli/detect.py:121-122);
+        per_strand=True: outputs are the len_k+1 positions of prediction.compute's cropped arrays.
+        """
+        n = len(seqs)
+        L = np.array([len(c) for c in cuts_plus], dtype=np.int64)
+        for k in range(n):
+            if len(cuts_minus[k]) != L[k]:
+                raise ValueError("interval %d: strand arrays differ in length" % k)
+            if len(seqs[k]) != L[k] + 6:
+                raise ValueError("interval %d: sequence has %d characters, expected %d" % (k, len(seqs[k]), L[k] + 6))
+        blk = L + 6
+        block_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(blk, out=block_off[1:])
+        n_track = int(block_off[-1])
+        cp = np.zeros(n_track, dtype=np.uint32)
+        cm = np.zeros(n_track, dtype=np.uint32)
+        for k in range(n):
+            o = block_off[k] + 3
+            cp[o:o + L[k]] = counts_to_u32(cuts_plus[k])
+            cm[o:o + L[k]] = counts_to_u32(cuts_minus[k])
+        seq2, nmask = _native.pack_sequence("".join(seqs))
+        out_len = L - 2 * pad - (0 if per_strand else 1)
+        if np.any(out_len < 0):
+            raise ValueError("interval shorter than its padding")
+        out_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(out_len, out=out_off[1:])
+        iv_start = block_off[:-1] + 3 + pad + (0 if per_strand else 1)
+        return IntervalBatch(seq2, nmask, cp, cm, n_track, iv_start, out_off, block_off)
+
+    def to_device(self, device):
+        """Device-resident copy (torch tensors; uint32 payloads carried as int32)."""
+        import torch
+
+        def dev(a):
+            if a.dtype == np.uint32:
+                a = a.view(np.int32)
+            return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
+
+        return DeviceBatch(dev(self.seq2), dev(self.nmask), dev(self.cuts_plus), dev(self.cuts_minus), self.n_track,
+                           dev(self.iv_start), dev(self.out_off), self.n_iv, self.total)
+
+
+class DeviceBatch(object):
+    def __init__(self, seq2, nmask, cuts_plus, cuts_minus, n_track, iv_start, out_off, n_iv, total):
+        self.seq2, self.nmask, self.cuts_plus, self.cuts_minus = seq2, nmask, cuts_plus, cuts_minus
+        self.n_track, self.iv_start, self.out_off, self.n_iv, self.total = n_track, iv_start, out_off, n_iv, total
+
+
+def make_args(batch, hw, shw, clip, combine=True, scales=(), exp=None, obs=None, win=None, pval=None, winp=None,
+              hist=None):
+    a = ScoreArgs()
+    p = _native._ptr
+    a.seq2, a.nmask = p(batch.seq2), p(batch.nmask)
+    a.cuts_plus, a.cuts_minus = p(batch.cuts_plus), p(batch.cuts_minus)
+    a.n_track = batch.n_track
+    a.iv_start, a.out_off = p(batch.iv_start), p(batch.out_off)
+    a.n_iv, a.total = batch.n_iv, batch.total
+    a.half_win_width, a.smoothing_half_win_width, a.smoothing_clip = int(hw), int(shw), float(clip)
+    a.combine_strands = 1 if combine else 0
+    scales = tuple(int(s) for s in scales)
+    if len(scales) > _native.MAX_SCALES:
+        raise ValueError("at most %d window scales" % _native.MAX_SCALES)
+    a.n_scales = len(scales)
+    for i, s in enumerate(scales):
+        a.win_half_width[i] = s
+    a.exp_out, a.obs_out, a.win_out, a.pval_out, a.winp_out = p(exp), p(obs), p(win), p(pval), p(winp)
+    if hist is not None:
+        a.hist = p(hist)
+        a.hist_d0, a.hist_d1 = int(hist.shape[0]), int(hist.shape[1])
+    return a
+
+
+def score_host(ctx, batch, hw=5, shw=50, clip=0.01, scales=(3,), want=("exp", "obs", "pval", "winp"), hist=None,
+               combine=True):
+    """Score a host-resident IntervalBatch; returns a dict of float64 numpy arrays.
+
+    combine=True: 'exp','obs','pval' have batch.total entries, 'winp' is (len(scales), total).
+    combine=False: 'exp','obs','win' are (2, total) (plus, minus); no p-values.
+    """
+    tot = batch.total
+    mult = 1 if combine else 2
+    out = {}
+    for k in want:
+        if k == "winp":
+            out[k] = np.empty((len(scales), tot), dtype=np.float64)
+        elif k in ("exp", "obs", "win"):
+            out[k] = np.empty((mult, tot) if not combine else tot, dtype=np.float64)
+        elif k == "pval":
+            out[k] = np.empty(tot, dtype=np.float64)
+        else:
+            raise KeyError(k)
+    if hist is not None and (hist.dtype != np.int64 or not hist.flags.c_contiguous):
+        raise ValueError("hist must be a C-contiguous int64 array")
+    args = make_args(batch, hw, shw, clip, combine, scales if "winp" in out else (), out.get("exp"), out.get("obs"),
+                     out.get("win"), out.get("pval"), out.get("winp"), hist)
+    ctx.score(args, MEM_HOST)
+    return out
+
+
+def score_device(ctx, dbatch, bufs, hw=5, shw=50, clip=0.01, scales=(3,), hist=None, combine=True):
+    """Asynchronous scoring of a DeviceBatch into preallocated torch float64 buffers
+    (bufs: dict with any of 'exp','obs','win','pval','winp'; hist: int64 tensor or None)."""
+    args = make_args(dbatch, hw, shw, clip, combine, scales if bufs.get("winp") is not None else (), bufs.get("exp"),
+                     bufs.get("obs"), bufs.get("win"), bufs.get("pval"), bufs.get("winp"), hist)
+    ctx.score(args, MEM_DEVICE)
+
+
+def shard_intervals(lengths, world_size):
+    """Bases-balanced partition of an interval list over `world_size` GPUs:
+    longest-processing-time-first greedy on the padded lengths; each rank's list keeps the
+    original order. Returns a list of int64 index arrays."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    order = np.argsort(-lengths, kind="stable")
+    load = np.zeros(world_size, dtype=np.int64)
+    owner = np.empty(len(lengths), dtype=np.int64)
+    for i in order:
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += lengths[i]
+    return [np.nonzero(owner == r)[0] for r in range(world_size)]
+
+
+def allreduce_histogram(hist, group=None):
+    """learn_dm's only collective: SUM all-reduce of the int64 (200 x 1000)
+    histogram across ranks through torch.distributed (NCCL on GPUs, gloo in CPU tests). Integer
+    addition is order-independent, so the result is bit-exact for any number of ranks."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return hist
+    if isinstance(hist, np.ndarray):
+        t = torch.from_numpy(hist)
+        backend = dist.get_backend(group)
+        if backend == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            td = t.to(dev)
+            dist.all_reduce(td, op=dist.ReduceOp.SUM, group=group)
+            hist[...] = td.cpu().numpy()
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return hist
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist

@@ -96,6 +96,11 @@ int fpt_dm_upload(fpt_ctx *ctx, const double *mu_params, const double *r_params,
 /* seq: n characters (any case); seq2 must hold (n+15)/16 words, nmask (n+31)/32 words (HOST). */
 int fpt_pack_sequence(const char *seq, int64_t n, uint32_t *seq2, uint32_t *nmask);
 
+/* kmer_model.probs (modeling/bias.py:88-111): out[u] = model[seq[u : u+6]] for u in [0, n_out), with
+ * n_out <= n_bases - 5 (the reference returns n_bases - 6 values). seq2/nmask as in the track layout. */
+int fpt_kmer_probs(fpt_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask, int64_t n_bases, int64_t n_out,
+                   double *out, int mem);
+
 /* ---- the hot path ------------------------------------------------------------------------- */
 
 typedef struct fpt_score_args {
@@ -169,8 +174,19 @@ int fpt_posterior(fpt_ctx *ctx, const double *obs, const double *exp, const doub
                   const double *betas, int n_samples, int64_t m, const int64_t *seg_off, int64_t n_seg,
                   double fdr_cutoff, int win_hw, double *out, int mem);
 
+/* The three array stages of stats/posterior.py as separate calls (the reference exposes them as
+ * separate functions): compute_prior_weighted (:12-42; out is n_samples x m), compute_delta_prior
+ * (:45-90; out is m) and posterior (:124-149; elementwise over n values). */
+int fpt_posterior_prior(fpt_ctx *ctx, const double *fdr, const double *w, int n_samples, int64_t m, double cutoff,
+                        double pseudocount, double *out, int mem);
+int fpt_posterior_delta(fpt_ctx *ctx, const double *obs, const double *exp, const double *fdr, const double *betas,
+                        int n_samples, int64_t m, double cutoff, double *out, int mem);
+int fpt_posterior_logpost(fpt_ctx *ctx, const double *prior, const double *ll_on, const double *ll_off, int64_t n,
+                          double *out, int mem);
+
 /* Scalar probes of the device special functions (used by the parity tests; HOST arrays).
- * fn: 0 incbet(a,b,x) 1 gamma(a) 2 lgam(a) 3 ndtr(a) 4 ndtri(a) 5 igamc(a,b) 6 chdtrc(a,b) 7 log1p(a) */
+ * fn: 0 incbet(a,b,x) 1 gamma(a) 2 lgam(a) 3 ndtr(a) 4 ndtri(a) 5 igamc(a,b) 6 chdtrc(a,b) 7 log1p(a)
+ *     8 nbinom.logpmf(k=a,p=b,r=x) 9 nbinom.pmf 10 nbinom.cdf (stats/distributions/nbinom.pyx:82-138) */
 int fpt_special(fpt_ctx *ctx, int fn, const double *a, const double *b, const double *x, int64_t n, double *out);
 
 #ifdef __cplusplus

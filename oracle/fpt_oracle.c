@@ -573,7 +573,7 @@ static int base_code(char c) {
 }
 ORC_API void orc_kmer_probs(const char *seq, long n, const double *table, double dflt, int strand, int uniform,
                             double *out) {
-    for (long u = 0; u + 6 <= n; ++u) {
+    for (long u = 0; u + 6 < n; ++u) { /* range(offset, len - offset): n-6 values */
         if (uniform) { out[u] = 1.0; continue; }
         int idx = 0, bad = 0;
         if (strand > 0) {
@@ -583,7 +583,6 @@ ORC_API void orc_kmer_probs(const char *seq, long n, const double *table, double
                 idx = idx * 4 + (c & 3);
             }
         } else {
-            if (u + 7 > n) { out[u] = dflt; continue; } /* cannot happen for u < n-6 */
             for (int j = 0; j < 6; ++j) {
                 int c = base_code(seq[u + 6 - j]);
                 if (c < 0) bad = 1;
