@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -76,6 +77,8 @@ struct fpt_ctx {
     int *d_status = nullptr;
     int64_t launches = 0;
     size_t score_smem_prepared = 0;
+    bool fast_prepared = false;
+    int force_general = 0;  // FPT_B200_GENERAL=1: route everything through the general kernel
     // scratch
     DevBuf plan, scratch;
     DevBuf h_in[8], h_out[8];  // staging for FPT_MEM_HOST calls
@@ -159,6 +162,8 @@ int fpt_ctx_create(int device, fpt_ctx **out) {
     CU(cudaMalloc(&c->d_bias, 4096 * sizeof(double)));
     CU(cudaMalloc(&c->d_status, sizeof(int)));
     CU(cudaMemset(c->d_status, 0, sizeof(int)));
+    const char *force = getenv("FPT_B200_GENERAL");
+    c->force_general = (force && force[0] == '1') ? 1 : 0;
     *out = c;
     return FPT_OK;
 }
@@ -314,12 +319,43 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     p.status = ctx->d_status;
     p.p_cap = kComputeMax + kMaxRegions * (2 * hw + 1);
     if (p.n_tiles == 0) return FPT_OK;
-    if (p.n_tiles > 0x7FFFFFFFLL) return fail(FPT_ERR_ARG, "fpt_score: too many tiles");
 
+    // The throughput kernel serves the ftd detect / learn_dm geometry family; everything else
+    // (per-strand outputs, other window half-widths, deeper trimming) runs on the general kernel.
+    const bool fast = !ctx->force_general && p.combine && hw == kFastHalfWin && (shw == 0 || shw >= 4) && ktrim <= 1 &&
+                      wh_max <= kFastMaxScaleHalfWin && !a->win_out;
+    if (fast) {
+        p.tile = kFastCCap - 2 * wh_max - 48;
+        p.n_tiles = (a->total + p.tile - 1) / p.tile;
+        auto al32 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
+        p.vec_ok = al32(a->exp_out) && al32(a->obs_out) && al32(a->pval_out);
+        p.winp_vec = 0;
+        p.scale_mask = 0;
+        for (int s = 0; s < p.n_scales; ++s) {
+            if (al32(a->winp_out + (size_t)s * (size_t)a->total)) p.winp_vec |= 1u << s;
+            p.scale_mask |= 1u << p.whw[s];
+        }
+        for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) p.inv_sqrt_k[h] = 1.0 / std::sqrt((double)(2 * h + 1));
+    }
+    if (p.n_tiles > 0x7FFFFFFFLL) return fail(FPT_ERR_ARG, "fpt_score: too many tiles");
     CU(ctx->plan.need((size_t)p.n_tiles * sizeof(int)));
     p.tile_first_iv = ctx->plan.as<int>();
     CU(launch_plan(ctx->stream, p.out_off, p.n_iv, p.total, p.tile, p.n_tiles, ctx->plan.as<int>()));
     ctx->launches++;
+    if (fast) {
+        const size_t smem = score_fast_smem_bytes();
+        if (!ctx->fast_prepared) {
+            CU(score_fast_prepare(smem));
+            ctx->fast_prepared = true;
+        }
+        int per_sm = score_fast_blocks_per_sm(smem);
+        if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: fast kernel does not fit on an SM (smem %zu)", smem);
+        long long grid = (long long)ctx->sm_count * per_sm;
+        if (grid > p.n_tiles) grid = p.n_tiles;
+        CU(launch_score_fast(ctx->stream, p, (int)grid));
+        ctx->launches++;
+        return FPT_OK;
+    }
     size_t smem = score_smem_bytes(hw, p.uniform != 0);
     if (smem > ctx->score_smem_prepared) {
         CU(score_kernel_prepare(smem));

@@ -1,0 +1,848 @@
+// fpt_fast.cu — the throughput kernel of the fused scoring path (sm_100a), used for the geometry
+// family of `ftd detect` / `ftd learn_dm`: strand-combined outputs, half_win_width = 5, smoothing
+// window of >= 13 (or none), at most one value trimmed per side, Stouffer half-widths <= 8. Every
+// other parameter combination is served by the general kernel in fpt_score.cu (same results).
+//
+// Reference behaviour reproduced (paths relative to /root/reference):
+//   6-mer bias lookup            footprint_tools/modeling/bias.py:88-111, predict.pyx:47-61,151-153
+//   window sums / expected       footprint_tools/modeling/predict.h:23-74
+//   trimmed-mean smoothing       footprint_tools/modeling/smoothing.h:11-132
+//   crop + strand combine        footprint_tools/modeling/predict.pyx:157-161, cli/detect.py:121-122
+//   NB lower-tail p-value        footprint_tools/modeling/dispersion.pyx:291-316 (table / direct)
+//   Stouffer windows             footprint_tools/stats/windowing.h:53-84, windowing.pyx:34-58
+//   learn_dm histogram           footprint_tools/cli/learn_dm.py:276-287
+//
+// Layout. A persistent grid walks tiles of the flat output index space. A tile is
+// cut into "regions" (the pieces of the intervals it covers). Two index spaces live in shared
+// memory, both in units of one base and both aligned so that 4 consecutive entries owned by one
+// thread are a 16-byte (u32) / 32-byte (f64) aligned group:
+//   c-space  computed positions (outputs + Stouffer halo), c == flat output index (mod 4)
+//   x-space  staged slots (c-space + the smoothing/window halo of each region), x == c (mod 4)
+// All per-slot arrays are structure-of-arrays u32 so that one LDS.128/STS.128 moves a thread's
+// whole group and a warp touches 512 contiguous bytes (no bank conflicts). Each thread owns 4
+// consecutive positions in every phase; global outputs leave as one 256-bit store per array.
+//
+// Exactness (SURVEY.md hard parts 1-3). Integer results must be bit-exact, floats within 1e-9:
+//  * window sums, the trimmed sum (sum - min - max with the reference's OS1==OS2 quirk) and the
+//    observed counts are exact integer arithmetic;
+//  * expected = round(p/win_p * smoothed) is first evaluated with a pairwise-summed win_p and a
+//    Newton reciprocal (relative error < 1e-14 against the reference's value); only when the result
+//    lies within 4e-12*(v+1) of a half-integer is it re-evaluated by a bit-faithful replica of the
+//    reference's operation order (sequential win_p, IEEE divide, quickselect-ordered trimmed
+//    mean). Outside the band both round to the same integer, so the output is bit-exact;
+//  * p-values come from the device-built (exp,obs) table (same device code as the direct path);
+//  * Stouffer sums are accumulated outward from the centre instead of left to right (|dS| ~ 1e-15,
+//    invisible at the 1e-9 tolerance on -log10 p; inf/NaN propagation is order-independent) and the
+//    normal tail uses the reference's own Cephes rationals (ndtr.c) with one exp(-x^2/2).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "fpt_internal.h"
+#include "fpt_math.cuh"
+
+namespace fpt {
+
+namespace {
+
+constexpr int kFT = kFastThreads;       // threads per CTA
+constexpr int kCCap = kFastCCap;        // c-space capacity (4 per thread)
+constexpr int kXCap = kFastXCap;        // x-space capacity
+constexpr int kNG = kXCap / 4;          // groups of 4 slots
+constexpr int kFReg = 16;               // regions per sub-tile
+constexpr int kXPad = 16;               // zero/scratch slots before and after the slot arrays
+constexpr int kZPad = 2;                // groups of padding around the z arrays
+
+struct FastRegions {
+    long long G0[kFReg];    // track coordinate of slot x  = x + G0
+    long long F0[kFReg];    // flat output index of c      = c + F0   (F0 % 4 == 0)
+    long long T0[kFReg];    // interval-local index of c   = c + T0
+    long long len[kFReg];   // interval length
+    long long fa[kFReg], fb[kFReg];  // flat output range written by this region
+    int cblk[kFReg + 1];    // c-space block prefix (multiples of 4)
+    int xblk[kFReg + 1];    // x-space block prefix (multiples of 4)
+    int cb[kFReg], cn[kFReg];
+    int D[kFReg];           // x = c + D  (D % 4 == 0)
+    int nreg;
+    long long next_cur, next_k;
+    unsigned wtot[2][2][kFT / 32];
+};
+
+// ---- constant tables of the normal tail (hcephes/src/cprob/ndtr.c:4-32) ----------------------
+__constant__ double kErfcP[9] = {2.46196981473530512524E-10, 5.64189564831068821977E-1, 7.46321056442269912687E0,
+                                 4.86371970985681366614E1,   1.96520832956077098242E2,  5.26445194995477358631E2,
+                                 9.34528527171957607540E2,   1.02755188689515710272E3,  5.57535335369399327526E2};
+__constant__ double kErfcQ[8] = {1.32281951154744992508E1, 8.67072140885989742329E1, 3.54937778887819891062E2,
+                                 9.75708501743205489753E2, 1.82390916687909736289E3, 2.24633760818710981792E3,
+                                 1.65666309194161350182E3, 5.57535340817727675546E2};
+__constant__ double kErfcR[6] = {5.64189583547755073984E-1, 1.27536670759978104416E0, 5.01905042251180477414E0,
+                                 6.16021097993053585195E0,  7.40974269950448939160E0, 2.97886665372100240670E0};
+__constant__ double kErfcS[6] = {2.26052863220117276590E0, 9.39603524938001434673E0, 1.20489539808096656605E1,
+                                 1.70814450747565897222E1, 9.60896809063285878198E0, 3.36907645100081516050E0};
+__constant__ double kErfT[5] = {9.60497373987051638749E0, 9.00260197203842689217E1, 2.23200534594684319226E3,
+                                7.00332514112805075473E3, 5.55923013010394962768E4};
+__constant__ double kErfU[5] = {3.35617141647503099647E1, 5.21357949780152679795E2, 4.59432382970980127987E3,
+                                2.26290000613890934246E4, 4.92673942608635921086E4};
+
+template <int N>
+__device__ __forceinline__ double cpoly(double x, const double *c) {
+    double a = c[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) a = fma(a, x, c[i]);
+    return a;
+}
+template <int N>
+__device__ __forceinline__ double cpoly1(double x, const double *c) {
+    double a = x + c[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) a = fma(a, x, c[i]);
+    return a;
+}
+
+// 1/d for finite normal d, full double precision (two Newton steps on MUFU.RCP64H)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Lower-tail normal probability of a (hcephes_ndtr, ndtr.c:34-59) with the same rationals; the
+// reference's exp(-a^2) split + sqrt (expx2.c, ndtr.c:52-53) is replaced by one exp(-a^2/2) whose
+// argument carries the rounding error of the square (relative error of the result < 1e-15).
+// Infinite arguments give NaN as in the reference (erfce(inf) = inf/inf, ndtr.c:65-76).
+__device__ __forceinline__ double ndtr_fast(double a) {
+    const double x = a * kSqrtH;
+    const double z = fabs(x);
+    double y;
+    if (z < 1.0) {
+        const double zz = x * x;
+        y = fma(0.5 * x, cpoly<5>(zz, kErfT) * fast_rcp(cpoly1<5>(zz, kErfU)), 0.5);
+    } else {
+        double num, den;
+        if (z < 8.0) {
+            num = cpoly<9>(z, kErfcP);
+            den = cpoly1<8>(z, kErfcQ);
+        } else {
+            num = cpoly<6>(z, kErfcR);
+            den = cpoly1<6>(z, kErfcS);
+        }
+        // exp(-z^2) with z^2 = s + e (s rounded, e the exact remainder): exp(-s) * (1 - e)
+        const double s = z * z;
+        const double e = fma(z, z, -s);
+        double ex = exp(-s);
+        ex = fma(-e, ex, ex);
+        y = 0.5 * num * fast_rcp(den) * ex;
+        if (!(z < 1e300)) y = CUDART_NAN;  // +-inf and NaN
+        if (x > 0) y = 1.0 - y;
+    }
+    return y;
+}
+
+__device__ __forceinline__ int fregion_of(const int *bases, int nreg, int v) {
+    int r = 0;
+#pragma unroll 4
+    for (int j = 1; j < nreg; ++j) r += (v >= bases[j]) ? 1 : 0;
+    return r;
+}
+
+__device__ __forceinline__ unsigned frevcomp12(unsigned x) {
+    unsigned r = __brev(x) >> 20;
+    r = ((r & 0xAAAu) >> 1) | ((r & 0x555u) << 1);
+    return r ^ 0xFFFu;
+}
+
+// `nbits` (<= 32) bits starting at bit `bit0` of a packed little-endian u32 array of `nwords`;
+// bits beyond the array read as `fill`.
+__device__ __forceinline__ unsigned ffetch_bits(const uint32_t *__restrict__ arr, long long nwords, long long bit0,
+                                               int nbits) {
+    long long w = bit0 >> 5;
+    int sh = (int)(bit0 & 31);
+    unsigned lo = (w >= 0 && w < nwords) ? __ldg(arr + w) : 0u;
+    unsigned hi = (w + 1 >= 0 && w + 1 < nwords) ? __ldg(arr + w + 1) : 0u;
+    unsigned v = __funnelshift_r(lo, hi, sh);
+    return nbits == 32 ? v : (v & ((1u << nbits) - 1u));
+}
+
+__device__ __forceinline__ void lds4(const uint32_t *p, unsigned (&v)[4]) {
+    const uint4 q = *reinterpret_cast<const uint4 *>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+
+// 4 consecutive u32 starting at arbitrary slot `i` (k = i & 3 is warp-uniform): two aligned loads
+__device__ __forceinline__ void lds4_unaligned(const uint32_t *arr, int i, unsigned (&o)[4]) {
+    const int k = i & 3;
+    unsigned a[4], b[4];
+    lds4(arr + (i - k), a);
+    if (k == 0) {
+        o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
+        return;
+    }
+    lds4(arr + (i - k + 4), b);
+    if (k == 1) { o[0] = a[1]; o[1] = a[2]; o[2] = a[3]; o[3] = b[0]; }
+    else if (k == 2) { o[0] = a[2]; o[1] = a[3]; o[2] = b[0]; o[3] = b[1]; }
+    else { o[0] = a[3]; o[1] = b[0]; o[2] = b[1]; o[3] = b[2]; }
+}
+
+// o[e] = s[k + e], k in 0..3 warp-uniform
+__device__ __forceinline__ void pick4(const unsigned (&s)[8], int k, unsigned (&o)[4]) {
+    if (k == 0) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; }
+    else if (k == 1) { o[0] = s[1]; o[1] = s[2]; o[2] = s[3]; o[3] = s[4]; }
+    else if (k == 2) { o[0] = s[2]; o[1] = s[3]; o[2] = s[4]; o[3] = s[5]; }
+    else { o[0] = s[3]; o[1] = s[4]; o[2] = s[5]; o[3] = s[6]; }
+}
+
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+// smoothing.h:11-53 on a thread-local buffer (exact path only)
+__device__ double fnr_select(double *arr, unsigned n, unsigned k) {
+    unsigned lo = 0, hi = n - 1;
+    for (;;) {
+        if (hi <= lo + 1) {
+            if (hi == lo + 1 && arr[hi] < arr[lo]) { double t = arr[lo]; arr[lo] = arr[hi]; arr[hi] = t; }
+            return arr[k];
+        }
+        unsigned mid = (lo + hi) >> 1;
+        double t;
+        t = arr[mid]; arr[mid] = arr[lo + 1]; arr[lo + 1] = t;
+        if (arr[lo] > arr[hi]) { t = arr[lo]; arr[lo] = arr[hi]; arr[hi] = t; }
+        if (arr[lo + 1] > arr[hi]) { t = arr[lo + 1]; arr[lo + 1] = arr[hi]; arr[hi] = t; }
+        if (arr[lo] > arr[lo + 1]) { t = arr[lo]; arr[lo] = arr[lo + 1]; arr[lo + 1] = t; }
+        unsigned i = lo + 1, j = hi;
+        double piv = arr[lo + 1];
+        for (;;) {
+            do i++; while (arr[i] < piv);
+            do j--; while (arr[j] > piv);
+            if (j < i) break;
+            t = arr[i]; arr[i] = arr[j]; arr[j] = t;
+        }
+        arr[lo + 1] = arr[j];
+        arr[j] = piv;
+        if (j >= k) hi = j - 1;
+        if (j <= k) lo = i;
+    }
+}
+
+// Bit-faithful trimmed_mean (smoothing.h:59-104) of wc[i0 .. i0+w)
+__device__ __noinline__ double ftrimmed_mean_exact(const uint32_t *wc, int i0, int w, int k) {
+    double buf[2 * kMaxSmoothHalfWin + 1];
+    for (int j = 0; j < w; ++j) buf[j] = (double)wc[i0 + j];
+    double os1 = fnr_select(buf, w, k);
+    double os2 = fnr_select(buf, w, w - k - 1);
+    double b = 0, d = 0, dm = 0, bm = 0;
+    for (int j = 0; j < w; ++j) {
+        double v = buf[j];
+        if (v < os1) bm += 1; else if (v == os1) b += 1;
+        if (v < os2) dm += 1; else if (v == os2) d += 1;
+    }
+    double w1 = __ddiv_rn(b + bm - (double)k, b);
+    double w2 = __ddiv_rn((double)(w - k) - dm, d);
+    double t = 0;
+    for (int j = 0; j < w; ++j) {
+        double v = buf[j], c;
+        if (v < os2 && v > os1) c = v;
+        else if (v < os1) c = 0;
+        else if (v > os2) c = 0;
+        else if (v == os1) c = __dmul_rn(w1, v);
+        else c = __dmul_rn(w2, v);
+        t = __dadd_rn(t, c);
+    }
+    return __ddiv_rn(t, (double)(w - 2 * k));
+}
+
+// propensity of the k-mer whose first base is track coordinate q (6 bases), forward or
+// reverse-complemented; any base outside the track or not ACGT gives the default
+__device__ __noinline__ double fkmer_prop(const ScoreParams &P, const double *tab, long long q, int rc) {
+    if (P.uniform) return 1.0;
+    if (q < 0 || q + 6 > P.n_track) return P.dflt;
+    const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
+    unsigned nb = ffetch_bits(P.nmask, nwm, q, 6);
+    if (nb) return P.dflt;
+    unsigned km = ffetch_bits(P.seq2, nw2, 2 * q, 12);
+    return tab[rc ? frevcomp12(km) : km];
+}
+
+// The reference's own operation order for one strand position (predict.h:41-63): sequential window
+// of propensities, IEEE divide, smoothed count, multiply, round half away from zero.
+//   strand 0: position j uses k-mers starting at j-3; strand 1: reverse complement of j-2
+__device__ __noinline__ double fexpected_exact(const ScoreParams &P, const double *tab, const uint32_t *wc, int hw,
+                                               int shw, int ktrim, long long j, int slot, int strand) {
+    const int off = strand ? 2 : 3;
+    double wp = 0.0;
+    for (int m = -hw; m < hw; ++m) wp = __dadd_rn(wp, fkmer_prop(P, tab, j + m - off, strand));
+    const double ratio = __ddiv_rn(fkmer_prop(P, tab, j - off, strand), wp);
+    double sm;
+    if (shw == 0) {
+        sm = (double)wc[slot];
+    } else if (ktrim == 0) {
+        unsigned long long t = 0;
+        for (int m = -shw; m <= shw; ++m) t += wc[slot + m];
+        sm = __ddiv_rn((double)t, (double)(2 * shw + 1));
+    } else {
+        sm = ftrimmed_mean_exact(wc, slot - shw, 2 * shw + 1, ktrim);
+    }
+    return round(__dmul_rn(ratio, sm));
+}
+
+template <int HW>
+__global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P) {
+    static_assert(HW >= 1 && HW <= 5, "slot loads cover [x0-8, x0+8)");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *tab = reinterpret_cast<double *>(smem_raw);                              // 4096 f64
+    uint32_t *cp = reinterpret_cast<uint32_t *>(tab + 4096) + kXPad;                 // cuts, plus strand
+    uint32_t *cm = cp + kXCap + 2 * kXPad;                                           // cuts, minus strand
+    uint32_t *wcp = cm + kXCap + kXPad;                                              // 2*HW-wide window sums
+    uint32_t *wcm = wcp + kXCap + kXPad;
+    uint32_t *prp = wcm + kXCap + kXPad;                                             // inclusive prefix of wc
+    uint32_t *prm = prp + kXCap + kXPad;
+    uint4 *G0 = reinterpret_cast<uint4 *>(prm + kXCap + kXPad);                      // group (min,max) x2 strands
+    uint4 *G1 = G0 + kNG;
+    double2 *zA = reinterpret_cast<double2 *>(G1 + kNG) + kZPad;                     // z of c%4 in {0,1}
+    double2 *zB = zA + kCCap / 4 + 2 * kZPad;                                        // z of c%4 in {2,3}
+    double *dmp = reinterpret_cast<double *>(zB + kCCap / 4 + kZPad);                // 24
+    FastRegions *R = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shw = P.shw, ktrim = P.ktrim;
+    const int pad = HW + shw;
+    const int wsm = 2 * shw + 1;
+    const int WH = P.wh_max;
+    const int PADX = (pad + 1 + 3) & ~3, PADR = (pad + 3) & ~3;
+    const bool want_z = (P.winp_out != nullptr && P.n_scales > 0);
+    const bool want_p = (P.pval_out != nullptr) || want_z;
+    const double dW = (double)(wsm - 2 * ktrim);
+
+    if (!P.uniform)
+        for (int i = tid; i < 4096; i += kFT) tab[i] = P.bias[i];
+    if (tid < kModelDoubles) dmp[tid] = P.dm ? P.dm[tid] : 0.0;
+    for (int i = tid; i < kXPad; i += kFT) {  // slots read before/after the staged range
+        cp[-1 - i] = 0; cm[-1 - i] = 0; cp[kXCap + i] = 0; cm[kXCap + i] = 0;
+    }
+    __syncthreads();
+
+    // smoothing-window group geometry (uniform): a window of wsm slots starting at slot a covers the
+    // tail of group a>>2, nf full groups and the head of the last group; nf >= nfmin >= pow2
+    int pow2 = 1;
+    if (shw > 0 && ktrim > 0) {
+        const int nfmin = (wsm - 5) >> 2;
+        while (pow2 * 2 <= nfmin) pow2 *= 2;
+    }
+
+    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const long long lo = tile * (long long)P.tile;
+        const long long hi = (lo + P.tile < P.total) ? lo + P.tile : P.total;
+        long long cur = lo;
+        long long k = P.tile_first_iv[tile];
+        while (cur < hi) {
+            // ---- region table (warp 0): lane l <-> interval k + l ----------------------------
+            if (warp == 0) {
+                const long long kk = k + lane;
+                const bool valid = lane < kFReg && kk < P.n_iv;
+                long long o0 = 0, o1 = 0, st = 0;
+                if (valid) {
+                    o0 = __ldg(P.out_off + kk);
+                    o1 = __ldg(P.out_off + kk + 1);
+                    st = __ldg(P.iv_start + kk);
+                }
+                long long fa = o0 > cur ? o0 : cur;
+                long long fb = o1 < hi ? o1 : hi;
+                bool has = valid && fa < fb;
+                const long long len = o1 - o0;
+                long long ta = fa - o0 - WH; if (ta < 0) ta = 0;
+                long long tb = fb - o0 + WH; if (tb > len) tb = len;
+                int cn = has ? (int)(tb - ta) : 0;
+                const int lead = (int)((o0 + ta) & 3);
+                int cspan = has ? ((lead + cn + 3) & ~3) : 0;
+                int xspan = has ? cspan + PADX + PADR : 0;
+                int cs = cspan, xs = xspan;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int a = __shfl_up_sync(0xffffffffu, cs, d);
+                    int b = __shfl_up_sync(0xffffffffu, xs, d);
+                    if (lane >= d) { cs += a; xs += b; }
+                }
+                const bool over = has && (cs > kCCap || xs > kXCap);
+                const unsigned overmask = __ballot_sync(0xffffffffu, over);
+                const int first_over = overmask ? (__ffs(overmask) - 1) : 32;
+                const int cex = cs - cspan, xex = xs - xspan;
+                if (lane == first_over) {
+                    int avail = kCCap - cex;
+                    const int ax = kXCap - xex - PADX - PADR;
+                    if (ax < avail) avail = ax;
+                    avail &= ~3;
+                    const int cn2 = avail - lead;
+                    const long long fb2 = o0 + ta + cn2 - WH;
+                    if (cn2 > 0 && fb2 > fa) {
+                        fb = fb2; tb = ta + cn2; cn = cn2; cspan = avail; xspan = cspan + PADX + PADR;
+                    } else {
+                        has = false;
+                    }
+                }
+                if (lane > first_over) has = false;
+                const unsigned incl = __ballot_sync(0xffffffffu, has);
+                const int r = __popc(incl & ((1u << lane) - 1u));
+                const int nreg = __popc(incl);
+                if (has) {
+                    const int cb = cex + lead;
+                    const int D = (xex - cex) + PADX;
+                    R->cblk[r] = cex; R->xblk[r] = xex;
+                    R->cb[r] = cb; R->cn[r] = cn; R->D[r] = D;
+                    R->G0[r] = st + ta - cb - D;
+                    R->F0[r] = o0 + ta - cb;
+                    R->T0[r] = ta - cb;
+                    R->len[r] = len;
+                    R->fa[r] = fa; R->fb[r] = fb;
+                }
+                const int last = incl ? (31 - __clz(incl)) : -1;
+                if (lane == (last < 0 ? 0 : last)) {
+                    if (last < 0) {
+                        R->nreg = 0;
+                        R->cblk[0] = R->xblk[0] = 0;
+                        const long long nk = k + kFReg;
+                        R->next_k = nk < P.n_iv ? nk : P.n_iv;
+                        R->next_cur = (nk >= P.n_iv) ? hi : cur;
+                    } else {
+                        R->nreg = nreg;
+                        R->cblk[nreg] = cex + cspan;
+                        R->xblk[nreg] = xex + xspan;
+                        R->next_cur = fb;
+                        R->next_k = (fb == o1) ? kk + 1 : kk;
+                    }
+                }
+            }
+            __syncthreads();
+            const int nreg = R->nreg;
+            cur = R->next_cur;
+            k = R->next_k;
+            if (nreg == 0) { __syncthreads(); continue; }
+            const int NX = R->xblk[nreg], NC = R->cblk[nreg];
+            const int NXG = NX >> 2;
+
+            // ---- phase 1: stage cut counts, coalesced per region ------------------------------
+            {
+                bool bad = false;
+                for (int r = 0; r < nreg; ++r) {
+                    const int xe = R->xblk[r + 1];
+                    const long long g0 = R->G0[r];
+                    for (int x = R->xblk[r] + tid; x < xe; x += kFT) {
+                        const long long g = x + g0;
+                        unsigned a = 0, b = 0;
+                        if (g >= 0 && g < P.n_track) {
+                            a = __ldg(P.cuts_p + g);
+                            b = __ldg(P.cuts_m + g);
+                        }
+                        bad |= (a > P.max_cut) | (b > P.max_cut);
+                        cp[x] = a;
+                        cm[x] = b;
+                    }
+                }
+                if (bad) atomicOr(P.status, 1);
+            }
+            __syncthreads();
+
+            // ---- phase 2: window sums, their block-wide prefix sums, group min/max ------------
+            {
+                unsigned pfx[2][2][4];  // [round][strand][e]: thread-local inclusive prefix of wc
+                unsigned incl_w[2][2];  // warp-inclusive scan of the thread totals
+#pragma unroll
+                for (int rd = 0; rd < 2; ++rd) {
+                    const int xg = tid + rd * kFT;
+                    const int x0 = xg << 2;
+                    unsigned wc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+                    if (xg < NXG) {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            const uint32_t *src = s ? cm : cp;
+                            unsigned c[16];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                unsigned t4[4];
+                                lds4(src + x0 - 8 + 4 * q, t4);
+                                c[4 * q] = t4[0]; c[4 * q + 1] = t4[1]; c[4 * q + 2] = t4[2]; c[4 * q + 3] = t4[3];
+                            }
+                            unsigned sum = 0;
+#pragma unroll
+                            for (int j = 8 - HW; j < 8 + HW; ++j) sum += c[j];
+                            wc[s][0] = sum;
+#pragma unroll
+                            for (int e = 0; e < 3; ++e) {
+                                sum += c[8 + e + HW] - c[8 + e - HW];
+                                wc[s][e + 1] = sum;
+                            }
+                        }
+                        *reinterpret_cast<uint4 *>(wcp + x0) = make_uint4(wc[0][0], wc[0][1], wc[0][2], wc[0][3]);
+                        *reinterpret_cast<uint4 *>(wcm + x0) = make_uint4(wc[1][0], wc[1][1], wc[1][2], wc[1][3]);
+                        if (ktrim > 0 && shw > 0) {
+                            uint4 g;
+                            g.x = min(min(wc[0][0], wc[0][1]), min(wc[0][2], wc[0][3]));
+                            g.y = max(max(wc[0][0], wc[0][1]), max(wc[0][2], wc[0][3]));
+                            g.z = min(min(wc[1][0], wc[1][1]), min(wc[1][2], wc[1][3]));
+                            g.w = max(max(wc[1][0], wc[1][1]), max(wc[1][2], wc[1][3]));
+                            G0[xg] = g;
+                        }
+                    }
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        unsigned a = wc[s][0];
+                        pfx[rd][s][0] = a;
+                        a += wc[s][1]; pfx[rd][s][1] = a;
+                        a += wc[s][2]; pfx[rd][s][2] = a;
+                        a += wc[s][3]; pfx[rd][s][3] = a;
+                        incl_w[rd][s] = a;
+                    }
+                }
+                if (shw > 0) {
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                        for (int rd = 0; rd < 2; ++rd)
+#pragma unroll
+                            for (int s = 0; s < 2; ++s) {
+                                unsigned v = __shfl_up_sync(0xffffffffu, incl_w[rd][s], d);
+                                if (lane >= d) incl_w[rd][s] += v;
+                            }
+                    }
+                    if (lane == 31) {
+                        R->wtot[0][0][warp] = incl_w[0][0]; R->wtot[0][1][warp] = incl_w[0][1];
+                        R->wtot[1][0][warp] = incl_w[1][0]; R->wtot[1][1][warp] = incl_w[1][1];
+                    }
+                    __syncthreads();
+                    unsigned base[2][2];
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        unsigned before = 0, all0 = 0;
+#pragma unroll
+                        for (int w2 = 0; w2 < kFT / 32; ++w2) {
+                            const unsigned t0 = R->wtot[0][s][w2];
+                            all0 += t0;
+                            if (w2 < warp) before += t0;
+                        }
+                        unsigned before1 = 0;
+#pragma unroll
+                        for (int w2 = 0; w2 < kFT / 32; ++w2)
+                            if (w2 < warp) before1 += R->wtot[1][s][w2];
+                        base[0][s] = before + incl_w[0][s] - pfx[0][s][3];
+                        base[1][s] = all0 + before1 + incl_w[1][s] - pfx[1][s][3];
+                    }
+#pragma unroll
+                    for (int rd = 0; rd < 2; ++rd) {
+                        const int xg = tid + rd * kFT;
+                        if (xg < NXG) {
+                            const int x0 = xg << 2;
+                            const unsigned bp = base[rd][0], bm = base[rd][1];
+                            *reinterpret_cast<uint4 *>(prp + x0) = make_uint4(bp + pfx[rd][0][0], bp + pfx[rd][0][1],
+                                                                              bp + pfx[rd][0][2], bp + pfx[rd][0][3]);
+                            *reinterpret_cast<uint4 *>(prm + x0) = make_uint4(bm + pfx[rd][1][0], bm + pfx[rd][1][1],
+                                                                              bm + pfx[rd][1][2], bm + pfx[rd][1][3]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- phase 3: sliding (min,max) over pow2 groups by doubling -----------------------
+            const uint4 *Mp = G0;
+            if (shw > 0 && ktrim > 0) {
+                uint4 *src = G0, *dst = G1;
+                for (int s = 1; s < pow2; s <<= 1) {
+#pragma unroll
+                    for (int rd = 0; rd < 2; ++rd) {
+                        const int xg = tid + rd * kFT;
+                        if (xg < NXG) {
+                            uint4 a = src[xg];
+                            if (xg + s < NXG) {
+                                const uint4 b = src[xg + s];
+                                a.x = min(a.x, b.x); a.y = max(a.y, b.y);
+                                a.z = min(a.z, b.z); a.w = max(a.w, b.w);
+                            }
+                            dst[xg] = a;
+                        }
+                    }
+                    __syncthreads();
+                    uint4 *t = src; src = dst; dst = t;
+                }
+                Mp = src;
+            }
+
+            // ---- phase 4: expected counts, strand combine, p-value (c-space, 4 per thread) ----
+            const int c0 = tid << 2;
+            const bool active = c0 < NC;
+            int r = 0;
+            long long F0 = 0, T0 = 0, ivlen = 0, rfa = 0, rfb = 0;
+            unsigned vmask = 0;   // elements that are computed positions
+            unsigned omask = 0;   // elements that are outputs of this region
+            double zv[4] = {0.0, 0.0, 0.0, 0.0};
+            if (active) {
+                r = fregion_of(R->cblk, nreg, c0);
+                const int cb = R->cb[r], cn = R->cn[r];
+                F0 = R->F0[r]; T0 = R->T0[r]; ivlen = R->len[r]; rfa = R->fa[r]; rfb = R->fb[r];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = c0 + e;
+                    if (c >= cb && c < cb + cn) {
+                        vmask |= 1u << e;
+                        const long long f = F0 + c;
+                        if (f >= rfa && f < rfb) omask |= 1u << e;
+                    }
+                }
+            }
+            if (vmask) {
+                const int x0 = c0 + R->D[r];
+                const long long g0 = x0 + R->G0[r];  // track coordinate of element 0 (plus strand)
+                // -- k-mer windows: 13 consecutive k-mers starting at base g0-8 serve both strands
+                unsigned long long kw = 0;  // 2-bit codes of bases g0-8 .. g0+9
+                unsigned nw = 0;            // N bits of the same 18 bases
+                if (!P.uniform) {
+                    const long long b0 = g0 - 8;
+                    if (b0 >= 0 && b0 + 18 <= P.n_track) {
+                        const long long nw2 = (P.n_track + 15) >> 4;
+                        const long long w = b0 >> 4;
+                        const int sh = (int)(b0 & 15) * 2;
+                        const unsigned q0 = __ldg(P.seq2 + w);
+                        const unsigned q1 = (w + 1 < nw2) ? __ldg(P.seq2 + w + 1) : 0u;
+                        const unsigned q2 = (w + 2 < nw2) ? __ldg(P.seq2 + w + 2) : 0u;
+                        const unsigned lo32 = __funnelshift_r(q0, q1, sh);
+                        const unsigned hi32 = __funnelshift_r(q1, q2, sh);
+                        kw = ((unsigned long long)hi32 << 32) | lo32;
+                        nw = ffetch_bits(P.nmask, (P.n_track + 31) >> 5, b0, 18);
+                    } else {
+                        const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
+                        for (int j = 0; j < 18; ++j) {
+                            const long long q = b0 + j;
+                            if (q >= 0 && q < P.n_track) {
+                                kw |= (unsigned long long)ffetch_bits(P.seq2, nw2, 2 * q, 2) << (2 * j);
+                                nw |= ffetch_bits(P.nmask, nwm, q, 1) << j;
+                            } else {
+                                nw |= 1u << j;
+                            }
+                        }
+                    }
+                }
+                double ev[2][4];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    // -- propensities P[m], m = 0..12: plus strand position g0-5+m, minus g0-6+m
+                    double Pv[13];
+#pragma unroll
+                    for (int m = 0; m < 13; ++m) {
+                        double v = 1.0;
+                        if (!P.uniform) {
+                            const unsigned km = (unsigned)(kw >> (2 * m)) & 0xFFFu;
+                            const bool isn = ((nw >> m) & 0x3Fu) != 0;
+                            v = tab[s ? frevcomp12(km) : km];
+                            if (isn) v = P.dflt;
+                        }
+                        Pv[m] = v;
+                    }
+                    // -- pairwise window sums of 2*HW = 10 propensities for the 4 elements
+                    double wp[4];
+                    {
+                        double s2[12], s4[8];
+#pragma unroll
+                        for (int m = 0; m < 12; ++m) s2[m] = Pv[m] + Pv[m + 1];
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) s4[m] = s2[m] + s2[m + 2];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) wp[e] = (s4[e] + s4[e + 4]) + s2[e + 8];
+                    }
+                    // -- smoothed window count (exact integers)
+                    const uint32_t *wcs = s ? wcm : wcp;
+                    const int i0 = x0 - s;  // slot of element 0 on this strand
+                    unsigned T[4];
+                    if (shw == 0) {
+                        lds4_unaligned(wcs, i0, T);
+                    } else {
+                        const uint32_t *prs = s ? prm : prp;
+                        unsigned up[4], dn[4];
+                        lds4_unaligned(prs, i0 + shw, up);
+                        lds4_unaligned(prs, i0 - shw - 1, dn);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) T[e] = up[e] - dn[e];
+                        if (ktrim > 0) {
+                            const int a0 = i0 - shw, e0 = i0 + shw;     // first / last slot of element 0's window
+                            const int ga = a0 >> 2, ka = a0 & 3;        // element e starts at v[ka+e]
+                            const int ge = e0 >> 2, ke = e0 & 3;        // element e ends at u[ke+e]
+                            unsigned va[4], vb[4], ua[4], ub[4];
+                            lds4(wcs + (ga << 2), va);
+                            lds4(wcs + (ga << 2) + 4, vb);
+                            lds4(wcs + (ge << 2), ua);
+                            lds4(wcs + (ge << 2) + 4, ub);
+                            // suffix (to the end of its own group) and prefix (from the start) extrema
+                            unsigned smn[8], smx[8], pmn[8], pmx[8];
+                            smn[3] = smx[3] = va[3];
+                            smn[2] = min(va[2], smn[3]); smx[2] = max(va[2], smx[3]);
+                            smn[1] = min(va[1], smn[2]); smx[1] = max(va[1], smx[2]);
+                            smn[0] = min(va[0], smn[1]); smx[0] = max(va[0], smx[1]);
+                            smn[7] = smx[7] = vb[3];
+                            smn[6] = min(vb[2], smn[7]); smx[6] = max(vb[2], smx[7]);
+                            smn[5] = min(vb[1], smn[6]); smx[5] = max(vb[1], smx[6]);
+                            smn[4] = min(vb[0], smn[5]); smx[4] = max(vb[0], smx[5]);
+                            pmn[0] = pmx[0] = ua[0];
+                            pmn[1] = min(ua[1], pmn[0]); pmx[1] = max(ua[1], pmx[0]);
+                            pmn[2] = min(ua[2], pmn[1]); pmx[2] = max(ua[2], pmx[1]);
+                            pmn[3] = min(ua[3], pmn[2]); pmx[3] = max(ua[3], pmx[2]);
+                            pmn[4] = pmx[4] = ub[0];
+                            pmn[5] = min(ub[1], pmn[4]); pmx[5] = max(ub[1], pmx[4]);
+                            pmn[6] = min(ub[2], pmn[5]); pmx[6] = max(ub[2], pmx[5]);
+                            pmn[7] = min(ub[3], pmn[6]); pmx[7] = max(ub[3], pmx[6]);
+                            // group extrema over the full groups in between: two overlapping pow2 runs
+                            const uint2 *M2 = reinterpret_cast<const uint2 *>(Mp) + s;  // (min,max) of strand s
+                            const uint2 m_lo0 = M2[2 * (ga + 1)], m_lo1 = M2[2 * (ga + 2)];
+                            const uint2 m_hi0 = M2[2 * (ge - pow2)], m_hi1 = M2[2 * (ge + 1 - pow2)];
+                            unsigned a_mn[4], a_mx[4], b_mn[4], b_mx[4];
+                            pick4(smn, ka, a_mn); pick4(smx, ka, a_mx);
+                            pick4(pmn, ke, b_mn); pick4(pmx, ke, b_mx);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const uint2 ml = (ka + e >= 4) ? m_lo1 : m_lo0;
+                                const uint2 mh = (ke + e >= 4) ? m_hi1 : m_hi0;
+                                const unsigned mn = min(min(a_mn[e], b_mn[e]), min(ml.x, mh.x));
+                                const unsigned mx = max(max(a_mx[e], b_mx[e]), max(ml.y, mh.y));
+                                const unsigned sum = T[e];
+                                // OS1==OS2 with nothing above (smoothing.h:59-70 never reaches the
+                                // second weight): all but one copy of the minimum equal the maximum
+                                const bool quirk =
+                                    (unsigned long long)(sum - mn) == (unsigned long long)(wsm - 1) * (unsigned long long)mx;
+                                T[e] = quirk ? (sum - mn) : (sum - mn - mx);
+                            }
+                        }
+                    }
+                    // -- expected count: fast evaluation + guard band, exact replica inside the band
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double den = wp[e] * dW;
+                        const double v = (Pv[e + 5] * (double)T[e]) * fast_rcp(den);
+                        const double rr = rint(v);
+                        const double dist = fabs(v - rr);
+                        const double av = fabs(v);
+                        double res = rr;
+                        const bool sure = (av < 4.0e15) && (dist < 0.5 - 4e-12 * (av + 1.0)) && (den > 1e-280) && (den < 1e280);
+                        if (!sure && ((vmask >> e) & 1u))
+                            res = fexpected_exact(P, tab, wcs, HW, shw, ktrim, g0 + e - s, i0 + e, s);
+                        ev[s][e] = res;
+                    }
+                }
+                // -- strand combine (cli/detect.py:121-122): plus[t+1] + minus[t]
+                unsigned cpv[4], cmv[4];
+                lds4(cp + x0, cpv);
+                lds4_unaligned(cm, x0 - 1, cmv);
+                double exv[4], obv[4], pvv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double ex = __dadd_rn(ev[0][e], ev[1][e]);
+                    const double ob = (double)((unsigned long long)cpv[e] + (unsigned long long)cmv[e]);
+                    exv[e] = ex; obv[e] = ob;
+                    double pv = 1.0, z = 0.0;
+                    if (want_p && ((vmask >> e) & 1u)) {
+                        if (ex < (double)P.lut_e && ob < (double)P.lut_o) {
+                            const double2 e2 = __ldg(P.lut + (size_t)((int)ex) * P.lut_o + (int)ob);
+                            pv = e2.x; z = e2.y;
+                        } else {
+                            const double rr = fit_r(dmp + 9, ex), mu = fit_mu(dmp, ex);
+                            const int kobs = ob < 2147483646.0 ? (int)ob : 2147483646;
+                            pv = nb_cdf(kobs, nb_prob(rr, mu), rr);
+                            z = ndtri_fn(1.0 - pv);
+                        }
+                    }
+                    pvv[e] = pv; zv[e] = z;
+                    if (P.hist && ((omask >> e) & 1u) && ex < (double)P.hist_d0 && ob < (double)P.hist_d1)
+                        atomicAdd(P.hist + (size_t)((int)ex) * P.hist_d1 + (int)ob, 1ULL);
+                }
+                // -- stores: one 256-bit store per array when the whole group is output
+                const long long f0 = F0 + c0;
+                if (omask == 0xFu && P.vec_ok) {
+                    if (P.exp_out) st256(P.exp_out + f0, exv[0], exv[1], exv[2], exv[3]);
+                    if (P.obs_out) st256(P.obs_out + f0, obv[0], obv[1], obv[2], obv[3]);
+                    if (P.pval_out) st256(P.pval_out + f0, pvv[0], pvv[1], pvv[2], pvv[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((omask >> e) & 1u) {
+                            if (P.exp_out) P.exp_out[f0 + e] = exv[e];
+                            if (P.obs_out) P.obs_out[f0 + e] = obv[e];
+                            if (P.pval_out) P.pval_out[f0 + e] = pvv[e];
+                        }
+                }
+            }
+            if (!want_z) { __syncthreads(); continue; }
+            if (active) {
+                zA[tid] = make_double2(zv[0], zv[1]);
+                zB[tid] = make_double2(zv[2], zv[3]);
+            }
+            __syncthreads();
+
+            // ---- phase 5: Stouffer windows at every requested half-width (windowing.h:53-84) ---
+            if (omask) {
+                double z[20];  // z[8 + e] is element e
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const double2 a = zA[tid - 2 + q], b = zB[tid - 2 + q];
+                    z[4 * q] = a.x; z[4 * q + 1] = a.y; z[4 * q + 2] = b.x; z[4 * q + 3] = b.y;
+                }
+                const long long f0 = F0 + c0;
+                const long long t0 = T0 + c0;
+                double acc[4] = {z[8], z[9], z[10], z[11]};
+#pragma unroll
+                for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
+                    if (h > WH) break;
+                    if (h > 0) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
+                    }
+                    if (!((P.scale_mask >> h) & 1u)) continue;
+                    const double cneg = -P.inv_sqrt_k[h];
+                    double res[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const long long t = t0 + e;
+                        res[e] = (t >= h && t < ivlen - h) ? ndtr_fast(acc[e] * cneg) : 1.0;
+                    }
+                    for (int s = 0; s < P.n_scales; ++s) {
+                        if (P.whw[s] != h) continue;
+                        double *dst = P.winp_out + (size_t)s * P.total + f0;
+                        if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) {
+                            st256(dst, res[0], res[1], res[2], res[3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if ((omask >> e) & 1u) dst[e] = res[e];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+
+size_t score_fast_smem_bytes() {
+    size_t b = 4096 * sizeof(double);
+    b += (size_t)(2 * (kXCap + 2 * kXPad) + 4 * (kXCap + kXPad)) * sizeof(uint32_t);
+    b += (size_t)2 * kNG * sizeof(uint4);
+    b += (size_t)2 * (kCCap / 4 + 2 * kZPad) * sizeof(double2);
+    b += sizeof(double) * kModelDoubles + sizeof(FastRegions) + 64;
+    return b;
+}
+
+cudaError_t score_fast_prepare(size_t smem) {
+    return cudaFuncSetAttribute(score_fast_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+int score_fast_blocks_per_sm(size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_fast_kernel<5>, kFT, smem) != cudaSuccess) return 0;
+    return n;
+}
+
+cudaError_t launch_score_fast(cudaStream_t st, const ScoreParams &p, int grid) {
+    score_fast_kernel<5><<<grid, kFT, score_fast_smem_bytes(), st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace fpt

@@ -20,6 +20,13 @@ constexpr int kMaxHalfWin = 16;                   // half_win_width limit
 constexpr int kMaxSmoothHalfWin = 100;            // smoothing_half_win_width limit
 constexpr int kMaxScaleHalfWin = 32;              // Stouffer half-width limit
 
+// Throughput kernel (fpt_fast.cu): one CTA = kFastThreads threads, 4 consecutive positions each.
+constexpr int kFastThreads = 256;
+constexpr int kFastCCap = 4 * kFastThreads;       // computed positions per sub-tile
+constexpr int kFastXCap = 8 * kFastThreads;       // staged slots per sub-tile
+constexpr int kFastHalfWin = 5;                   // half_win_width it is instantiated for
+constexpr int kFastMaxScaleHalfWin = 8;           // Stouffer half-width limit of the fast kernel
+
 struct ScoreParams {
     const uint32_t *seq2, *nmask, *cuts_p, *cuts_m;
     long long n_track;
@@ -46,6 +53,11 @@ struct ScoreParams {
     unsigned int max_cut;
     int *status;
     int p_cap;  // capacity of each bias-propensity staging array
+    // fast kernel only
+    int vec_ok;            // exp/obs/pval output pointers are 32-byte aligned
+    unsigned winp_vec;     // bit s: row s of winp_out is 32-byte aligned
+    unsigned scale_mask;   // bit h: some scale has half-width h
+    double inv_sqrt_k[kFastMaxScaleHalfWin + 1];  // 1/sqrt(2h+1)
 };
 
 size_t score_smem_bytes(int hw, bool uniform);
@@ -54,6 +66,11 @@ cudaError_t launch_plan(cudaStream_t st, const long long *out_off, long long n_i
 cudaError_t launch_score(cudaStream_t st, const ScoreParams &p, int grid);
 cudaError_t score_kernel_prepare(size_t smem);
 int score_kernel_blocks_per_sm(size_t smem);
+
+size_t score_fast_smem_bytes();
+cudaError_t score_fast_prepare(size_t smem);
+int score_fast_blocks_per_sm(size_t smem);
+cudaError_t launch_score_fast(cudaStream_t st, const ScoreParams &p, int grid);
 
 cudaError_t launch_lut_build(cudaStream_t st, const double *dm, double2 *lut, int lut_e, int lut_o);
 cudaError_t launch_nb_values(cudaStream_t st, const double *dm, const double *e, const double *o, long long n,

@@ -1,5 +1,5 @@
 """Device FP64 special functions (csrc/fpt_math.cuh) vs the oracle. Tolerance: 1e-9 relative plus
-the 4.4e-16 floor (they may differ from glibc/no-FMA by a few ulp; never more)."""
+the absolute floor of tests/parity.py (they may differ from glibc/no-FMA by a few ulp; never more)."""
 import numpy as np
 import pytest
 
