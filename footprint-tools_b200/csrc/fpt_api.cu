@@ -330,10 +330,9 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
         auto al32 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
         p.vec_ok = al32(a->exp_out) && al32(a->obs_out) && al32(a->pval_out);
         p.winp_vec = 0;
-        p.scale_mask = 0;
         for (int s = 0; s < p.n_scales; ++s) {
             if (al32(a->winp_out + (size_t)s * (size_t)a->total)) p.winp_vec |= 1u << s;
-            p.scale_mask |= 1u << p.whw[s];
+            p.h_rows[p.whw[s]] |= 1u << s;
         }
         for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) p.inv_sqrt_k[h] = 1.0 / std::sqrt((double)(2 * h + 1));
     }

@@ -67,22 +67,6 @@ struct FastRegions {
     unsigned wtot[2][2][kFT / 32];
 };
 
-// ---- constant tables of the normal tail (hcephes/src/cprob/ndtr.c:4-32) ----------------------
-__constant__ double kErfcP[9] = {2.46196981473530512524E-10, 5.64189564831068821977E-1, 7.46321056442269912687E0,
-                                 4.86371970985681366614E1,   1.96520832956077098242E2,  5.26445194995477358631E2,
-                                 9.34528527171957607540E2,   1.02755188689515710272E3,  5.57535335369399327526E2};
-__constant__ double kErfcQ[8] = {1.32281951154744992508E1, 8.67072140885989742329E1, 3.54937778887819891062E2,
-                                 9.75708501743205489753E2, 1.82390916687909736289E3, 2.24633760818710981792E3,
-                                 1.65666309194161350182E3, 5.57535340817727675546E2};
-__constant__ double kErfcR[6] = {5.64189583547755073984E-1, 1.27536670759978104416E0, 5.01905042251180477414E0,
-                                 6.16021097993053585195E0,  7.40974269950448939160E0, 2.97886665372100240670E0};
-__constant__ double kErfcS[6] = {2.26052863220117276590E0, 9.39603524938001434673E0, 1.20489539808096656605E1,
-                                 1.70814450747565897222E1, 9.60896809063285878198E0, 3.36907645100081516050E0};
-__constant__ double kErfT[5] = {9.60497373987051638749E0, 9.00260197203842689217E1, 2.23200534594684319226E3,
-                                7.00332514112805075473E3, 5.55923013010394962768E4};
-__constant__ double kErfU[5] = {3.35617141647503099647E1, 5.21357949780152679795E2, 4.59432382970980127987E3,
-                                2.26290000613890934246E4, 4.92673942608635921086E4};
-
 template <int N>
 __device__ __forceinline__ double cpoly(double x, const double *c) {
     double a = c[0];
@@ -109,36 +93,49 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return r;
 }
 
-// Lower-tail normal probability of a (hcephes_ndtr, ndtr.c:34-59) with the same rationals; the
-// reference's exp(-a^2) split + sqrt (expx2.c, ndtr.c:52-53) is replaced by one exp(-a^2/2) whose
-// argument carries the rounding error of the square (relative error of the result < 1e-15).
-// Infinite arguments give NaN as in the reference (erfce(inf) = inf/inf, ndtr.c:65-76).
-__device__ __forceinline__ double ndtr_fast(double a) {
-    const double x = a * kSqrtH;
-    const double z = fabs(x);
-    double y;
-    if (z < 1.0) {
-        const double zz = x * x;
-        y = fma(0.5 * x, cpoly<5>(zz, kErfT) * fast_rcp(cpoly1<5>(zz, kErfU)), 0.5);
-    } else {
-        double num, den;
-        if (z < 8.0) {
-            num = cpoly<9>(z, kErfcP);
-            den = cpoly1<8>(z, kErfcQ);
-        } else {
-            num = cpoly<6>(z, kErfcR);
-            den = cpoly1<6>(z, kErfcS);
-        }
-        // exp(-z^2) with z^2 = s + e (s rounded, e the exact remainder): exp(-s) * (1 - e)
-        const double s = z * z;
-        const double e = fma(z, z, -s);
-        double ex = exp(-s);
-        ex = fma(-e, ex, ex);
-        y = 0.5 * num * fast_rcp(den) * ex;
-        if (!(z < 1e300)) y = CUDART_NAN;  // +-inf and NaN
-        if (x > 0) y = 1.0 - y;
+// ---- normal lower tail for the Stouffer windows ------------------------------------------------
+// ndtr(a) = Phi(a) (reference: hcephes_ndtr, ndtr.c:34-59). For |a| < 26 it is evaluated as
+//   Q(t) = exp(-t^2/2) * F(u),  t = |a|,  u = (t - 5)/(t + 5),  F = 0.5*erfcx(t/sqrt 2)
+// with F a degree-16 polynomial (Chebyshev fit generated by tools/fit_ndtr.py against mpmath; max
+// relative error of Q over [0, 26]: 3.5e-13, i.e. < 2e-13 on -log10 p — the bar is 1e-9) and a
+// table-free exp (Cody-Waite reduction + degree-11 Taylor polynomial, |r| <= ln2/2). One branch-free
+// path for every lane instead of Cephes' three ranges. |a| >= 26 (p < 1e-149), infinities and NaN
+// go to the branch-for-branch Cephes replica ndtr_fn (fpt_math.cuh), which also reproduces the
+// reference's denormal exp(-a^2) behaviour above |a| = 26.6 and its NaN for infinite arguments.
+__constant__ double kNdF[17] = {8.34755278698498880e-08,  1.85387184289488118e-07,  -7.05646170130192722e-07,
+                                -1.23208123023565909e-06, 6.67121890420153935e-06,  9.47978503161857321e-07,
+                                -6.04384263432253854e-05, 1.34279562238030851e-04,  2.19553084872871904e-04,
+                                -2.37884470097069183e-03, 8.99137029253909911e-03,  -2.34139004594596037e-02,
+                                4.78553522966640513e-02,  -8.08838772654492111e-02, 1.16068811885835940e-01,
+                                -1.43457555263989955e-01, 7.69193049750059588e-02};
+__constant__ double kExpT[12] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
+                                 1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,           1.0,          1.0};
+
+__device__ __noinline__ double ndtr_slow(double a) { return ndtr_fn(a); }
+
+__device__ __forceinline__ double ndtr_tail(double a) {
+    const double t = fabs(a);
+    if (!(t < 26.0)) return ndtr_slow(a);
+    double r;
+    {
+        const double d = t + 5.0;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+        const double e = fma(-d, r, 1.0);
+        r = fma(r, e, r);  // 1/(t+5), relative error ~1e-14
     }
-    return y;
+    const double u = fma(-10.0, r, 1.0);
+    const double F = cpoly<17>(u, kNdF);
+    // exp(-t^2/2)
+    const double y = -0.5 * (t * t);
+    const double kf = fma(y, 1.4426950408889634, 6755399441055744.0);
+    const int n = __double2loint(kf);
+    const double nf = kf - 6755399441055744.0;
+    double q = fma(nf, -6.93147180369123816490e-01, y);
+    q = fma(nf, -1.90821492927058770002e-10, q);
+    const double pe = cpoly<12>(q, kExpT);
+    const double E = __hiloint2double(__double2hiint(pe) + (n << 20), __double2loint(pe));
+    const double tail = E * F;
+    return a > 0.0 ? 1.0 - tail : tail;
 }
 
 __device__ __forceinline__ int fregion_of(const int *bases, int nreg, int v) {
@@ -256,7 +253,14 @@ __device__ __noinline__ double ftrimmed_mean_exact(const uint32_t *wc, int i0, i
 
 // propensity of the k-mer whose first base is track coordinate q (6 bases), forward or
 // reverse-complemented; any base outside the track or not ACGT gives the default
-__device__ __noinline__ double fkmer_prop(const ScoreParams &P, const double *tab, long long q, int rc) {
+struct SeqView {  // passed by value to the exact path (a reference to the kernel parameters would force a stack copy)
+    const uint32_t *seq2, *nmask;
+    long long n_track;
+    double dflt;
+    int uniform;
+};
+
+__device__ __noinline__ double fkmer_prop(SeqView P, const double *tab, long long q, int rc) {
     if (P.uniform) return 1.0;
     if (q < 0 || q + 6 > P.n_track) return P.dflt;
     const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
@@ -269,7 +273,7 @@ __device__ __noinline__ double fkmer_prop(const ScoreParams &P, const double *ta
 // The reference's own operation order for one strand position (predict.h:41-63): sequential window
 // of propensities, IEEE divide, smoothed count, multiply, round half away from zero.
 //   strand 0: position j uses k-mers starting at j-3; strand 1: reverse complement of j-2
-__device__ __noinline__ double fexpected_exact(const ScoreParams &P, const double *tab, const uint32_t *wc, int hw,
+__device__ __noinline__ double fexpected_exact(SeqView P, const double *tab, const uint32_t *wc, int hw,
                                                int shw, int ktrim, long long j, int slot, int strand) {
     const int off = strand ? 2 : 3;
     double wp = 0.0;
@@ -288,6 +292,115 @@ __device__ __noinline__ double fexpected_exact(const ScoreParams &P, const doubl
     return round(__dmul_rn(ratio, sm));
 }
 
+// Region table of one sub-tile, built by warp 0 (lane l <-> interval k + l) for the sub-tile that
+// starts at flat index `cur` of tile [.., hi).
+__device__ __forceinline__ void build_regions(const ScoreParams &P, FastRegions *R, long long cur, long long hi,
+                                              long long k, int lane, int WH, int PADX, int PADR) {
+    const long long kk = k + lane;
+    const bool valid = lane < kFReg && kk < P.n_iv;
+    long long o0 = 0, o1 = 0, st = 0;
+    if (valid) {
+        o0 = __ldg(P.out_off + kk);
+        o1 = __ldg(P.out_off + kk + 1);
+        st = __ldg(P.iv_start + kk);
+    }
+    long long fa = o0 > cur ? o0 : cur;
+    long long fb = o1 < hi ? o1 : hi;
+    bool has = valid && fa < fb;
+    const long long len = o1 - o0;
+    long long ta = fa - o0 - WH; if (ta < 0) ta = 0;
+    long long tb = fb - o0 + WH; if (tb > len) tb = len;
+    int cn = has ? (int)(tb - ta) : 0;
+    const int lead = (int)((o0 + ta) & 3);
+    int cspan = has ? ((lead + cn + 3) & ~3) : 0;
+    int xspan = has ? cspan + PADX + PADR : 0;
+    int cs = cspan, xs = xspan;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int a = __shfl_up_sync(0xffffffffu, cs, d);
+        int b = __shfl_up_sync(0xffffffffu, xs, d);
+        if (lane >= d) { cs += a; xs += b; }
+    }
+    const bool over = has && (cs > kCCap || xs > kXCap);
+    const unsigned overmask = __ballot_sync(0xffffffffu, over);
+    const int first_over = overmask ? (__ffs(overmask) - 1) : 32;
+    const int cex = cs - cspan, xex = xs - xspan;
+    if (lane == first_over) {
+        int avail = kCCap - cex;
+        const int ax = kXCap - xex - PADX - PADR;
+        if (ax < avail) avail = ax;
+        avail &= ~3;
+        const int cn2 = avail - lead;
+        const long long fb2 = o0 + ta + cn2 - WH;
+        if (cn2 > 0 && fb2 > fa) {
+            fb = fb2; tb = ta + cn2; cn = cn2; cspan = avail; xspan = cspan + PADX + PADR;
+        } else {
+            has = false;
+        }
+    }
+    if (lane > first_over) has = false;
+    const unsigned incl = __ballot_sync(0xffffffffu, has);
+    const int r = __popc(incl & ((1u << lane) - 1u));
+    const int nreg = __popc(incl);
+    if (has) {
+        const int cb = cex + lead;
+        const int D = (xex - cex) + PADX;
+        R->cblk[r] = cex; R->xblk[r] = xex;
+        R->cb[r] = cb; R->cn[r] = cn; R->D[r] = D;
+        R->G0[r] = st + ta - cb - D;
+        R->F0[r] = o0 + ta - cb;
+        R->T0[r] = ta - cb;
+        R->len[r] = len;
+        R->fa[r] = fa; R->fb[r] = fb;
+    }
+    const int last = incl ? (31 - __clz(incl)) : -1;
+    if (lane == (last < 0 ? 0 : last)) {
+        if (last < 0) {
+            R->nreg = 0;
+            R->cblk[0] = R->xblk[0] = 0;
+            const long long nk = k + kFReg;
+            R->next_k = nk < P.n_iv ? nk : P.n_iv;
+            R->next_cur = (nk >= P.n_iv) ? hi : cur;
+        } else {
+            R->nreg = nreg;
+            R->cblk[nreg] = cex + cspan;
+            R->xblk[nreg] = xex + xspan;
+            R->next_cur = fb;
+            R->next_k = (fb == o1) ? kk + 1 : kk;
+        }
+    }
+}
+
+// Stouffer p-values of 4 consecutive positions at one half-width (windowing.h:53-67 with the edge
+// rule of windowing.pyx:51-54) and their stores into every output row that asked for this width.
+__device__ __noinline__ void emit_scale(double a0, double a1, double a2, double a3, int h, double cneg, unsigned rows,
+                                        unsigned winp_vec, double *winp_out, long long total, long long t0,
+                                        long long ivlen, long long f0, unsigned omask) {
+    const long long tmax = ivlen - h;
+    double res[4];
+    res[0] = (t0 >= h && t0 < tmax) ? ndtr_tail(a0 * cneg) : 1.0;
+    res[1] = (t0 + 1 >= h && t0 + 1 < tmax) ? ndtr_tail(a1 * cneg) : 1.0;
+    res[2] = (t0 + 2 >= h && t0 + 2 < tmax) ? ndtr_tail(a2 * cneg) : 1.0;
+    res[3] = (t0 + 3 >= h && t0 + 3 < tmax) ? ndtr_tail(a3 * cneg) : 1.0;
+    for (unsigned m = rows; m; m &= m - 1) {
+        const int s = __ffs(m) - 1;
+        double *dst = winp_out + (size_t)s * total + f0;
+        if (omask == 0xFu && ((winp_vec >> s) & 1u)) {
+            st256(dst, res[0], res[1], res[2], res[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((omask >> e) & 1u) dst[e] = res[e];
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc, bool ok) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = ok ? 4 : 0;  // src-size 0: the 4 destination bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gsrc), "r"(n) : "memory");
+}
+
 template <int HW>
 __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P) {
     static_assert(HW >= 1 && HW <= 5, "slot loads cover [x0-8, x0+8)");
@@ -304,7 +417,7 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
     double2 *zA = reinterpret_cast<double2 *>(G1 + kNG) + kZPad;                     // z of c%4 in {0,1}
     double2 *zB = zA + kCCap / 4 + 2 * kZPad;                                        // z of c%4 in {2,3}
     double *dmp = reinterpret_cast<double *>(zB + kCCap / 4 + kZPad);                // 24
-    FastRegions *R = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);
+    FastRegions *Rbuf = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);        // double-buffered
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shw = P.shw, ktrim = P.ktrim;
@@ -322,7 +435,6 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
     for (int i = tid; i < kXPad; i += kFT) {  // slots read before/after the staged range
         cp[-1 - i] = 0; cm[-1 - i] = 0; cp[kXCap + i] = 0; cm[kXCap + i] = 0;
     }
-    __syncthreads();
 
     // smoothing-window group geometry (uniform): a window of wsm slots starting at slot a covers the
     // tail of group a>>2, nf full groups and the head of the last group; nf >= nfmin >= pow2
@@ -332,122 +444,58 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
         while (pow2 * 2 <= nfmin) pow2 *= 2;
     }
 
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const long long lo = tile * (long long)P.tile;
-        const long long hi = (lo + P.tile < P.total) ? lo + P.tile : P.total;
-        long long cur = lo;
-        long long k = P.tile_first_iv[tile];
-        while (cur < hi) {
-            // ---- region table (warp 0): lane l <-> interval k + l ----------------------------
-            if (warp == 0) {
-                const long long kk = k + lane;
-                const bool valid = lane < kFReg && kk < P.n_iv;
-                long long o0 = 0, o1 = 0, st = 0;
-                if (valid) {
-                    o0 = __ldg(P.out_off + kk);
-                    o1 = __ldg(P.out_off + kk + 1);
-                    st = __ldg(P.iv_start + kk);
-                }
-                long long fa = o0 > cur ? o0 : cur;
-                long long fb = o1 < hi ? o1 : hi;
-                bool has = valid && fa < fb;
-                const long long len = o1 - o0;
-                long long ta = fa - o0 - WH; if (ta < 0) ta = 0;
-                long long tb = fb - o0 + WH; if (tb > len) tb = len;
-                int cn = has ? (int)(tb - ta) : 0;
-                const int lead = (int)((o0 + ta) & 3);
-                int cspan = has ? ((lead + cn + 3) & ~3) : 0;
-                int xspan = has ? cspan + PADX + PADR : 0;
-                int cs = cspan, xs = xspan;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int a = __shfl_up_sync(0xffffffffu, cs, d);
-                    int b = __shfl_up_sync(0xffffffffu, xs, d);
-                    if (lane >= d) { cs += a; xs += b; }
-                }
-                const bool over = has && (cs > kCCap || xs > kXCap);
-                const unsigned overmask = __ballot_sync(0xffffffffu, over);
-                const int first_over = overmask ? (__ffs(overmask) - 1) : 32;
-                const int cex = cs - cspan, xex = xs - xspan;
-                if (lane == first_over) {
-                    int avail = kCCap - cex;
-                    const int ax = kXCap - xex - PADX - PADR;
-                    if (ax < avail) avail = ax;
-                    avail &= ~3;
-                    const int cn2 = avail - lead;
-                    const long long fb2 = o0 + ta + cn2 - WH;
-                    if (cn2 > 0 && fb2 > fa) {
-                        fb = fb2; tb = ta + cn2; cn = cn2; cspan = avail; xspan = cspan + PADX + PADR;
-                    } else {
-                        has = false;
-                    }
-                }
-                if (lane > first_over) has = false;
-                const unsigned incl = __ballot_sync(0xffffffffu, has);
-                const int r = __popc(incl & ((1u << lane) - 1u));
-                const int nreg = __popc(incl);
-                if (has) {
-                    const int cb = cex + lead;
-                    const int D = (xex - cex) + PADX;
-                    R->cblk[r] = cex; R->xblk[r] = xex;
-                    R->cb[r] = cb; R->cn[r] = cn; R->D[r] = D;
-                    R->G0[r] = st + ta - cb - D;
-                    R->F0[r] = o0 + ta - cb;
-                    R->T0[r] = ta - cb;
-                    R->len[r] = len;
-                    R->fa[r] = fa; R->fb[r] = fb;
-                }
-                const int last = incl ? (31 - __clz(incl)) : -1;
-                if (lane == (last < 0 ? 0 : last)) {
-                    if (last < 0) {
-                        R->nreg = 0;
-                        R->cblk[0] = R->xblk[0] = 0;
-                        const long long nk = k + kFReg;
-                        R->next_k = nk < P.n_iv ? nk : P.n_iv;
-                        R->next_cur = (nk >= P.n_iv) ? hi : cur;
-                    } else {
-                        R->nreg = nreg;
-                        R->cblk[nreg] = cex + cspan;
-                        R->xblk[nreg] = xex + xspan;
-                        R->next_cur = fb;
-                        R->next_k = (fb == o1) ? kk + 1 : kk;
-                    }
-                }
-            }
-            __syncthreads();
-            const int nreg = R->nreg;
-            cur = R->next_cur;
-            k = R->next_k;
-            if (nreg == 0) { __syncthreads(); continue; }
-            const int NX = R->xblk[nreg], NC = R->cblk[nreg];
-            const int NXG = NX >> 2;
+    // ---- sub-tile walk: (tile, cur, k) is the sub-tile being scored, its table is Rbuf[buf] ---
+    long long tile = blockIdx.x;
+    if (tile >= P.n_tiles) return;
+    long long hi = (tile + 1) * (long long)P.tile < P.total ? (tile + 1) * (long long)P.tile : P.total;
+    int buf = 0;
+    if (warp == 0)
+        build_regions(P, &Rbuf[0], tile * (long long)P.tile, hi, P.tile_first_iv[tile], lane, WH, PADX, PADR);
+    __syncthreads();
 
-            // ---- phase 1: stage cut counts, coalesced per region ------------------------------
-            {
-                bool bad = false;
-                for (int r = 0; r < nreg; ++r) {
-                    const int xe = R->xblk[r + 1];
-                    const long long g0 = R->G0[r];
-                    for (int x = R->xblk[r] + tid; x < xe; x += kFT) {
-                        const long long g = x + g0;
-                        unsigned a = 0, b = 0;
-                        if (g >= 0 && g < P.n_track) {
-                            a = __ldg(P.cuts_p + g);
-                            b = __ldg(P.cuts_m + g);
-                        }
-                        bad |= (a > P.max_cut) | (b > P.max_cut);
-                        cp[x] = a;
-                        cm[x] = b;
-                    }
-                }
-                if (bad) atomicOr(P.status, 1);
+    for (;;) {
+        FastRegions *R = &Rbuf[buf];
+        const int nreg = R->nreg;
+        // successor sub-tile
+        long long ncur = R->next_cur, nk = R->next_k, ntile = tile, nhi = hi;
+        if (ncur >= hi) {
+            ntile = tile + gridDim.x;
+            if (ntile < P.n_tiles) {
+                ncur = ntile * (long long)P.tile;
+                nhi = (ntile + 1) * (long long)P.tile < P.total ? (ntile + 1) * (long long)P.tile : P.total;
+                nk = P.tile_first_iv[ntile];
             }
-            __syncthreads();
+        }
+        const bool more = ntile < P.n_tiles;
+        const int NX = R->xblk[nreg], NC = R->cblk[nreg];
+        const int NXG = NX >> 2;
 
+        // ---- phase 1: stage cut counts (asynchronous copies, coalesced per region); warp 0 builds
+        //      the next sub-tile's region table while they are in flight -------------------------
+        for (int r = 0; r < nreg; ++r) {
+            const int xe = R->xblk[r + 1];
+            const long long g0 = R->G0[r];
+            const uint32_t *bp = P.cuts_p + g0, *bm = P.cuts_m + g0;
+            // slots whose track coordinate x + g0 lies inside [0, n_track)
+            const long long vlo = -g0, vhi = P.n_track - g0;
+            const int xlo = vlo < 0 ? 0 : (vlo > kXCap ? kXCap : (int)vlo);
+            const int xhi = vhi < 0 ? 0 : (vhi > kXCap ? kXCap : (int)vhi);
+            for (int x = R->xblk[r] + tid; x < xe; x += kFT) {
+                const bool ok = x >= xlo && x < xhi;
+                cp_async4(cp + x, ok ? bp + x : P.cuts_p, ok);
+                cp_async4(cm + x, ok ? bm + x : P.cuts_m, ok);
+            }
+        }
+        if (warp == 0 && more) build_regions(P, &Rbuf[buf ^ 1], ncur, nhi, nk, lane, WH, PADX, PADR);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+
+        if (nreg > 0) {
             // ---- phase 2: window sums, their block-wide prefix sums, group min/max ------------
             {
                 unsigned pfx[2][2][4];  // [round][strand][e]: thread-local inclusive prefix of wc
                 unsigned incl_w[2][2];  // warp-inclusive scan of the thread totals
+                bool bad = false;
 #pragma unroll
                 for (int rd = 0; rd < 2; ++rd) {
                     const int xg = tid + rd * kFT;
@@ -464,6 +512,7 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                                 lds4(src + x0 - 8 + 4 * q, t4);
                                 c[4 * q] = t4[0]; c[4 * q + 1] = t4[1]; c[4 * q + 2] = t4[2]; c[4 * q + 3] = t4[3];
                             }
+                            bad |= (max(max(c[8], c[9]), max(c[10], c[11])) > P.max_cut);
                             unsigned sum = 0;
 #pragma unroll
                             for (int j = 8 - HW; j < 8 + HW; ++j) sum += c[j];
@@ -495,6 +544,7 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                         incl_w[rd][s] = a;
                     }
                 }
+                if (bad) atomicOr(P.status, 1);
                 if (shw > 0) {
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -572,14 +622,15 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
             const int c0 = tid << 2;
             const bool active = c0 < NC;
             int r = 0;
-            long long F0 = 0, T0 = 0, ivlen = 0, rfa = 0, rfb = 0;
+            long long F0 = 0, T0 = 0, ivlen = 0;
             unsigned vmask = 0;   // elements that are computed positions
             unsigned omask = 0;   // elements that are outputs of this region
             double zv[4] = {0.0, 0.0, 0.0, 0.0};
             if (active) {
                 r = fregion_of(R->cblk, nreg, c0);
                 const int cb = R->cb[r], cn = R->cn[r];
-                F0 = R->F0[r]; T0 = R->T0[r]; ivlen = R->len[r]; rfa = R->fa[r]; rfb = R->fb[r];
+                F0 = R->F0[r]; T0 = R->T0[r]; ivlen = R->len[r];
+                const long long rfa = R->fa[r], rfb = R->fb[r];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int c = c0 + e;
@@ -593,8 +644,10 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
             if (vmask) {
                 const int x0 = c0 + R->D[r];
                 const long long g0 = x0 + R->G0[r];  // track coordinate of element 0 (plus strand)
-                // -- k-mer windows: 13 consecutive k-mers starting at base g0-8 serve both strands
+                // -- k-mer windows: the 13 k-mers starting at bases g0-8 .. g0+4 serve both strands:
+                //    plus-strand position g0-5+m and minus-strand position g0-6+m use k-mer m
                 unsigned long long kw = 0;  // 2-bit codes of bases g0-8 .. g0+9
+                unsigned long long rcw = 0; // reverse complement of the same 18 bases
                 unsigned nw = 0;            // N bits of the same 18 bases
                 if (!P.uniform) {
                     const long long b0 = g0 - 8;
@@ -607,7 +660,7 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                         const unsigned q2 = (w + 2 < nw2) ? __ldg(P.seq2 + w + 2) : 0u;
                         const unsigned lo32 = __funnelshift_r(q0, q1, sh);
                         const unsigned hi32 = __funnelshift_r(q1, q2, sh);
-                        kw = ((unsigned long long)hi32 << 32) | lo32;
+                        kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
                         nw = ffetch_bits(P.nmask, (P.n_track + 31) >> 5, b0, 18);
                     } else {
                         const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
@@ -621,22 +674,30 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                             }
                         }
                     }
+                    // reverse the order of the 18 fields, then complement (code ^ 3)
+                    unsigned long long t = __brevll(kw) >> 28;
+                    t = ((t & 0xAAAAAAAAAull) >> 1) | ((t & 0x555555555ull) << 1);
+                    rcw = t ^ 0xFFFFFFFFFull;
                 }
                 double ev[2][4];
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
-                    // -- propensities P[m], m = 0..12: plus strand position g0-5+m, minus g0-6+m
+                    // -- propensities Pv[m] of k-mer m on this strand
                     double Pv[13];
+                    if (P.uniform) {
 #pragma unroll
-                    for (int m = 0; m < 13; ++m) {
-                        double v = 1.0;
-                        if (!P.uniform) {
-                            const unsigned km = (unsigned)(kw >> (2 * m)) & 0xFFFu;
-                            const bool isn = ((nw >> m) & 0x3Fu) != 0;
-                            v = tab[s ? frevcomp12(km) : km];
-                            if (isn) v = P.dflt;
+                        for (int m = 0; m < 13; ++m) Pv[m] = 1.0;
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < 13; ++m) {
+                            const unsigned km = s ? (unsigned)(rcw >> (24 - 2 * m)) & 0xFFFu : (unsigned)(kw >> (2 * m)) & 0xFFFu;
+                            Pv[m] = tab[km];
                         }
-                        Pv[m] = v;
+                        if (nw != 0) {
+#pragma unroll
+                            for (int m = 0; m < 13; ++m)
+                                if ((nw >> m) & 0x3Fu) Pv[m] = P.dflt;
+                        }
                     }
                     // -- pairwise window sums of 2*HW = 10 propensities for the 4 elements
                     double wp[4];
@@ -712,17 +773,17 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                         }
                     }
                     // -- expected count: fast evaluation + guard band, exact replica inside the band
+                    //    (a non-finite or huge v fails the first comparison and takes the exact path)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const double den = wp[e] * dW;
-                        const double v = (Pv[e + 5] * (double)T[e]) * fast_rcp(den);
+                        const double v = (Pv[e + 5] * (double)T[e]) * fast_rcp(wp[e] * dW);
                         const double rr = rint(v);
-                        const double dist = fabs(v - rr);
                         const double av = fabs(v);
                         double res = rr;
-                        const bool sure = (av < 4.0e15) && (dist < 0.5 - 4e-12 * (av + 1.0)) && (den > 1e-280) && (den < 1e280);
+                        const bool sure = (av < 4.0e15) && (fabs(v - rr) < fma(av, -4e-12, 0.5 - 4e-12));
                         if (!sure && ((vmask >> e) & 1u))
-                            res = fexpected_exact(P, tab, wcs, HW, shw, ktrim, g0 + e - s, i0 + e, s);
+                            res = fexpected_exact(SeqView{P.seq2, P.nmask, P.n_track, P.dflt, P.uniform}, tab, wcs, HW, shw, ktrim,
+                                                  g0 + e - s, i0 + e, s);
                         ev[s][e] = res;
                     }
                 }
@@ -734,12 +795,13 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const double ex = __dadd_rn(ev[0][e], ev[1][e]);
-                    const double ob = (double)((unsigned long long)cpv[e] + (unsigned long long)cmv[e]);
+                    const unsigned long long obi = (unsigned long long)cpv[e] + (unsigned long long)cmv[e];
+                    const double ob = (double)obi;
                     exv[e] = ex; obv[e] = ob;
                     double pv = 1.0, z = 0.0;
                     if (want_p && ((vmask >> e) & 1u)) {
                         if (ex < (double)P.lut_e && ob < (double)P.lut_o) {
-                            const double2 e2 = __ldg(P.lut + (size_t)((int)ex) * P.lut_o + (int)ob);
+                            const double2 e2 = __ldg(P.lut + (unsigned)((int)ex * P.lut_o + (int)obi));
                             pv = e2.x; z = e2.y;
                         } else {
                             const double rr = fit_r(dmp + 9, ex), mu = fit_mu(dmp, ex);
@@ -768,54 +830,42 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                         }
                 }
             }
-            if (!want_z) { __syncthreads(); continue; }
-            if (active) {
-                zA[tid] = make_double2(zv[0], zv[1]);
-                zB[tid] = make_double2(zv[2], zv[3]);
-            }
-            __syncthreads();
+            if (want_z) {
+                if (active) {
+                    zA[tid] = make_double2(zv[0], zv[1]);
+                    zB[tid] = make_double2(zv[2], zv[3]);
+                }
+                __syncthreads();
 
-            // ---- phase 5: Stouffer windows at every requested half-width (windowing.h:53-84) ---
-            if (omask) {
-                double z[20];  // z[8 + e] is element e
+                // ---- phase 5: Stouffer windows at every requested half-width ---------------------
+                if (omask) {
+                    double z[20];  // z[8 + e] is element e
 #pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const double2 a = zA[tid - 2 + q], b = zB[tid - 2 + q];
-                    z[4 * q] = a.x; z[4 * q + 1] = a.y; z[4 * q + 2] = b.x; z[4 * q + 3] = b.y;
-                }
-                const long long f0 = F0 + c0;
-                const long long t0 = T0 + c0;
-                double acc[4] = {z[8], z[9], z[10], z[11]};
-#pragma unroll
-                for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
-                    if (h > WH) break;
-                    if (h > 0) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
+                    for (int q = 0; q < 5; ++q) {
+                        const double2 a = zA[tid - 2 + q], b = zB[tid - 2 + q];
+                        z[4 * q] = a.x; z[4 * q + 1] = a.y; z[4 * q + 2] = b.x; z[4 * q + 3] = b.y;
                     }
-                    if (!((P.scale_mask >> h) & 1u)) continue;
-                    const double cneg = -P.inv_sqrt_k[h];
-                    double res[4];
+                    const long long f0 = F0 + c0;
+                    const long long t0 = T0 + c0;
+                    double acc[4] = {z[8], z[9], z[10], z[11]};
+                    // sums grow outward from the centre: S_h = S_{h-1} + z[-h] + z[+h]
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const long long t = t0 + e;
-                        res[e] = (t >= h && t < ivlen - h) ? ndtr_fast(acc[e] * cneg) : 1.0;
-                    }
-                    for (int s = 0; s < P.n_scales; ++s) {
-                        if (P.whw[s] != h) continue;
-                        double *dst = P.winp_out + (size_t)s * P.total + f0;
-                        if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) {
-                            st256(dst, res[0], res[1], res[2], res[3]);
-                        } else {
+                    for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
+                        if (h > WH) break;
+                        if (h > 0) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if ((omask >> e) & 1u) dst[e] = res[e];
+                            for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
                         }
+                        if (P.h_rows[h])
+                            emit_scale(acc[0], acc[1], acc[2], acc[3], h, -P.inv_sqrt_k[h], P.h_rows[h], P.winp_vec, P.winp_out,
+                                       P.total, t0, ivlen, f0, omask);
                     }
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
+        if (!more) break;
+        tile = ntile; hi = nhi; buf ^= 1;
     }
 }
 
@@ -826,7 +876,7 @@ size_t score_fast_smem_bytes() {
     b += (size_t)(2 * (kXCap + 2 * kXPad) + 4 * (kXCap + kXPad)) * sizeof(uint32_t);
     b += (size_t)2 * kNG * sizeof(uint4);
     b += (size_t)2 * (kCCap / 4 + 2 * kZPad) * sizeof(double2);
-    b += sizeof(double) * kModelDoubles + sizeof(FastRegions) + 64;
+    b += sizeof(double) * kModelDoubles + 2 * sizeof(FastRegions) + 64;
     return b;
 }
 

@@ -56,7 +56,7 @@ struct ScoreParams {
     // fast kernel only
     int vec_ok;            // exp/obs/pval output pointers are 32-byte aligned
     unsigned winp_vec;     // bit s: row s of winp_out is 32-byte aligned
-    unsigned scale_mask;   // bit h: some scale has half-width h
+    unsigned h_rows[kFastMaxScaleHalfWin + 1];  // bit s of h_rows[h]: output row s has half-width h
     double inv_sqrt_k[kFastMaxScaleHalfWin + 1];  // 1/sqrt(2h+1)
 };
 
