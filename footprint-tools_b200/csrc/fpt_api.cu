@@ -324,17 +324,31 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     // (per-strand outputs, other window half-widths, deeper trimming) runs on the general kernel.
     const bool fast = !ctx->force_general && p.combine && hw == kFastHalfWin && (shw == 0 || shw >= 4) && ktrim <= 1 &&
                       wh_max <= kFastMaxScaleHalfWin && !a->win_out;
+    WindowParams wp;
+    memset(&wp, 0, sizeof wp);
+    const bool windows = fast && a->winp_out && a->n_scales > 0;
     if (fast) {
-        p.tile = kFastCCap - 2 * wh_max - 48;
+        p.tile = kFastCCap - 48;
         p.n_tiles = (a->total + p.tile - 1) / p.tile;
+        p.wh_max = 0;  // the window kernel works on the flat z array: no halo of computed positions
         auto al32 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 31u) == 0; };
         p.vec_ok = al32(a->exp_out) && al32(a->obs_out) && al32(a->pval_out);
-        p.winp_vec = 0;
-        for (int s = 0; s < p.n_scales; ++s) {
-            if (al32(a->winp_out + (size_t)s * (size_t)a->total)) p.winp_vec |= 1u << s;
-            p.h_rows[p.whw[s]] |= 1u << s;
+        if (windows) {
+            // scratch: [8 pad | z(total) | pad] doubles, then the edge bytes
+            const size_t zdoubles = ((size_t)a->total + 16 + 3) & ~(size_t)3;
+            CU(ctx->scratch.need(zdoubles * sizeof(double) + (((size_t)a->total + 7) & ~(size_t)3)));
+            double *zbase = ctx->scratch.as<double>();
+            CU(cudaMemsetAsync(zbase, 0, 8 * sizeof(double), ctx->stream));
+            CU(cudaMemsetAsync(zbase + 8 + a->total, 0, (zdoubles - 8 - (size_t)a->total) * sizeof(double), ctx->stream));
+            p.z_out = zbase + 8;
+            p.edge_out = reinterpret_cast<unsigned char *>(zbase + zdoubles);
+            wp.z = p.z_out; wp.edge = p.edge_out; wp.total = a->total; wp.winp_out = a->winp_out; wp.wh_max = wh_max;
+            for (int s = 0; s < a->n_scales; ++s) {
+                if (al32(a->winp_out + (size_t)s * (size_t)a->total)) wp.winp_vec |= 1u << s;
+                wp.h_rows[p.whw[s]] |= 1u << s;
+            }
+            for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) wp.inv_sqrt_k[h] = 1.0 / std::sqrt((double)(2 * h + 1));
         }
-        for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) p.inv_sqrt_k[h] = 1.0 / std::sqrt((double)(2 * h + 1));
     }
     if (p.n_tiles > 0x7FFFFFFFLL) return fail(FPT_ERR_ARG, "fpt_score: too many tiles");
     CU(ctx->plan.need((size_t)p.n_tiles * sizeof(int)));
@@ -353,6 +367,10 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
         if (grid > p.n_tiles) grid = p.n_tiles;
         CU(launch_score_fast(ctx->stream, p, (int)grid));
         ctx->launches++;
+        if (windows) {
+            CU(launch_window_fast(ctx->stream, wp, ctx->sm_count));
+            ctx->launches++;
+        }
         return FPT_OK;
     }
     size_t smem = score_smem_bytes(hw, p.uniform != 0);

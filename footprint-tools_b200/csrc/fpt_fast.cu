@@ -50,7 +50,6 @@ constexpr int kXCap = kFastXCap;        // x-space capacity
 constexpr int kNG = kXCap / 4;          // groups of 4 slots
 constexpr int kFReg = 16;               // regions per sub-tile
 constexpr int kXPad = 16;               // zero/scratch slots before and after the slot arrays
-constexpr int kZPad = 2;                // groups of padding around the z arrays
 
 struct FastRegions {
     long long G0[kFReg];    // track coordinate of slot x  = x + G0
@@ -113,9 +112,8 @@ __constant__ double kExpT[12] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880
 
 __device__ __noinline__ double ndtr_slow(double a) { return ndtr_fn(a); }
 
-__device__ __forceinline__ double ndtr_tail(double a) {
-    const double t = fabs(a);
-    if (!(t < 26.0)) return ndtr_slow(a);
+// branch-free core: Phi(-t) for 0 <= t < 26 (callers clamp; the clamped lanes are recomputed by ndtr_slow)
+__device__ __forceinline__ double ndtr_tail_core(double t) {
     double r;
     {
         const double d = t + 5.0;
@@ -134,8 +132,7 @@ __device__ __forceinline__ double ndtr_tail(double a) {
     q = fma(nf, -1.90821492927058770002e-10, q);
     const double pe = cpoly<12>(q, kExpT);
     const double E = __hiloint2double(__double2hiint(pe) + (n << 20), __double2loint(pe));
-    const double tail = E * F;
-    return a > 0.0 ? 1.0 - tail : tail;
+    return E * F;
 }
 
 __device__ __forceinline__ int fregion_of(const int *bases, int nreg, int v) {
@@ -373,15 +370,29 @@ __device__ __forceinline__ void build_regions(const ScoreParams &P, FastRegions 
 
 // Stouffer p-values of 4 consecutive positions at one half-width (windowing.h:53-67 with the edge
 // rule of windowing.pyx:51-54) and their stores into every output row that asked for this width.
+// edge4 holds, per position, min(t, len-1-t, 255) with t the interval-local index.
 __device__ __noinline__ void emit_scale(double a0, double a1, double a2, double a3, int h, double cneg, unsigned rows,
-                                        unsigned winp_vec, double *winp_out, long long total, long long t0,
-                                        long long ivlen, long long f0, unsigned omask) {
-    const long long tmax = ivlen - h;
+                                        unsigned winp_vec, double *winp_out, long long total, unsigned edge4,
+                                        long long f0, unsigned omask) {
+    // four independent evaluations, interleaved by the compiler (no per-element branches)
+    const double av[4] = {a0 * cneg, a1 * cneg, a2 * cneg, a3 * cneg};
     double res[4];
-    res[0] = (t0 >= h && t0 < tmax) ? ndtr_tail(a0 * cneg) : 1.0;
-    res[1] = (t0 + 1 >= h && t0 + 1 < tmax) ? ndtr_tail(a1 * cneg) : 1.0;
-    res[2] = (t0 + 2 >= h && t0 + 2 < tmax) ? ndtr_tail(a2 * cneg) : 1.0;
-    res[3] = (t0 + 3 >= h && t0 + 3 < tmax) ? ndtr_tail(a3 * cneg) : 1.0;
+    bool slow = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double t = fabs(av[e]);
+        slow |= !(t < 26.0);
+        const double tail = ndtr_tail_core(fmin(t, 26.0));
+        res[e] = av[e] > 0.0 ? 1.0 - tail : tail;
+    }
+    if (slow) {  // |a| >= 26, infinite or NaN: the Cephes replica (rare)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (!(fabs(av[e]) < 26.0)) res[e] = ndtr_slow(av[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if ((int)((edge4 >> (8 * e)) & 0xFFu) < h) res[e] = 1.0;  // closer than h to an interval end
     for (unsigned m = rows; m; m &= m - 1) {
         const int s = __ffs(m) - 1;
         double *dst = winp_out + (size_t)s * total + f0;
@@ -391,6 +402,42 @@ __device__ __noinline__ void emit_scale(double a0, double a1, double a2, double 
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if ((omask >> e) & 1u) dst[e] = res[e];
+        }
+    }
+}
+
+__device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+// ---- window kernel: multi-scale Stouffer combination over the flat z array -----------------------
+// z (ndtri(1 - p) of every scored position, written by the scoring kernel) is padded by 8 doubles on
+// both sides and 32-byte aligned; a thread owns 4 consecutive positions and reads its +-8 halo with
+// five 256-bit loads (neighbouring threads overlap in L1). Windows never need interval geometry:
+// a window that would cross an interval end is exactly the one the edge rule sets to 1.0.
+__global__ void __launch_bounds__(256, 3) window_fast_kernel(const WindowParams W) {
+    const long long ngroups = (W.total + 3) >> 2;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long f0 = g << 2;
+        double z[20];  // z[8 + e] is element e
+#pragma unroll
+        for (int q = 0; q < 5; ++q) ld256(W.z + f0 - 8 + 4 * q, z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+        const unsigned edge4 = __ldg(reinterpret_cast<const unsigned *>(W.edge) + g);
+        const long long left = W.total - f0;
+        const unsigned omask = left >= 4 ? 0xFu : ((1u << (int)left) - 1u);
+        double acc[4] = {z[8], z[9], z[10], z[11]};
+        // sums grow outward from the centre: S_h = S_{h-1} + z[-h] + z[+h]
+#pragma unroll
+        for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
+            if (h > W.wh_max) break;
+            if (h > 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
+            }
+            if (W.h_rows[h])
+                emit_scale(acc[0], acc[1], acc[2], acc[3], h, -W.inv_sqrt_k[h], W.h_rows[h], W.winp_vec, W.winp_out,
+                           W.total, edge4, f0, omask);
         }
     }
 }
@@ -414,9 +461,7 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
     uint32_t *prm = prp + kXCap + kXPad;
     uint4 *G0 = reinterpret_cast<uint4 *>(prm + kXCap + kXPad);                      // group (min,max) x2 strands
     uint4 *G1 = G0 + kNG;
-    double2 *zA = reinterpret_cast<double2 *>(G1 + kNG) + kZPad;                     // z of c%4 in {0,1}
-    double2 *zB = zA + kCCap / 4 + 2 * kZPad;                                        // z of c%4 in {2,3}
-    double *dmp = reinterpret_cast<double *>(zB + kCCap / 4 + kZPad);                // 24
+    double *dmp = reinterpret_cast<double *>(G1 + kNG);                              // 24
     FastRegions *Rbuf = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);        // double-buffered
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,7 +470,7 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
     const int wsm = 2 * shw + 1;
     const int WH = P.wh_max;
     const int PADX = (pad + 1 + 3) & ~3, PADR = (pad + 3) & ~3;
-    const bool want_z = (P.winp_out != nullptr && P.n_scales > 0);
+    const bool want_z = P.z_out != nullptr;  // the window kernel runs after this one
     const bool want_p = (P.pval_out != nullptr) || want_z;
     const double dW = (double)(wsm - 2 * ktrim);
 
@@ -473,17 +518,25 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
         // ---- phase 1: stage cut counts (asynchronous copies, coalesced per region); warp 0 builds
         //      the next sub-tile's region table while they are in flight -------------------------
         for (int r = 0; r < nreg; ++r) {
-            const int xe = R->xblk[r + 1];
+            const int xb = R->xblk[r], xe = R->xblk[r + 1];
             const long long g0 = R->G0[r];
-            const uint32_t *bp = P.cuts_p + g0, *bm = P.cuts_m + g0;
-            // slots whose track coordinate x + g0 lies inside [0, n_track)
-            const long long vlo = -g0, vhi = P.n_track - g0;
-            const int xlo = vlo < 0 ? 0 : (vlo > kXCap ? kXCap : (int)vlo);
-            const int xhi = vhi < 0 ? 0 : (vhi > kXCap ? kXCap : (int)vhi);
-            for (int x = R->xblk[r] + tid; x < xe; x += kFT) {
-                const bool ok = x >= xlo && x < xhi;
-                cp_async4(cp + x, ok ? bp + x : P.cuts_p, ok);
-                cp_async4(cm + x, ok ? bm + x : P.cuts_m, ok);
+            if (g0 + xb >= 0 && g0 + xe <= P.n_track) {  // whole region inside the track (the common case)
+                const uint32_t *sp = P.cuts_p + (g0 + xb + tid), *sm = P.cuts_m + (g0 + xb + tid);
+                unsigned dp = (unsigned)__cvta_generic_to_shared(cp + xb + tid);
+                unsigned dm = (unsigned)__cvta_generic_to_shared(cm + xb + tid);
+#pragma unroll 2
+                for (int x = xb + tid; x < xe; x += kFT) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dp), "l"(sp) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dm), "l"(sm) : "memory");
+                    sp += kFT; sm += kFT; dp += 4 * kFT; dm += 4 * kFT;
+                }
+            } else {
+                for (int x = xb + tid; x < xe; x += kFT) {
+                    const long long g = x + g0;
+                    const bool ok = g >= 0 && g < P.n_track;
+                    cp_async4(cp + x, ok ? P.cuts_p + g : P.cuts_p, ok);
+                    cp_async4(cm + x, ok ? P.cuts_m + g : P.cuts_m, ok);
+                }
             }
         }
         if (warp == 0 && more) build_regions(P, &Rbuf[buf ^ 1], ncur, nhi, nk, lane, WH, PADX, PADR);
@@ -820,6 +873,16 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                     if (P.exp_out) st256(P.exp_out + f0, exv[0], exv[1], exv[2], exv[3]);
                     if (P.obs_out) st256(P.obs_out + f0, obv[0], obv[1], obv[2], obv[3]);
                     if (P.pval_out) st256(P.pval_out + f0, pvv[0], pvv[1], pvv[2], pvv[3]);
+                    if (want_z) {
+                        st256(P.z_out + f0, zv[0], zv[1], zv[2], zv[3]);
+                        unsigned edge4 = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const long long t = T0 + c0 + e, d = min(t, ivlen - 1 - t);
+                            edge4 |= (unsigned)(d < 255 ? d : 255) << (8 * e);
+                        }
+                        *reinterpret_cast<unsigned *>(P.edge_out + f0) = edge4;
+                    }
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
@@ -827,39 +890,12 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                             if (P.exp_out) P.exp_out[f0 + e] = exv[e];
                             if (P.obs_out) P.obs_out[f0 + e] = obv[e];
                             if (P.pval_out) P.pval_out[f0 + e] = pvv[e];
+                            if (want_z) {
+                                const long long t = T0 + c0 + e, d = min(t, ivlen - 1 - t);
+                                P.z_out[f0 + e] = zv[e];
+                                P.edge_out[f0 + e] = (unsigned char)(d < 255 ? d : 255);
+                            }
                         }
-                }
-            }
-            if (want_z) {
-                if (active) {
-                    zA[tid] = make_double2(zv[0], zv[1]);
-                    zB[tid] = make_double2(zv[2], zv[3]);
-                }
-                __syncthreads();
-
-                // ---- phase 5: Stouffer windows at every requested half-width ---------------------
-                if (omask) {
-                    double z[20];  // z[8 + e] is element e
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        const double2 a = zA[tid - 2 + q], b = zB[tid - 2 + q];
-                        z[4 * q] = a.x; z[4 * q + 1] = a.y; z[4 * q + 2] = b.x; z[4 * q + 3] = b.y;
-                    }
-                    const long long f0 = F0 + c0;
-                    const long long t0 = T0 + c0;
-                    double acc[4] = {z[8], z[9], z[10], z[11]};
-                    // sums grow outward from the centre: S_h = S_{h-1} + z[-h] + z[+h]
-#pragma unroll
-                    for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
-                        if (h > WH) break;
-                        if (h > 0) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
-                        }
-                        if (P.h_rows[h])
-                            emit_scale(acc[0], acc[1], acc[2], acc[3], h, -P.inv_sqrt_k[h], P.h_rows[h], P.winp_vec, P.winp_out,
-                                       P.total, t0, ivlen, f0, omask);
-                    }
                 }
             }
         }
@@ -875,7 +911,6 @@ size_t score_fast_smem_bytes() {
     size_t b = 4096 * sizeof(double);
     b += (size_t)(2 * (kXCap + 2 * kXPad) + 4 * (kXCap + kXPad)) * sizeof(uint32_t);
     b += (size_t)2 * kNG * sizeof(uint4);
-    b += (size_t)2 * (kCCap / 4 + 2 * kZPad) * sizeof(double2);
     b += sizeof(double) * kModelDoubles + 2 * sizeof(FastRegions) + 64;
     return b;
 }
@@ -892,6 +927,16 @@ int score_fast_blocks_per_sm(size_t smem) {
 
 cudaError_t launch_score_fast(cudaStream_t st, const ScoreParams &p, int grid) {
     score_fast_kernel<5><<<grid, kFT, score_fast_smem_bytes(), st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_window_fast(cudaStream_t st, const WindowParams &w, int sm_count) {
+    const long long ngroups = (w.total + 3) >> 2;
+    if (ngroups <= 0) return cudaSuccess;
+    long long blocks = (ngroups + 255) / 256;
+    const long long cap = (long long)sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    window_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(w);
     return cudaGetLastError();
 }
 

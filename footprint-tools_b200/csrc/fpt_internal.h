@@ -55,7 +55,18 @@ struct ScoreParams {
     int p_cap;  // capacity of each bias-propensity staging array
     // fast kernel only
     int vec_ok;            // exp/obs/pval output pointers are 32-byte aligned
-    unsigned winp_vec;     // bit s: row s of winp_out is 32-byte aligned
+    double *z_out;             // ndtri(1 - p) per scored position for the window kernel (or NULL)
+    unsigned char *edge_out;   // min(t, len-1-t, 255) per scored position
+};
+
+// window kernel of the fast path (fpt_fast.cu)
+struct WindowParams {
+    const double *z;            // 32-byte aligned, 8 doubles of padding on both sides
+    const unsigned char *edge;  // 4-byte aligned
+    long long total;
+    double *winp_out;
+    int wh_max;
+    unsigned winp_vec;                          // bit s: row s of winp_out is 32-byte aligned
     unsigned h_rows[kFastMaxScaleHalfWin + 1];  // bit s of h_rows[h]: output row s has half-width h
     double inv_sqrt_k[kFastMaxScaleHalfWin + 1];  // 1/sqrt(2h+1)
 };
@@ -71,6 +82,7 @@ size_t score_fast_smem_bytes();
 cudaError_t score_fast_prepare(size_t smem);
 int score_fast_blocks_per_sm(size_t smem);
 cudaError_t launch_score_fast(cudaStream_t st, const ScoreParams &p, int grid);
+cudaError_t launch_window_fast(cudaStream_t st, const WindowParams &w, int sm_count);
 
 cudaError_t launch_lut_build(cudaStream_t st, const double *dm, double2 *lut, int lut_e, int lut_o);
 cudaError_t launch_nb_values(cudaStream_t st, const double *dm, const double *e, const double *o, long long n,
