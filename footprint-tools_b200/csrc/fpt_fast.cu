@@ -279,12 +279,26 @@ __device__ __noinline__ double fexpected_exact(SeqView P, const double *tab, con
     double sm;
     if (shw == 0) {
         sm = (double)wc[slot];
-    } else if (ktrim == 0) {
-        unsigned long long t = 0;
-        for (int m = -shw; m <= shw; ++m) t += wc[slot + m];
-        sm = __ddiv_rn((double)t, (double)(2 * shw + 1));
     } else {
-        sm = ftrimmed_mean_exact(wc, slot - shw, 2 * shw + 1, ktrim);
+        const int w = 2 * shw + 1;
+        unsigned long long sum = 0;
+        unsigned mn = 0xFFFFFFFFu, mx = 0;
+        for (int m = -shw; m <= shw; ++m) {
+            const unsigned v = wc[slot + m];
+            sum += v; mn = min(mn, v); mx = max(mx, v);
+        }
+        if (ktrim == 0) {
+            sm = __ddiv_rn((double)sum, (double)w);
+        } else {
+            // second tier: everything but the trimmed sum is now in the reference's own order; the integer
+            // trimmed sum differs from the reference's float one by < 1e-14 relative (tie weights)
+            const bool quirk = (sum - mn) == (unsigned long long)(w - 1) * (unsigned long long)mx;
+            const unsigned long long T = quirk ? (sum - mn) : (sum - mn - mx);
+            const double v = __dmul_rn(ratio, __ddiv_rn((double)T, (double)(w - 2)));
+            const double rr = rint(v), av = fabs(v);
+            if (ktrim == 1 && (av < 4.0e15) && (fabs(v - rr) < fma(av, -4e-12, 0.5 - 4e-12))) return rr;
+            sm = ftrimmed_mean_exact(wc, slot - shw, w, ktrim);
+        }
     }
     return round(__dmul_rn(ratio, sm));
 }
@@ -448,18 +462,21 @@ __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gs
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa), "l"(gsrc), "r"(n) : "memory");
 }
 
+#ifndef FPT_FAST_CTAS
+#define FPT_FAST_CTAS 2
+#endif
 template <int HW>
-__global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P) {
+__global__ void __launch_bounds__(kFT, FPT_FAST_CTAS) score_fast_kernel(const ScoreParams P) {
     static_assert(HW >= 1 && HW <= 5, "slot loads cover [x0-8, x0+8)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *tab = reinterpret_cast<double *>(smem_raw);                              // 4096 f64
+    float *tab = reinterpret_cast<float *>(smem_raw);                                // 4096 f32 (see phase 4)
     uint32_t *cp = reinterpret_cast<uint32_t *>(tab + 4096) + kXPad;                 // cuts, plus strand
     uint32_t *cm = cp + kXCap + 2 * kXPad;                                           // cuts, minus strand
     uint32_t *wcp = cm + kXCap + kXPad;                                              // 2*HW-wide window sums
     uint32_t *wcm = wcp + kXCap + kXPad;
-    uint32_t *prp = wcm + kXCap + kXPad;                                             // inclusive prefix of wc
-    uint32_t *prm = prp + kXCap + kXPad;
-    uint4 *G0 = reinterpret_cast<uint4 *>(prm + kXCap + kXPad);                      // group (min,max) x2 strands
+    uint32_t *gpp = wcm + kXCap + kXPad;                                             // inclusive prefix of the
+    uint32_t *gpm = gpp + kNG + 4;                                                   //   group totals of wc
+    uint4 *G0 = reinterpret_cast<uint4 *>(gpm + kNG + 4);                            // group (min,max) x2 strands
     uint4 *G1 = G0 + kNG;
     double *dmp = reinterpret_cast<double *>(G1 + kNG);                              // 24
     FastRegions *Rbuf = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);        // double-buffered
@@ -473,9 +490,10 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
     const bool want_z = P.z_out != nullptr;  // the window kernel runs after this one
     const bool want_p = (P.pval_out != nullptr) || want_z;
     const double dW = (double)(wsm - 2 * ktrim);
+    const float dflt_f = (float)P.dflt;
 
     if (!P.uniform)
-        for (int i = tid; i < 4096; i += kFT) tab[i] = P.bias[i];
+        for (int i = tid; i < 4096; i += kFT) tab[i] = (float)P.bias[i];
     if (tid < kModelDoubles) dmp[tid] = P.dm ? P.dm[tid] : 0.0;
     for (int i = tid; i < kXPad; i += kFT) {  // slots read before/after the staged range
         cp[-1 - i] = 0; cm[-1 - i] = 0; cp[kXCap + i] = 0; cm[kXCap + i] = 0;
@@ -546,8 +564,8 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
         if (nreg > 0) {
             // ---- phase 2: window sums, their block-wide prefix sums, group min/max ------------
             {
-                unsigned pfx[2][2][4];  // [round][strand][e]: thread-local inclusive prefix of wc
-                unsigned incl_w[2][2];  // warp-inclusive scan of the thread totals
+                unsigned tot[2][2];     // [round][strand]: total of the thread's group
+                unsigned incl_w[2][2];  // warp-inclusive scan of the group totals
                 bool bad = false;
 #pragma unroll
                 for (int rd = 0; rd < 2; ++rd) {
@@ -589,12 +607,8 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                     }
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
-                        unsigned a = wc[s][0];
-                        pfx[rd][s][0] = a;
-                        a += wc[s][1]; pfx[rd][s][1] = a;
-                        a += wc[s][2]; pfx[rd][s][2] = a;
-                        a += wc[s][3]; pfx[rd][s][3] = a;
-                        incl_w[rd][s] = a;
+                        tot[rd][s] = (wc[s][0] + wc[s][1]) + (wc[s][2] + wc[s][3]);
+                        incl_w[rd][s] = tot[rd][s];
                     }
                 }
                 if (bad) atomicOr(P.status, 1);
@@ -628,19 +642,15 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
 #pragma unroll
                         for (int w2 = 0; w2 < kFT / 32; ++w2)
                             if (w2 < warp) before1 += R->wtot[1][s][w2];
-                        base[0][s] = before + incl_w[0][s] - pfx[0][s][3];
-                        base[1][s] = all0 + before1 + incl_w[1][s] - pfx[1][s][3];
+                        base[0][s] = before + incl_w[0][s];          // inclusive prefix of the group totals
+                        base[1][s] = all0 + before1 + incl_w[1][s];
                     }
 #pragma unroll
                     for (int rd = 0; rd < 2; ++rd) {
                         const int xg = tid + rd * kFT;
                         if (xg < NXG) {
-                            const int x0 = xg << 2;
-                            const unsigned bp = base[rd][0], bm = base[rd][1];
-                            *reinterpret_cast<uint4 *>(prp + x0) = make_uint4(bp + pfx[rd][0][0], bp + pfx[rd][0][1],
-                                                                              bp + pfx[rd][0][2], bp + pfx[rd][0][3]);
-                            *reinterpret_cast<uint4 *>(prm + x0) = make_uint4(bm + pfx[rd][1][0], bm + pfx[rd][1][1],
-                                                                              bm + pfx[rd][1][2], bm + pfx[rd][1][3]);
+                            gpp[xg] = base[rd][0];
+                            gpm[xg] = base[rd][1];
                         }
                     }
                 }
@@ -732,14 +742,16 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                     t = ((t & 0xAAAAAAAAAull) >> 1) | ((t & 0x555555555ull) << 1);
                     rcw = t ^ 0xFFFFFFFFFull;
                 }
-                double ev[2][4];
+                double exv[4] = {0.0, 0.0, 0.0, 0.0};  // plus[t+1] + minus[t] (cli/detect.py:121-122)
+                unsigned redo = 0;  // bit 4*s + e: strand s of element e needs the out-of-line evaluation
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
-                    // -- propensities Pv[m] of k-mer m on this strand
-                    double Pv[13];
+                    // -- propensities Pv[m] of k-mer m on this strand, in single precision: the estimate
+                    //    only has to place v relative to the guard band (see "expected count" below)
+                    float Pv[13];
                     if (P.uniform) {
 #pragma unroll
-                        for (int m = 0; m < 13; ++m) Pv[m] = 1.0;
+                        for (int m = 0; m < 13; ++m) Pv[m] = 1.0f;
                     } else {
 #pragma unroll
                         for (int m = 0; m < 13; ++m) {
@@ -749,13 +761,13 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                         if (nw != 0) {
 #pragma unroll
                             for (int m = 0; m < 13; ++m)
-                                if ((nw >> m) & 0x3Fu) Pv[m] = P.dflt;
+                                if ((nw >> m) & 0x3Fu) Pv[m] = dflt_f;
                         }
                     }
                     // -- pairwise window sums of 2*HW = 10 propensities for the 4 elements
-                    double wp[4];
+                    float wp[4];
                     {
-                        double s2[12], s4[8];
+                        float s2[12], s4[8];
 #pragma unroll
                         for (int m = 0; m < 12; ++m) s2[m] = Pv[m] + Pv[m + 1];
 #pragma unroll
@@ -770,21 +782,31 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                     if (shw == 0) {
                         lds4_unaligned(wcs, i0, T);
                     } else {
-                        const uint32_t *prs = s ? prm : prp;
-                        unsigned up[4], dn[4];
-                        lds4_unaligned(prs, i0 + shw, up);
-                        lds4_unaligned(prs, i0 - shw - 1, dn);
+                        // window of element e: slots [a0 + e, e0 + e]; tail of its first group, the full
+                        // groups in between (difference of group prefixes), head of its last group
+                        const uint32_t *gps = s ? gpm : gpp;
+                        const int a0 = i0 - shw, e0 = i0 + shw;
+                        const int ga = a0 >> 2, ka = a0 & 3;        // element e starts at v[ka+e]
+                        const int ge = e0 >> 2, ke = e0 & 3;        // element e ends at u[ke+e]
+                        unsigned va[4], vb[4], ua[4], ub[4];
+                        lds4(wcs + (ga << 2), va);
+                        lds4(wcs + (ga << 2) + 4, vb);
+                        lds4(wcs + (ge << 2), ua);
+                        lds4(wcs + (ge << 2) + 4, ub);
+                        {
+                            unsigned ssum[8], psum[8], A[4], B[4];
+                            ssum[3] = va[3]; ssum[2] = va[2] + ssum[3]; ssum[1] = va[1] + ssum[2]; ssum[0] = va[0] + ssum[1];
+                            ssum[7] = vb[3]; ssum[6] = vb[2] + ssum[7]; ssum[5] = vb[1] + ssum[6]; ssum[4] = vb[0] + ssum[5];
+                            psum[0] = ua[0]; psum[1] = ua[1] + psum[0]; psum[2] = ua[2] + psum[1]; psum[3] = ua[3] + psum[2];
+                            psum[4] = ub[0]; psum[5] = ub[1] + psum[4]; psum[6] = ub[2] + psum[5]; psum[7] = ub[3] + psum[6];
+                            pick4(ssum, ka, A);
+                            pick4(psum, ke, B);
+                            const unsigned g_lo0 = gps[ga], g_lo1 = gps[ga + 1], g_hi0 = gps[ge - 1], g_hi1 = gps[ge];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) T[e] = up[e] - dn[e];
+                            for (int e = 0; e < 4; ++e)
+                                T[e] = A[e] + B[e] + (((ke + e >= 4) ? g_hi1 : g_hi0) - ((ka + e >= 4) ? g_lo1 : g_lo0));
+                        }
                         if (ktrim > 0) {
-                            const int a0 = i0 - shw, e0 = i0 + shw;     // first / last slot of element 0's window
-                            const int ga = a0 >> 2, ka = a0 & 3;        // element e starts at v[ka+e]
-                            const int ge = e0 >> 2, ke = e0 & 3;        // element e ends at u[ke+e]
-                            unsigned va[4], vb[4], ua[4], ub[4];
-                            lds4(wcs + (ga << 2), va);
-                            lds4(wcs + (ga << 2) + 4, vb);
-                            lds4(wcs + (ge << 2), ua);
-                            lds4(wcs + (ge << 2) + 4, ub);
                             // suffix (to the end of its own group) and prefix (from the start) extrema
                             unsigned smn[8], smx[8], pmn[8], pmx[8];
                             smn[3] = smx[3] = va[3];
@@ -825,47 +847,75 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
                             }
                         }
                     }
-                    // -- expected count: fast evaluation + guard band, exact replica inside the band
-                    //    (a non-finite or huge v fails the first comparison and takes the exact path)
+                    // -- expected count. v = p/win_p * smoothed is estimated from the single-precision
+                    //    propensities (relative error < 5e-7) and rounded; if it lies within 2e-6*(v+1) of
+                    //    a half-integer the out-of-line path redoes it in the reference's own double
+                    //    operation order (and, inside a 4e-12 band, with the quickselect replica).
+                    //    A non-finite or huge v fails the first comparison and goes the same way.
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const double v = (Pv[e + 5] * (double)T[e]) * fast_rcp(wp[e] * dW);
+                        const double v = ((double)Pv[e + 5] * (double)T[e]) * fast_rcp((double)wp[e] * dW);
                         const double rr = rint(v);
                         const double av = fabs(v);
-                        double res = rr;
-                        const bool sure = (av < 4.0e15) && (fabs(v - rr) < fma(av, -4e-12, 0.5 - 4e-12));
-                        if (!sure && ((vmask >> e) & 1u))
-                            res = fexpected_exact(SeqView{P.seq2, P.nmask, P.n_track, P.dflt, P.uniform}, tab, wcs, HW, shw, ktrim,
-                                                  g0 + e - s, i0 + e, s);
-                        ev[s][e] = res;
+                        const bool sure = (av < 4.0e15) && (fabs(v - rr) < fma(av, -2e-6, 0.5 - 2e-6));
+                        if (sure) exv[e] = __dadd_rn(exv[e], rr);
+                        else redo |= 1u << (4 * s + e);
                     }
                 }
-                // -- strand combine (cli/detect.py:121-122): plus[t+1] + minus[t]
+                redo &= vmask | (vmask << 4);
+                if (redo) {  // rare; kept out of the loops above so that nothing is live across the calls
+                    for (unsigned m = redo; m; m &= m - 1) {
+                        const int b = __ffs(m) - 1, s = b >> 2, e = b & 3;
+                        const double res = fexpected_exact(SeqView{P.seq2, P.nmask, P.n_track, P.dflt, P.uniform}, P.bias,
+                                                           s ? wcm : wcp, HW, shw, ktrim, g0 + e - s, x0 - s + e, s);
+                        if (e == 0) exv[0] = __dadd_rn(exv[0], res);
+                        else if (e == 1) exv[1] = __dadd_rn(exv[1], res);
+                        else if (e == 2) exv[2] = __dadd_rn(exv[2], res);
+                        else exv[3] = __dadd_rn(exv[3], res);
+                    }
+                }
+                // -- observed counts and p-values. The (exp, obs) table serves what it holds; the rest
+                //    is evaluated directly afterwards (same device functions => same bits)
                 unsigned cpv[4], cmv[4];
                 lds4(cp + x0, cpv);
                 lds4_unaligned(cm, x0 - 1, cmv);
-                double exv[4], obv[4], pvv[4];
+                double obv[4], pvv[4];
+                unsigned direct = 0;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const double ex = __dadd_rn(ev[0][e], ev[1][e]);
                     const unsigned long long obi = (unsigned long long)cpv[e] + (unsigned long long)cmv[e];
-                    const double ob = (double)obi;
-                    exv[e] = ex; obv[e] = ob;
-                    double pv = 1.0, z = 0.0;
+                    obv[e] = (double)obi;
+                    pvv[e] = 1.0;
                     if (want_p && ((vmask >> e) & 1u)) {
-                        if (ex < (double)P.lut_e && ob < (double)P.lut_o) {
-                            const double2 e2 = __ldg(P.lut + (unsigned)((int)ex * P.lut_o + (int)obi));
-                            pv = e2.x; z = e2.y;
+                        if (exv[e] < (double)P.lut_e && obv[e] < (double)P.lut_o) {
+                            const double2 e2 = __ldg(P.lut + (unsigned)((int)exv[e] * P.lut_o + (int)obi));
+                            pvv[e] = e2.x; zv[e] = e2.y;
                         } else {
-                            const double rr = fit_r(dmp + 9, ex), mu = fit_mu(dmp, ex);
-                            const int kobs = ob < 2147483646.0 ? (int)ob : 2147483646;
-                            pv = nb_cdf(kobs, nb_prob(rr, mu), rr);
-                            z = ndtri_fn(1.0 - pv);
+                            direct |= 1u << e;
                         }
                     }
-                    pvv[e] = pv; zv[e] = z;
-                    if (P.hist && ((omask >> e) & 1u) && ex < (double)P.hist_d0 && ob < (double)P.hist_d1)
-                        atomicAdd(P.hist + (size_t)((int)ex) * P.hist_d1 + (int)ob, 1ULL);
+                }
+                if (direct) {
+#pragma unroll 1
+                    for (int e = 0; e < 4; ++e) {
+                        if (!((direct >> e) & 1u)) continue;
+                        const double ex = e == 0 ? exv[0] : e == 1 ? exv[1] : e == 2 ? exv[2] : exv[3];
+                        const double ob = e == 0 ? obv[0] : e == 1 ? obv[1] : e == 2 ? obv[2] : obv[3];
+                        const double rr = fit_r(dmp + 9, ex), mu = fit_mu(dmp, ex);
+                        const int kobs = ob < 2147483646.0 ? (int)ob : 2147483646;
+                        const double pv = nb_cdf(kobs, nb_prob(rr, mu), rr);
+                        const double z = ndtri_fn(1.0 - pv);
+                        if (e == 0) { pvv[0] = pv; zv[0] = z; }
+                        else if (e == 1) { pvv[1] = pv; zv[1] = z; }
+                        else if (e == 2) { pvv[2] = pv; zv[2] = z; }
+                        else { pvv[3] = pv; zv[3] = z; }
+                    }
+                }
+                if (P.hist) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (((omask >> e) & 1u) && exv[e] < (double)P.hist_d0 && obv[e] < (double)P.hist_d1)
+                            atomicAdd(P.hist + (size_t)((int)exv[e]) * P.hist_d1 + (int)obv[e], 1ULL);
                 }
                 // -- stores: one 256-bit store per array when the whole group is output
                 const long long f0 = F0 + c0;
@@ -908,8 +958,8 @@ __global__ void __launch_bounds__(kFT, 2) score_fast_kernel(const ScoreParams P)
 }  // namespace
 
 size_t score_fast_smem_bytes() {
-    size_t b = 4096 * sizeof(double);
-    b += (size_t)(2 * (kXCap + 2 * kXPad) + 4 * (kXCap + kXPad)) * sizeof(uint32_t);
+    size_t b = 4096 * sizeof(float);
+    b += (size_t)(2 * (kXCap + 2 * kXPad) + 2 * (kXCap + kXPad) + 2 * (kNG + 4)) * sizeof(uint32_t);
     b += (size_t)2 * kNG * sizeof(uint4);
     b += sizeof(double) * kModelDoubles + 2 * sizeof(FastRegions) + 64;
     return b;
