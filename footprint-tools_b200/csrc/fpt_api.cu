@@ -82,6 +82,13 @@ struct fpt_ctx {
     // scratch
     DevBuf plan, scratch;
     DevBuf h_in[8], h_out[8];  // staging for FPT_MEM_HOST calls
+    // per-kernel CUDA-event timers (fpt_ctx_profile)
+    bool prof = false;
+    struct ProfSlot { cudaEvent_t a, b; int kid; };
+    std::vector<ProfSlot> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[FPT_KERNEL_COUNT] = {0};
+    int64_t prof_n[FPT_KERNEL_COUNT] = {0};
 };
 
 namespace {
@@ -97,6 +104,29 @@ struct DeviceGuard {
         if (prev != want) cudaSetDevice(prev);
     }
     int want;
+};
+
+// Brackets one kernel launch with a pair of events on the context's stream when profiling is on.
+struct ProfScope {
+    fpt_ctx *c;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kid;
+    static cudaEvent_t get(fpt_ctx *c) {
+        cudaEvent_t e = nullptr;
+        if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+        return e;
+    }
+    ProfScope(fpt_ctx *ctx, int kernel) : c(ctx), kid(kernel) {
+        if (!c->prof) return;
+        a = get(c); b = get(c);
+        if (a && b) cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() {
+        if (!a || !b) return;
+        cudaEventRecord(b, c->stream);
+        c->prof_pending.push_back({a, b, kid});
+    }
 };
 
 int check_status(fpt_ctx *ctx, const char *what) {
@@ -180,6 +210,8 @@ int fpt_ctx_destroy(fpt_ctx *ctx) {
     ctx->scratch.release();
     for (auto &b : ctx->h_in) b.release();
     for (auto &b : ctx->h_out) b.release();
+    for (auto &s : ctx->prof_pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FPT_OK;
@@ -199,6 +231,35 @@ int fpt_ctx_sync(fpt_ctx *ctx) {
 }
 
 int64_t fpt_ctx_launch_count(const fpt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fpt_ctx_profile(fpt_ctx *ctx, int enable) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_ctx_profile: ctx is NULL");
+    ctx->prof = enable != 0;
+    return FPT_OK;
+}
+
+int fpt_ctx_profile_read(fpt_ctx *ctx, double *total_ms, int64_t *launches) {
+    if (!ctx || !total_ms || !launches) return fail(FPT_ERR_ARG, "fpt_ctx_profile_read: NULL argument");
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto &s : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            ctx->prof_ms[s.kid] += ms;
+            ctx->prof_n[s.kid]++;
+        }
+        ctx->ev_pool.push_back(s.a);
+        ctx->ev_pool.push_back(s.b);
+    }
+    ctx->prof_pending.clear();
+    for (int k = 0; k < FPT_KERNEL_COUNT; ++k) {
+        total_ms[k] = ctx->prof_ms[k];
+        launches[k] = ctx->prof_n[k];
+        ctx->prof_ms[k] = 0.0;
+        ctx->prof_n[k] = 0;
+    }
+    return FPT_OK;
+}
 
 int fpt_bias_upload(fpt_ctx *ctx, const double *table4096, double dflt, int uniform) {
     if (!ctx) return fail(FPT_ERR_ARG, "fpt_bias_upload: ctx is NULL");
@@ -353,7 +414,10 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     if (p.n_tiles > 0x7FFFFFFFLL) return fail(FPT_ERR_ARG, "fpt_score: too many tiles");
     CU(ctx->plan.need((size_t)p.n_tiles * sizeof(int)));
     p.tile_first_iv = ctx->plan.as<int>();
-    CU(launch_plan(ctx->stream, p.out_off, p.n_iv, p.total, p.tile, p.n_tiles, ctx->plan.as<int>()));
+    {
+        ProfScope ps(ctx, FPT_KERNEL_PLAN);
+        CU(launch_plan(ctx->stream, p.out_off, p.n_iv, p.total, p.tile, p.n_tiles, ctx->plan.as<int>()));
+    }
     ctx->launches++;
     if (fast) {
         const size_t smem = score_fast_smem_bytes();
@@ -365,9 +429,13 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
         if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: fast kernel does not fit on an SM (smem %zu)", smem);
         long long grid = (long long)ctx->sm_count * per_sm;
         if (grid > p.n_tiles) grid = p.n_tiles;
-        CU(launch_score_fast(ctx->stream, p, (int)grid));
+        {
+            ProfScope ps(ctx, FPT_KERNEL_SCORE_FAST);
+            CU(launch_score_fast(ctx->stream, p, (int)grid));
+        }
         ctx->launches++;
         if (windows) {
+            ProfScope ps(ctx, FPT_KERNEL_WINDOW_FAST);
             CU(launch_window_fast(ctx->stream, wp, ctx->sm_count));
             ctx->launches++;
         }
@@ -382,7 +450,10 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: kernel does not fit on an SM (smem %zu)", smem);
     long long grid = (long long)ctx->sm_count * per_sm;
     if (grid > p.n_tiles) grid = p.n_tiles;
-    CU(launch_score(ctx->stream, p, (int)grid));
+    {
+        ProfScope ps(ctx, FPT_KERNEL_SCORE_GENERAL);
+        CU(launch_score(ctx->stream, p, (int)grid));
+    }
     ctx->launches++;
     return FPT_OK;
 }

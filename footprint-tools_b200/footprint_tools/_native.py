@@ -66,6 +66,8 @@ SIGNATURES = {
     "fpt_ctx_sync": (C.c_int, [C.c_void_p]),
     "fpt_ctx_check": (C.c_int, [C.c_void_p]),
     "fpt_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "fpt_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "fpt_ctx_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fpt_bias_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
     "fpt_dm_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "fpt_pack_sequence": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -179,6 +181,19 @@ class Context(object):
     @property
     def launches(self):
         return int(lib().fpt_ctx_launch_count(self._h))
+
+    KERNELS = ("plan", "score_fast", "window_fast", "score_general")
+
+    def profile(self, enable=True):
+        """Turn the per-kernel CUDA-event timers on or off (fpt_ctx_profile)."""
+        _check(lib().fpt_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kernel: (total_ms, launches)} since the last read (synchronises the stream)."""
+        ms = np.zeros(len(self.KERNELS), dtype=np.float64)
+        n = np.zeros(len(self.KERNELS), dtype=np.int64)
+        _check(lib().fpt_ctx_profile_read(self._h, _ptr(ms), _ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNELS)}
 
     # -- models ----------------------------------------------------------------------------------
     def set_bias(self, table4096=None, dflt=1e-6, uniform=False):

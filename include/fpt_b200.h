@@ -73,6 +73,18 @@ int fpt_ctx_check(fpt_ctx *ctx);
 /* Number of this library's kernel launches issued on the context so far. */
 int64_t fpt_ctx_launch_count(const fpt_ctx *ctx);
 
+/* Per-kernel device timers (CUDA events on the context's stream around each launch of the scoring
+ * path; used by bench.py for the roofline figures — the reference has no counterpart). Enable, run,
+ * then read: total_ms / launches are FPT_KERNEL_COUNT-long HOST arrays indexed by FPT_KERNEL_*;
+ * reading synchronises the stream and resets the totals. */
+#define FPT_KERNEL_PLAN 0          /* tile -> first interval table */
+#define FPT_KERNEL_SCORE_FAST 1    /* fused scoring kernel of the detect/learn_dm geometry */
+#define FPT_KERNEL_WINDOW_FAST 2   /* multi-scale Stouffer windows over the flat z array */
+#define FPT_KERNEL_SCORE_GENERAL 3 /* fused scoring kernel, any geometry */
+#define FPT_KERNEL_COUNT 4
+int fpt_ctx_profile(fpt_ctx *ctx, int enable);
+int fpt_ctx_profile_read(fpt_ctx *ctx, double *total_ms, int64_t *launches);
+
 /* ---- models ------------------------------------------------------------------------------- */
 
 /* Replaces bias_model.__getitem__/kmer_model.probs (footprint_tools/modeling/bias.py:16-17,88-111)
