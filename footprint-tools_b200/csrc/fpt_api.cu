@@ -78,7 +78,10 @@ struct fpt_ctx {
     int64_t launches = 0;
     size_t score_smem_prepared = 0;
     bool fast_prepared = false;
-    int force_general = 0;  // FPT_B200_GENERAL=1: route everything through the general kernel
+    int force_general = 0;  // FPT_B200_GENERAL=1 / FPT_B200_PATH=general: route everything through the general kernel
+    int allow_fused = 1;    // FPT_B200_PATH=fast: skip the fused kernel (two-kernel throughput path instead)
+    bool fused_prepared = false;
+    DevBuf redo;            // [0] = count, [1..] = tiles the fused kernel handed to the general kernel
     // scratch
     DevBuf plan, scratch;
     DevBuf h_in[8], h_out[8];  // staging for FPT_MEM_HOST calls
@@ -194,6 +197,9 @@ int fpt_ctx_create(int device, fpt_ctx **out) {
     CU(cudaMemset(c->d_status, 0, sizeof(int)));
     const char *force = getenv("FPT_B200_GENERAL");
     c->force_general = (force && force[0] == '1') ? 1 : 0;
+    const char *path = getenv("FPT_B200_PATH");
+    if (path && !strcmp(path, "general")) c->force_general = 1;
+    if (path && !strcmp(path, "fast")) c->allow_fused = 0;
     *out = c;
     return FPT_OK;
 }
@@ -208,6 +214,7 @@ int fpt_ctx_destroy(fpt_ctx *ctx) {
     cudaFree(ctx->d_status);
     ctx->plan.release();
     ctx->scratch.release();
+    ctx->redo.release();
     for (auto &b : ctx->h_in) b.release();
     for (auto &b : ctx->h_out) b.release();
     for (auto &s : ctx->prof_pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -385,6 +392,68 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     // (per-strand outputs, other window half-widths, deeper trimming) runs on the general kernel.
     const bool fast = !ctx->force_general && p.combine && hw == kFastHalfWin && (shw == 0 || shw >= 4) && ktrim <= 1 &&
                       wh_max <= kFastMaxScaleHalfWin && !a->win_out;
+    // The fused kernel serves the two geometries the reference's programs use (cli/detect.py defaults:
+    // smoothing half-width 50 with one value trimmed per side; cli/learn_dm.py: no smoothing).
+    const bool fused = fast && ctx->allow_fused && ((shw == 50 && ktrim == 1) || shw == 0);
+    if (fused) {
+        auto al = [](const void *q, unsigned m) { return (reinterpret_cast<uintptr_t>(q) & m) == 0; };
+        p.wh_max = wh_max;
+        p.tile = kFastCCap - 40 - 2 * wh_max;
+        p.n_tiles = (a->total + p.tile - 1) / p.tile;
+        if (p.n_tiles > 0x7FFFFFFFLL) return fail(FPT_ERR_ARG, "fpt_score: too many tiles");
+        p.vec_ok = al(a->exp_out, 31) && al(a->obs_out, 31) && al(a->pval_out, 31);
+        p.cuts_vec = al(a->cuts_plus, 15) && al(a->cuts_minus, 15);
+        if (a->winp_out) {
+            for (int s = 0; s < a->n_scales; ++s) {
+                if (al(a->winp_out + (size_t)s * (size_t)a->total, 31)) p.winp_vec |= 1u << s;
+                p.h_rows[p.whw[s]] |= 1u << s;
+            }
+        }
+        for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) p.inv_sqrt_k[h] = 1.0 / std::sqrt((double)(2 * h + 1));
+        CU(ctx->plan.need((size_t)p.n_tiles * sizeof(int)));
+        CU(ctx->redo.need(((size_t)p.n_tiles + 1) * sizeof(int)));
+        p.tile_first_iv = ctx->plan.as<int>();
+        p.redo_count = ctx->redo.as<int>();
+        p.redo_list = ctx->redo.as<int>() + 1;
+        CU(cudaMemsetAsync(p.redo_count, 0, sizeof(int), ctx->stream));
+        {
+            ProfScope ps(ctx, FPT_KERNEL_PLAN);
+            CU(launch_plan(ctx->stream, p.out_off, p.n_iv, p.total, p.tile, p.n_tiles, ctx->plan.as<int>()));
+        }
+        ctx->launches++;
+        const size_t smem = score_fused_smem_bytes();
+        if (!ctx->fused_prepared) {
+            CU(score_fused_prepare(smem));
+            ctx->fused_prepared = true;
+        }
+        const int per_sm = score_fused_blocks_per_sm(smem, shw != 0);
+        if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: fused kernel does not fit on an SM (smem %zu)", smem);
+        long long grid = (long long)ctx->sm_count * per_sm;
+        if (grid > p.n_tiles) grid = p.n_tiles;
+        {
+            ProfScope ps(ctx, FPT_KERNEL_SCORE_FUSED);
+            CU(launch_score_fused(ctx->stream, p, (int)grid, shw != 0));
+        }
+        ctx->launches++;
+        // tiles with cut counts beyond the packed 16-bit window format: rescored by the general kernel
+        // (same tiling, list mode; exits at once when the list is empty)
+        ScoreParams q = p;
+        q.tile_list = p.redo_list;
+        q.n_list = p.redo_count;
+        const size_t gsmem = score_smem_bytes(hw, q.uniform != 0);
+        if (gsmem > ctx->score_smem_prepared) {
+            CU(score_kernel_prepare(gsmem));
+            ctx->score_smem_prepared = gsmem;
+        }
+        long long rgrid = ctx->sm_count;
+        if (rgrid > p.n_tiles) rgrid = p.n_tiles;
+        {
+            ProfScope ps(ctx, FPT_KERNEL_REDO);
+            CU(launch_score(ctx->stream, q, (int)rgrid));
+        }
+        ctx->launches++;
+        return FPT_OK;
+    }
     WindowParams wp;
     memset(&wp, 0, sizeof wp);
     const bool windows = fast && a->winp_out && a->n_scales > 0;

@@ -34,353 +34,11 @@
 //  * Stouffer sums are accumulated outward from the centre instead of left to right (|dS| ~ 1e-15,
 //    invisible at the 1e-9 tolerance on -log10 p; inf/NaN propagation is order-independent) and the
 //    normal tail uses the reference's own Cephes rationals (ndtr.c) with one exp(-x^2/2).
-#include <cuda_runtime.h>
-#include <math_constants.h>
-
-#include "fpt_internal.h"
-#include "fpt_math.cuh"
+#include "fpt_tile.cuh"
 
 namespace fpt {
 
 namespace {
-
-constexpr int kFT = kFastThreads;       // threads per CTA
-constexpr int kCCap = kFastCCap;        // c-space capacity (4 per thread)
-constexpr int kXCap = kFastXCap;        // x-space capacity
-constexpr int kNG = kXCap / 4;          // groups of 4 slots
-constexpr int kFReg = 16;               // regions per sub-tile
-constexpr int kXPad = 16;               // zero/scratch slots before and after the slot arrays
-
-struct FastRegions {
-    long long G0[kFReg];    // track coordinate of slot x  = x + G0
-    long long F0[kFReg];    // flat output index of c      = c + F0   (F0 % 4 == 0)
-    long long T0[kFReg];    // interval-local index of c   = c + T0
-    long long len[kFReg];   // interval length
-    long long fa[kFReg], fb[kFReg];  // flat output range written by this region
-    int cblk[kFReg + 1];    // c-space block prefix (multiples of 4)
-    int xblk[kFReg + 1];    // x-space block prefix (multiples of 4)
-    int cb[kFReg], cn[kFReg];
-    int D[kFReg];           // x = c + D  (D % 4 == 0)
-    int nreg;
-    long long next_cur, next_k;
-    unsigned wtot[2][2][kFT / 32];
-};
-
-template <int N>
-__device__ __forceinline__ double cpoly(double x, const double *c) {
-    double a = c[0];
-#pragma unroll
-    for (int i = 1; i < N; ++i) a = fma(a, x, c[i]);
-    return a;
-}
-template <int N>
-__device__ __forceinline__ double cpoly1(double x, const double *c) {
-    double a = x + c[0];
-#pragma unroll
-    for (int i = 1; i < N; ++i) a = fma(a, x, c[i]);
-    return a;
-}
-
-// 1/d for finite normal d, full double precision (two Newton steps on MUFU.RCP64H)
-__device__ __forceinline__ double fast_rcp(double d) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
-
-// ---- normal lower tail for the Stouffer windows ------------------------------------------------
-// ndtr(a) = Phi(a) (reference: hcephes_ndtr, ndtr.c:34-59). For |a| < 26 it is evaluated as
-//   Q(t) = exp(-t^2/2) * F(u),  t = |a|,  u = (t - 5)/(t + 5),  F = 0.5*erfcx(t/sqrt 2)
-// with F a degree-16 polynomial (Chebyshev fit generated by tools/fit_ndtr.py against mpmath; max
-// relative error of Q over [0, 26]: 3.5e-13, i.e. < 2e-13 on -log10 p — the bar is 1e-9) and a
-// table-free exp (Cody-Waite reduction + degree-11 Taylor polynomial, |r| <= ln2/2). One branch-free
-// path for every lane instead of Cephes' three ranges. |a| >= 26 (p < 1e-149), infinities and NaN
-// go to the branch-for-branch Cephes replica ndtr_fn (fpt_math.cuh), which also reproduces the
-// reference's denormal exp(-a^2) behaviour above |a| = 26.6 and its NaN for infinite arguments.
-__constant__ double kNdF[17] = {8.34755278698498880e-08,  1.85387184289488118e-07,  -7.05646170130192722e-07,
-                                -1.23208123023565909e-06, 6.67121890420153935e-06,  9.47978503161857321e-07,
-                                -6.04384263432253854e-05, 1.34279562238030851e-04,  2.19553084872871904e-04,
-                                -2.37884470097069183e-03, 8.99137029253909911e-03,  -2.34139004594596037e-02,
-                                4.78553522966640513e-02,  -8.08838772654492111e-02, 1.16068811885835940e-01,
-                                -1.43457555263989955e-01, 7.69193049750059588e-02};
-__constant__ double kExpT[12] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
-                                 1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,           1.0,          1.0};
-
-__device__ __noinline__ double ndtr_slow(double a) { return ndtr_fn(a); }
-
-// branch-free core: Phi(-t) for 0 <= t < 26 (callers clamp; the clamped lanes are recomputed by ndtr_slow)
-__device__ __forceinline__ double ndtr_tail_core(double t) {
-    double r;
-    {
-        const double d = t + 5.0;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-        const double e = fma(-d, r, 1.0);
-        r = fma(r, e, r);  // 1/(t+5), relative error ~1e-14
-    }
-    const double u = fma(-10.0, r, 1.0);
-    const double F = cpoly<17>(u, kNdF);
-    // exp(-t^2/2)
-    const double y = -0.5 * (t * t);
-    const double kf = fma(y, 1.4426950408889634, 6755399441055744.0);
-    const int n = __double2loint(kf);
-    const double nf = kf - 6755399441055744.0;
-    double q = fma(nf, -6.93147180369123816490e-01, y);
-    q = fma(nf, -1.90821492927058770002e-10, q);
-    const double pe = cpoly<12>(q, kExpT);
-    const double E = __hiloint2double(__double2hiint(pe) + (n << 20), __double2loint(pe));
-    return E * F;
-}
-
-__device__ __forceinline__ int fregion_of(const int *bases, int nreg, int v) {
-    int r = 0;
-#pragma unroll 4
-    for (int j = 1; j < nreg; ++j) r += (v >= bases[j]) ? 1 : 0;
-    return r;
-}
-
-__device__ __forceinline__ unsigned frevcomp12(unsigned x) {
-    unsigned r = __brev(x) >> 20;
-    r = ((r & 0xAAAu) >> 1) | ((r & 0x555u) << 1);
-    return r ^ 0xFFFu;
-}
-
-// `nbits` (<= 32) bits starting at bit `bit0` of a packed little-endian u32 array of `nwords`;
-// bits beyond the array read as `fill`.
-__device__ __forceinline__ unsigned ffetch_bits(const uint32_t *__restrict__ arr, long long nwords, long long bit0,
-                                               int nbits) {
-    long long w = bit0 >> 5;
-    int sh = (int)(bit0 & 31);
-    unsigned lo = (w >= 0 && w < nwords) ? __ldg(arr + w) : 0u;
-    unsigned hi = (w + 1 >= 0 && w + 1 < nwords) ? __ldg(arr + w + 1) : 0u;
-    unsigned v = __funnelshift_r(lo, hi, sh);
-    return nbits == 32 ? v : (v & ((1u << nbits) - 1u));
-}
-
-__device__ __forceinline__ void lds4(const uint32_t *p, unsigned (&v)[4]) {
-    const uint4 q = *reinterpret_cast<const uint4 *>(p);
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-}
-
-// 4 consecutive u32 starting at arbitrary slot `i` (k = i & 3 is warp-uniform): two aligned loads
-__device__ __forceinline__ void lds4_unaligned(const uint32_t *arr, int i, unsigned (&o)[4]) {
-    const int k = i & 3;
-    unsigned a[4], b[4];
-    lds4(arr + (i - k), a);
-    if (k == 0) {
-        o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = a[3];
-        return;
-    }
-    lds4(arr + (i - k + 4), b);
-    if (k == 1) { o[0] = a[1]; o[1] = a[2]; o[2] = a[3]; o[3] = b[0]; }
-    else if (k == 2) { o[0] = a[2]; o[1] = a[3]; o[2] = b[0]; o[3] = b[1]; }
-    else { o[0] = a[3]; o[1] = b[0]; o[2] = b[1]; o[3] = b[2]; }
-}
-
-// o[e] = s[k + e], k in 0..3 warp-uniform
-__device__ __forceinline__ void pick4(const unsigned (&s)[8], int k, unsigned (&o)[4]) {
-    if (k == 0) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; }
-    else if (k == 1) { o[0] = s[1]; o[1] = s[2]; o[2] = s[3]; o[3] = s[4]; }
-    else if (k == 2) { o[0] = s[2]; o[1] = s[3]; o[2] = s[4]; o[3] = s[5]; }
-    else { o[0] = s[3]; o[1] = s[4]; o[2] = s[5]; o[3] = s[6]; }
-}
-
-__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-
-// smoothing.h:11-53 on a thread-local buffer (exact path only)
-__device__ double fnr_select(double *arr, unsigned n, unsigned k) {
-    unsigned lo = 0, hi = n - 1;
-    for (;;) {
-        if (hi <= lo + 1) {
-            if (hi == lo + 1 && arr[hi] < arr[lo]) { double t = arr[lo]; arr[lo] = arr[hi]; arr[hi] = t; }
-            return arr[k];
-        }
-        unsigned mid = (lo + hi) >> 1;
-        double t;
-        t = arr[mid]; arr[mid] = arr[lo + 1]; arr[lo + 1] = t;
-        if (arr[lo] > arr[hi]) { t = arr[lo]; arr[lo] = arr[hi]; arr[hi] = t; }
-        if (arr[lo + 1] > arr[hi]) { t = arr[lo + 1]; arr[lo + 1] = arr[hi]; arr[hi] = t; }
-        if (arr[lo] > arr[lo + 1]) { t = arr[lo]; arr[lo] = arr[lo + 1]; arr[lo + 1] = t; }
-        unsigned i = lo + 1, j = hi;
-        double piv = arr[lo + 1];
-        for (;;) {
-            do i++; while (arr[i] < piv);
-            do j--; while (arr[j] > piv);
-            if (j < i) break;
-            t = arr[i]; arr[i] = arr[j]; arr[j] = t;
-        }
-        arr[lo + 1] = arr[j];
-        arr[j] = piv;
-        if (j >= k) hi = j - 1;
-        if (j <= k) lo = i;
-    }
-}
-
-// Bit-faithful trimmed_mean (smoothing.h:59-104) of wc[i0 .. i0+w)
-__device__ __noinline__ double ftrimmed_mean_exact(const uint32_t *wc, int i0, int w, int k) {
-    double buf[2 * kMaxSmoothHalfWin + 1];
-    for (int j = 0; j < w; ++j) buf[j] = (double)wc[i0 + j];
-    double os1 = fnr_select(buf, w, k);
-    double os2 = fnr_select(buf, w, w - k - 1);
-    double b = 0, d = 0, dm = 0, bm = 0;
-    for (int j = 0; j < w; ++j) {
-        double v = buf[j];
-        if (v < os1) bm += 1; else if (v == os1) b += 1;
-        if (v < os2) dm += 1; else if (v == os2) d += 1;
-    }
-    double w1 = __ddiv_rn(b + bm - (double)k, b);
-    double w2 = __ddiv_rn((double)(w - k) - dm, d);
-    double t = 0;
-    for (int j = 0; j < w; ++j) {
-        double v = buf[j], c;
-        if (v < os2 && v > os1) c = v;
-        else if (v < os1) c = 0;
-        else if (v > os2) c = 0;
-        else if (v == os1) c = __dmul_rn(w1, v);
-        else c = __dmul_rn(w2, v);
-        t = __dadd_rn(t, c);
-    }
-    return __ddiv_rn(t, (double)(w - 2 * k));
-}
-
-// propensity of the k-mer whose first base is track coordinate q (6 bases), forward or
-// reverse-complemented; any base outside the track or not ACGT gives the default
-struct SeqView {  // passed by value to the exact path (a reference to the kernel parameters would force a stack copy)
-    const uint32_t *seq2, *nmask;
-    long long n_track;
-    double dflt;
-    int uniform;
-};
-
-__device__ __noinline__ double fkmer_prop(SeqView P, const double *tab, long long q, int rc) {
-    if (P.uniform) return 1.0;
-    if (q < 0 || q + 6 > P.n_track) return P.dflt;
-    const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
-    unsigned nb = ffetch_bits(P.nmask, nwm, q, 6);
-    if (nb) return P.dflt;
-    unsigned km = ffetch_bits(P.seq2, nw2, 2 * q, 12);
-    return tab[rc ? frevcomp12(km) : km];
-}
-
-// The reference's own operation order for one strand position (predict.h:41-63): sequential window
-// of propensities, IEEE divide, smoothed count, multiply, round half away from zero.
-//   strand 0: position j uses k-mers starting at j-3; strand 1: reverse complement of j-2
-__device__ __noinline__ double fexpected_exact(SeqView P, const double *tab, const uint32_t *wc, int hw,
-                                               int shw, int ktrim, long long j, int slot, int strand) {
-    const int off = strand ? 2 : 3;
-    double wp = 0.0;
-    for (int m = -hw; m < hw; ++m) wp = __dadd_rn(wp, fkmer_prop(P, tab, j + m - off, strand));
-    const double ratio = __ddiv_rn(fkmer_prop(P, tab, j - off, strand), wp);
-    double sm;
-    if (shw == 0) {
-        sm = (double)wc[slot];
-    } else {
-        const int w = 2 * shw + 1;
-        unsigned long long sum = 0;
-        unsigned mn = 0xFFFFFFFFu, mx = 0;
-        for (int m = -shw; m <= shw; ++m) {
-            const unsigned v = wc[slot + m];
-            sum += v; mn = min(mn, v); mx = max(mx, v);
-        }
-        if (ktrim == 0) {
-            sm = __ddiv_rn((double)sum, (double)w);
-        } else {
-            // second tier: everything but the trimmed sum is now in the reference's own order; the integer
-            // trimmed sum differs from the reference's float one by < 1e-14 relative (tie weights)
-            const bool quirk = (sum - mn) == (unsigned long long)(w - 1) * (unsigned long long)mx;
-            const unsigned long long T = quirk ? (sum - mn) : (sum - mn - mx);
-            const double v = __dmul_rn(ratio, __ddiv_rn((double)T, (double)(w - 2)));
-            const double rr = rint(v), av = fabs(v);
-            if (ktrim == 1 && (av < 4.0e15) && (fabs(v - rr) < fma(av, -4e-12, 0.5 - 4e-12))) return rr;
-            sm = ftrimmed_mean_exact(wc, slot - shw, w, ktrim);
-        }
-    }
-    return round(__dmul_rn(ratio, sm));
-}
-
-// Region table of one sub-tile, built by warp 0 (lane l <-> interval k + l) for the sub-tile that
-// starts at flat index `cur` of tile [.., hi).
-__device__ __forceinline__ void build_regions(const ScoreParams &P, FastRegions *R, long long cur, long long hi,
-                                              long long k, int lane, int WH, int PADX, int PADR) {
-    const long long kk = k + lane;
-    const bool valid = lane < kFReg && kk < P.n_iv;
-    long long o0 = 0, o1 = 0, st = 0;
-    if (valid) {
-        o0 = __ldg(P.out_off + kk);
-        o1 = __ldg(P.out_off + kk + 1);
-        st = __ldg(P.iv_start + kk);
-    }
-    long long fa = o0 > cur ? o0 : cur;
-    long long fb = o1 < hi ? o1 : hi;
-    bool has = valid && fa < fb;
-    const long long len = o1 - o0;
-    long long ta = fa - o0 - WH; if (ta < 0) ta = 0;
-    long long tb = fb - o0 + WH; if (tb > len) tb = len;
-    int cn = has ? (int)(tb - ta) : 0;
-    const int lead = (int)((o0 + ta) & 3);
-    int cspan = has ? ((lead + cn + 3) & ~3) : 0;
-    int xspan = has ? cspan + PADX + PADR : 0;
-    int cs = cspan, xs = xspan;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int a = __shfl_up_sync(0xffffffffu, cs, d);
-        int b = __shfl_up_sync(0xffffffffu, xs, d);
-        if (lane >= d) { cs += a; xs += b; }
-    }
-    const bool over = has && (cs > kCCap || xs > kXCap);
-    const unsigned overmask = __ballot_sync(0xffffffffu, over);
-    const int first_over = overmask ? (__ffs(overmask) - 1) : 32;
-    const int cex = cs - cspan, xex = xs - xspan;
-    if (lane == first_over) {
-        int avail = kCCap - cex;
-        const int ax = kXCap - xex - PADX - PADR;
-        if (ax < avail) avail = ax;
-        avail &= ~3;
-        const int cn2 = avail - lead;
-        const long long fb2 = o0 + ta + cn2 - WH;
-        if (cn2 > 0 && fb2 > fa) {
-            fb = fb2; tb = ta + cn2; cn = cn2; cspan = avail; xspan = cspan + PADX + PADR;
-        } else {
-            has = false;
-        }
-    }
-    if (lane > first_over) has = false;
-    const unsigned incl = __ballot_sync(0xffffffffu, has);
-    const int r = __popc(incl & ((1u << lane) - 1u));
-    const int nreg = __popc(incl);
-    if (has) {
-        const int cb = cex + lead;
-        const int D = (xex - cex) + PADX;
-        R->cblk[r] = cex; R->xblk[r] = xex;
-        R->cb[r] = cb; R->cn[r] = cn; R->D[r] = D;
-        R->G0[r] = st + ta - cb - D;
-        R->F0[r] = o0 + ta - cb;
-        R->T0[r] = ta - cb;
-        R->len[r] = len;
-        R->fa[r] = fa; R->fb[r] = fb;
-    }
-    const int last = incl ? (31 - __clz(incl)) : -1;
-    if (lane == (last < 0 ? 0 : last)) {
-        if (last < 0) {
-            R->nreg = 0;
-            R->cblk[0] = R->xblk[0] = 0;
-            const long long nk = k + kFReg;
-            R->next_k = nk < P.n_iv ? nk : P.n_iv;
-            R->next_cur = (nk >= P.n_iv) ? hi : cur;
-        } else {
-            R->nreg = nreg;
-            R->cblk[nreg] = cex + cspan;
-            R->xblk[nreg] = xex + xspan;
-            R->next_cur = fb;
-            R->next_k = (fb == o1) ? kk + 1 : kk;
-        }
-    }
-}
 
 // Stouffer p-values of 4 consecutive positions at one half-width (windowing.h:53-67 with the edge
 // rule of windowing.pyx:51-54) and their stores into every output row that asked for this width.

@@ -57,6 +57,16 @@ struct ScoreParams {
     int vec_ok;            // exp/obs/pval output pointers are 32-byte aligned
     double *z_out;             // ndtri(1 - p) per scored position for the window kernel (or NULL)
     unsigned char *edge_out;   // min(t, len-1-t, 255) per scored position
+    // fused kernel only (fpt_fused.cu)
+    int cuts_vec;              // cuts_p / cuts_m are 16-byte aligned
+    int *redo_count;           // number of tiles appended to redo_list (cut counts beyond the packed range)
+    int *redo_list;            // n_tiles ints
+    unsigned winp_vec;                          // bit s: row s of winp_out is 32-byte aligned
+    unsigned h_rows[kFastMaxScaleHalfWin + 1];  // bit s of h_rows[h]: output row s has half-width h
+    double inv_sqrt_k[kFastMaxScaleHalfWin + 1];  // 1/sqrt(2h+1)
+    // general kernel in list mode: score tiles tile_list[0 .. *n_list) instead of 0 .. n_tiles
+    const int *tile_list;
+    const int *n_list;
 };
 
 // window kernel of the fast path (fpt_fast.cu)
@@ -77,6 +87,11 @@ cudaError_t launch_plan(cudaStream_t st, const long long *out_off, long long n_i
 cudaError_t launch_score(cudaStream_t st, const ScoreParams &p, int grid);
 cudaError_t score_kernel_prepare(size_t smem);
 int score_kernel_blocks_per_sm(size_t smem);
+
+size_t score_fused_smem_bytes();
+cudaError_t score_fused_prepare(size_t smem);
+int score_fused_blocks_per_sm(size_t smem, bool smooth);
+cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth);
 
 size_t score_fast_smem_bytes();
 cudaError_t score_fast_prepare(size_t smem);

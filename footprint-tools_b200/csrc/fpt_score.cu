@@ -30,8 +30,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
-#include "fpt_internal.h"
-#include "fpt_math.cuh"
+#include "fpt_tile.cuh"
 
 namespace fpt {
 
@@ -225,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
     double *dmp = reinterpret_cast<double *>(W + kStageCap);                  // 24
     RegionTable *R = reinterpret_cast<RegionTable *>(dmp + kModelDoubles);
 
+    if (P.tile_list && (long long)blockIdx.x >= (long long)*P.n_list) return;  // list mode: nothing for this CTA
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int hw = P.hw, shw = P.shw, ktrim = P.ktrim;
@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
     int pow2 = 1;
     while (pow2 * 2 <= wsm) pow2 *= 2;
 
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    // list mode (redo of the tiles the fused kernel could not carry): tiles tile_list[0 .. *n_list)
+    const long long n_work = P.tile_list ? (long long)*P.n_list : P.n_tiles;
+    for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+        const long long tile = P.tile_list ? (long long)P.tile_list[work] : work;
         const long long lo = tile * (long long)P.tile;
         const long long hi = (lo + P.tile < P.total) ? lo + P.tile : P.total;
         long long cur = lo;
@@ -555,6 +558,30 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
                 const long long f = R->flat0[r] + q;
                 if (f < sub_lo || f >= sub_hi) continue;
                 const long long t = R->t0[r] + q, len = R->ivlen[r];
+                if (P.tile_list) {
+                    // list mode = tiles handed back by the fused kernel: use that kernel's window arithmetic
+                    // (sums grown outward from the centre, branch-free normal tail) so that a position
+                    // carries the same bits whichever kernel scored its tile
+                    double acc = zs[c];
+                    for (int h = 0; h <= P.wh_max && h <= kFastMaxScaleHalfWin; ++h) {
+                        if (h > 0) acc += zs[c - h] + zs[c + h];
+                        const unsigned rows = P.h_rows[h];
+                        if (!rows) continue;
+                        double res = 1.0;
+                        if (t >= h && t < len - h) {
+                            const double a = acc * (-P.inv_sqrt_k[h]);
+                            const double ta = fabs(a);
+                            if (ta < 26.0) {
+                                const double tail = ndtr_tail_core(fmin(ta, 26.0));
+                                res = a > 0.0 ? 1.0 - tail : tail;
+                            } else {
+                                res = ndtr_slow(a);
+                            }
+                        }
+                        for (unsigned m = rows; m; m &= m - 1) P.winp_out[(size_t)(__ffs(m) - 1) * P.total + f] = res;
+                    }
+                    continue;
+                }
                 for (int s = 0; s < P.n_scales; ++s) {
                     const int h = P.whw[s];
                     double res = 1.0;

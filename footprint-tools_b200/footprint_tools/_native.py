@@ -182,7 +182,7 @@ class Context(object):
     def launches(self):
         return int(lib().fpt_ctx_launch_count(self._h))
 
-    KERNELS = ("plan", "score_fast", "window_fast", "score_general")
+    KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo")
 
     def profile(self, enable=True):
         """Turn the per-kernel CUDA-event timers on or off (fpt_ctx_profile)."""

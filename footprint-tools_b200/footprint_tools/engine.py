@@ -28,6 +28,27 @@ def counts_to_u32(a, what="cut counts"):
     return np.ascontiguousarray(f.astype(np.uint32))
 
 
+def aligned_block_offsets(block_len, out_off, lead):
+    """Track offsets of per-interval blocks such that the first scored position of every interval sits
+    at a track coordinate congruent (mod 4) to its output offset: block_off[k] + lead == out_off[k]
+    (mod 4). That congruence lets the scoring kernel stage cut counts with 16-byte loads and write its
+    outputs with 32-byte stores from the same lanes (csrc/fpt_fused.cu, phase 1); any layout is
+    accepted, this one is the fast one. Costs at most 3 filler positions per interval.
+    Returns (block_off[n+1], fill[n]) with fill[k] = filler positions inserted before block k."""
+    block_len = np.asarray(block_len, dtype=np.int64)
+    n = block_len.shape[0]
+    rho = (np.asarray(out_off[:n], dtype=np.int64) - lead) % 4       # wanted residue of block_off[k]
+    prev = np.concatenate([[0], (rho[:-1] + block_len[:-1]) % 4]) if n else np.zeros(0, dtype=np.int64)
+    fill = (rho - prev) % 4
+    block_off = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        ends = np.cumsum(block_len + fill)                  # end of block k (= start of filler k+1)
+        block_off[0] = fill[0]
+        block_off[1:-1] = ends[:-1] + fill[1:]
+        block_off[-1] = ends[-1]                            # track length
+    return block_off, fill
+
+
 class IntervalBatch(object):
     """Host-side packed batch: per-interval padded arrays laid back to back in one track.
 
@@ -36,13 +57,17 @@ class IntervalBatch(object):
     counts per strand (read_func[padded interval], predict.pyx:136) placed 3 positions in.
     """
 
-    def __init__(self, seq2, nmask, cuts_plus, cuts_minus, n_track, iv_start, out_off, block_off):
+    def __init__(self, seq2, nmask, cuts_plus, cuts_minus, n_track, iv_start, out_off, block_off, block_len=None):
         self.seq2, self.nmask = seq2, nmask
         self.cuts_plus, self.cuts_minus = cuts_plus, cuts_minus
         self.n_track = int(n_track)
         self.iv_start = np.ascontiguousarray(iv_start, dtype=np.int64)
         self.out_off = np.ascontiguousarray(out_off, dtype=np.int64)
         self.block_off = np.ascontiguousarray(block_off, dtype=np.int64)
+        # block k occupies [block_off[k], block_off[k] + block_len[k]); up to 3 filler positions may
+        # precede it (block_off[-1] is the track length)
+        self.block_len = np.ascontiguousarray(
+            np.diff(self.block_off) if block_len is None else block_len, dtype=np.int64)
 
     @property
     def n_iv(self):
@@ -66,9 +91,13 @@ class IntervalBatch(object):
                 raise ValueError("interval %d: strand arrays differ in length" % k)
             if len(seqs[k]) != L[k] + 6:
                 raise ValueError("interval %d: sequence has %d characters, expected %d" % (k, len(seqs[k]), L[k] + 6))
-        blk = L + 6
-        block_off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(blk, out=block_off[1:])
+        out_len = L - 2 * pad - (0 if per_strand else 1)
+        if np.any(out_len < 0):
+            raise ValueError("interval shorter than its padding")
+        out_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(out_len, out=out_off[1:])
+        lead = 3 + pad + (0 if per_strand else 1)       # block start -> first scored position
+        block_off, fill = aligned_block_offsets(L + 6, out_off, lead)
         n_track = int(block_off[-1])
         cp = np.zeros(n_track, dtype=np.uint32)
         cm = np.zeros(n_track, dtype=np.uint32)
@@ -76,14 +105,15 @@ class IntervalBatch(object):
             o = block_off[k] + 3
             cp[o:o + L[k]] = counts_to_u32(cuts_plus[k])
             cm[o:o + L[k]] = counts_to_u32(cuts_minus[k])
-        seq2, nmask = _native.pack_sequence("".join(seqs))
-        out_len = L - 2 * pad - (0 if per_strand else 1)
-        if np.any(out_len < 0):
-            raise ValueError("interval shorter than its padding")
-        out_off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(out_len, out=out_off[1:])
-        iv_start = block_off[:-1] + 3 + pad + (0 if per_strand else 1)
-        return IntervalBatch(seq2, nmask, cp, cm, n_track, iv_start, out_off, block_off)
+        # filler bases between blocks read as N
+        parts = []
+        for k in range(n):
+            if fill[k]:
+                parts.append("N" * int(fill[k]))
+            parts.append(seqs[k])
+        seq2, nmask = _native.pack_sequence("".join(parts))
+        iv_start = block_off[:-1] + lead
+        return IntervalBatch(seq2, nmask, cp, cm, n_track, iv_start, out_off, block_off, block_len=L + 6)
 
     def to_device(self, device):
         """Device-resident copy (torch tensors; uint32 payloads carried as int32)."""

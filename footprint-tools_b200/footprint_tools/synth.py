@@ -56,7 +56,8 @@ def codes_to_str(codes):
     return np.array(list("ACGTN"), dtype="U1")[np.minimum(codes, 4)].astype("S1").tobytes().decode("ascii")
 
 
-def make_batch(n_iv, pad, seed, table=None, fixed_len=None, depth_scale=1.0, per_strand=False, n_frac=0.001):
+def make_batch(n_iv, pad, seed, table=None, fixed_len=None, depth_scale=1.0, per_strand=False, n_frac=0.001,
+               aligned=True):
     """Synthetic IntervalBatch of n_iv intervals (each with its own padded block, as the reference's
     per-interval reads would deliver them). Returns (batch, info) where info holds the raw pieces
     (codes, lengths) for oracle-side checks."""
@@ -66,8 +67,15 @@ def make_batch(n_iv, pad, seed, table=None, fixed_len=None, depth_scale=1.0, per
     lens = interval_lengths(n_iv, rng, fixed_len)
     L = lens + 2 * pad + 1
     blk = L + 6
-    block_off = np.zeros(n_iv + 1, dtype=np.int64)
-    np.cumsum(blk, out=block_off[1:])
+    out_len = L - 2 * pad - (0 if per_strand else 1)
+    out_off = np.zeros(n_iv + 1, dtype=np.int64)
+    np.cumsum(out_len, out=out_off[1:])
+    lead = 3 + pad + (0 if per_strand else 1)
+    if aligned:
+        block_off, fill = engine.aligned_block_offsets(blk, out_off, lead)
+    else:
+        block_off = np.zeros(n_iv + 1, dtype=np.int64)
+        np.cumsum(blk, out=block_off[1:])
     n = int(block_off[-1])
     # genome
     codes = rng.choice(4, size=n, p=[0.29, 0.21, 0.21, 0.29]).astype(np.uint8)
@@ -86,7 +94,10 @@ def make_batch(n_iv, pad, seed, table=None, fixed_len=None, depth_scale=1.0, per
         idx[3:n - 3] = idx[3:n - 3] * 4 + c4[j:n - 6 + j]
     prop = table[idx] / table.mean()
     # per-interval depth and triangular profile
-    iv = np.repeat(np.arange(n_iv), blk)
+    # position -> (interval, offset in its block); filler positions before a block get a negative offset
+    ends = block_off[:-1] + blk                             # end of block k; its filler precedes it
+    span = np.diff(np.concatenate([[0], ends]))
+    iv = np.repeat(np.arange(n_iv), span)
     x = np.arange(n, dtype=np.int64) - block_off[iv]
     half = blk[iv] / 2.0
     profile = 1.0 + 2.0 * (1.0 - np.abs(x - half) / half)
@@ -103,16 +114,14 @@ def make_batch(n_iv, pad, seed, table=None, fixed_len=None, depth_scale=1.0, per
     rate[np.cumsum(d[:-1]) > 0] *= 0.2
     cp = rng.poisson(rate).astype(np.uint32)
     cm = rng.poisson(rate).astype(np.uint32)
-    # the 3 positions at both ends of every block hold sequence only
+    # the 3 positions at both ends of every block hold sequence only; filler holds nothing
     edge = (x < 3) | (x >= (blk[iv] - 3))
+    codes[x < 0] = 4
     cp[edge] = 0
     cm[edge] = 0
     seq2, nmask = pack_codes(codes)
-    out_len = L - 2 * pad - (0 if per_strand else 1)
-    out_off = np.zeros(n_iv + 1, dtype=np.int64)
-    np.cumsum(out_len, out=out_off[1:])
-    iv_start = block_off[:-1] + 3 + pad + (0 if per_strand else 1)
-    batch = engine.IntervalBatch(seq2, nmask, cp, cm, n, iv_start, out_off, block_off)
+    iv_start = block_off[:-1] + lead
+    batch = engine.IntervalBatch(seq2, nmask, cp, cm, n, iv_start, out_off, block_off, block_len=blk)
     return batch, {"codes": codes, "lengths": lens, "pad": pad, "table": table}
 
 
@@ -121,14 +130,18 @@ def oracle_inputs(batch, info):
     base, float64 cut counts without the 3-base sequence margins; in_off[k] = offset of interval k in
     the cut arrays (its sequence starts at in_off[k] + 6k)."""
     codes = info["codes"]
-    seq = codes_to_str(codes)
-    bo = batch.block_off
+    bo, bl = batch.block_off, batch.block_len
     n_iv = batch.n_iv
-    keep = np.ones(batch.n_track, dtype=bool)
+    inblock = np.zeros(batch.n_track + 1, dtype=np.int32)   # 1 inside a block, 0 on filler
+    np.add.at(inblock, bo[:-1], 1)
+    np.add.at(inblock, bo[:-1] + bl, -1)
+    inblock = np.cumsum(inblock[:-1]) > 0
+    seq = codes_to_str(codes[inblock])
+    keep = inblock.copy()
     for d in range(3):
         keep[bo[:-1] + d] = False
-        keep[bo[1:] - 1 - d] = False
+        keep[bo[:-1] + bl - 1 - d] = False
     cp = batch.cuts_plus[keep].astype(np.float64)
     cm = batch.cuts_minus[keep].astype(np.float64)
-    in_off = (bo - 6 * np.arange(n_iv + 1)).astype(np.int64)
+    in_off = np.concatenate([[0], np.cumsum(bl - 6)]).astype(np.int64)
     return seq, cp, cm, in_off

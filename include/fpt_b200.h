@@ -78,10 +78,12 @@ int64_t fpt_ctx_launch_count(const fpt_ctx *ctx);
  * then read: total_ms / launches are FPT_KERNEL_COUNT-long HOST arrays indexed by FPT_KERNEL_*;
  * reading synchronises the stream and resets the totals. */
 #define FPT_KERNEL_PLAN 0          /* tile -> first interval table */
-#define FPT_KERNEL_SCORE_FAST 1    /* fused scoring kernel of the detect/learn_dm geometry */
+#define FPT_KERNEL_SCORE_FAST 1    /* two-kernel throughput path: scoring kernel */
 #define FPT_KERNEL_WINDOW_FAST 2   /* multi-scale Stouffer windows over the flat z array */
-#define FPT_KERNEL_SCORE_GENERAL 3 /* fused scoring kernel, any geometry */
-#define FPT_KERNEL_COUNT 4
+#define FPT_KERNEL_SCORE_GENERAL 3 /* scoring kernel, any geometry */
+#define FPT_KERNEL_SCORE_FUSED 4   /* single-launch scoring + windows kernel of the detect/learn_dm geometry */
+#define FPT_KERNEL_REDO 5          /* general kernel over the tiles the fused kernel handed back */
+#define FPT_KERNEL_COUNT 6
 int fpt_ctx_profile(fpt_ctx *ctx, int enable);
 int fpt_ctx_profile_read(fpt_ctx *ctx, double *total_ms, int64_t *launches);
 
