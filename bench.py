@@ -287,7 +287,7 @@ def main():
     # between them is overhead, not algorithmic traffic. `achieved` is reported for the dominant
     # kernel from its own event-timed launches, and for the whole path in `path`.
     alg = {"score_fused": BYTES_PER_BASE, "score_fast": 8.5 + 24.0, "window_fast": 8.0 * len(SCALES),
-           "score_general": BYTES_PER_BASE, "plan": 0.0, "redo": 0.0}
+           "score_general": BYTES_PER_BASE, "plan": 0.0, "redo": 0.0, "direct_fix": 0.0}
     per_kernel = {}
     for name, (tot_ms, n) in kern.items():
         if n:
@@ -305,7 +305,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD % args.intervals, "bases_per_step_per_gpu": total,
                    "l2_policy": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % ((h2d + d2h) / 1e9),
-                   "nb_cdf": "direct" if args.no_lut else "device-built (exp,obs) table 256x512 + direct fallback",
+                   "nb_cdf": "direct" if args.no_lut else "device-built (exp,obs) table %dx%d + deferred direct evaluation" % _native.DEFAULT_LUT + "",
                    "parallelism": "intervals sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": TRAFFIC.get(dominant), "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs, burst)" % peak_src,

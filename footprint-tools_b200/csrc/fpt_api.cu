@@ -80,7 +80,9 @@ struct fpt_ctx {
     bool fast_prepared = false;
     int force_general = 0;  // FPT_B200_GENERAL=1 / FPT_B200_PATH=general: route everything through the general kernel
     int allow_fused = 1;    // FPT_B200_PATH=fast: skip the fused kernel (two-kernel throughput path instead)
+    int fused_inwin = 0;    // FPT_B200_FUSED_WIN=1: Stouffer windows inside the fused kernel instead of the streaming kernel
     bool fused_prepared = false;
+    DevBuf direct;          // [count | list] of positions whose NB p-value is evaluated by direct_fix_kernel
     DevBuf redo;            // [0] = count, [1..] = tiles the fused kernel handed to the general kernel
     // scratch
     DevBuf plan, scratch;
@@ -200,6 +202,8 @@ int fpt_ctx_create(int device, fpt_ctx **out) {
     const char *path = getenv("FPT_B200_PATH");
     if (path && !strcmp(path, "general")) c->force_general = 1;
     if (path && !strcmp(path, "fast")) c->allow_fused = 0;
+    const char *inw = getenv("FPT_B200_FUSED_WIN");
+    c->fused_inwin = (inw && inw[0] == '1') ? 1 : 0;
     *out = c;
     return FPT_OK;
 }
@@ -215,6 +219,7 @@ int fpt_ctx_destroy(fpt_ctx *ctx) {
     ctx->plan.release();
     ctx->scratch.release();
     ctx->redo.release();
+    ctx->direct.release();
     for (auto &b : ctx->h_in) b.release();
     for (auto &b : ctx->h_out) b.release();
     for (auto &s : ctx->prof_pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -397,47 +402,79 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     const bool fused = fast && ctx->allow_fused && ((shw == 50 && ktrim == 1) || shw == 0);
     if (fused) {
         auto al = [](const void *q, unsigned m) { return (reinterpret_cast<uintptr_t>(q) & m) == 0; };
-        p.wh_max = wh_max;
+        const bool windows = a->winp_out && a->n_scales > 0;
+        const bool inwin = windows && ctx->fused_inwin;   // windows inside the kernel (else the streaming kernel follows)
+        p.wh_max = inwin ? wh_max : 0;
         p.tile = kFastCCap - 40 - 2 * wh_max;
         p.n_tiles = (a->total + p.tile - 1) / p.tile;
         if (p.n_tiles > 0x7FFFFFFFLL) return fail(FPT_ERR_ARG, "fpt_score: too many tiles");
         p.vec_ok = al(a->exp_out, 31) && al(a->obs_out, 31) && al(a->pval_out, 31);
         p.cuts_vec = al(a->cuts_plus, 15) && al(a->cuts_minus, 15);
-        if (a->winp_out) {
+        if (windows) {
             for (int s = 0; s < a->n_scales; ++s) {
                 if (al(a->winp_out + (size_t)s * (size_t)a->total, 31)) p.winp_vec |= 1u << s;
                 p.h_rows[p.whw[s]] |= 1u << s;
             }
         }
         for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) p.inv_sqrt_k[h] = 1.0 / std::sqrt((double)(2 * h + 1));
+        WindowParams wq;
+        memset(&wq, 0, sizeof wq);
+        if (windows && !inwin) {
+            // scratch: [8 pad | z(total) | pad] doubles, then the edge bytes
+            const size_t zdoubles = ((size_t)a->total + 16 + 3) & ~(size_t)3;
+            CU(ctx->scratch.need(zdoubles * sizeof(double) + (((size_t)a->total + 7) & ~(size_t)3)));
+            double *zbase = ctx->scratch.as<double>();
+            CU(cudaMemsetAsync(zbase, 0, 8 * sizeof(double), ctx->stream));
+            CU(cudaMemsetAsync(zbase + 8 + a->total, 0, (zdoubles - 8 - (size_t)a->total) * sizeof(double), ctx->stream));
+            p.z_out = zbase + 8;
+            p.edge_out = reinterpret_cast<unsigned char *>(zbase + zdoubles);
+            wq.z = p.z_out; wq.edge = p.edge_out; wq.total = a->total; wq.winp_out = a->winp_out; wq.wh_max = wh_max;
+            wq.winp_vec = p.winp_vec;
+            for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
+                wq.h_rows[h] = p.h_rows[h];
+                wq.inv_sqrt_k[h] = p.inv_sqrt_k[h];
+            }
+        }
         CU(ctx->plan.need((size_t)p.n_tiles * sizeof(int)));
         CU(ctx->redo.need(((size_t)p.n_tiles + 1) * sizeof(int)));
         p.tile_first_iv = ctx->plan.as<int>();
         p.redo_count = ctx->redo.as<int>();
         p.redo_list = ctx->redo.as<int>() + 1;
         CU(cudaMemsetAsync(p.redo_count, 0, sizeof(int), ctx->stream));
+        // positions outside the (exp, obs) table: listed by the scoring kernel, evaluated by direct_fix_kernel.
+        // Only with a table (without one every base is evaluated where it is scored) and only when z goes
+        // through global memory anyway.
+        const bool defer = !inwin && ctx->lut_e > 0 && (a->pval_out || windows);
+        if (defer) {
+            const size_t cap = (size_t)a->total / 8 + 4096;
+            CU(ctx->direct.need(16 + cap * sizeof(int4)));
+            p.direct_count = ctx->direct.as<int>();
+            p.direct_list = reinterpret_cast<int4 *>(ctx->direct.as<char>() + 16);
+            p.direct_cap = (int)(cap > 0x7FFFFFF0u ? 0x7FFFFFF0u : cap);
+            CU(cudaMemsetAsync(p.direct_count, 0, sizeof(int), ctx->stream));
+        }
         {
             ProfScope ps(ctx, FPT_KERNEL_PLAN);
             CU(launch_plan(ctx->stream, p.out_off, p.n_iv, p.total, p.tile, p.n_tiles, ctx->plan.as<int>()));
         }
         ctx->launches++;
-        const size_t smem = score_fused_smem_bytes();
         if (!ctx->fused_prepared) {
-            CU(score_fused_prepare(smem));
+            CU(score_fused_prepare());
             ctx->fused_prepared = true;
         }
-        const int per_sm = score_fused_blocks_per_sm(smem, shw != 0);
-        if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: fused kernel does not fit on an SM (smem %zu)", smem);
+        const int per_sm = score_fused_blocks_per_sm(shw != 0, inwin);
+        if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: fused kernel does not fit on an SM");
         long long grid = (long long)ctx->sm_count * per_sm;
         if (grid > p.n_tiles) grid = p.n_tiles;
         {
             ProfScope ps(ctx, FPT_KERNEL_SCORE_FUSED);
-            CU(launch_score_fused(ctx->stream, p, (int)grid, shw != 0));
+            CU(launch_score_fused(ctx->stream, p, (int)grid, shw != 0, inwin));
         }
         ctx->launches++;
         // tiles with cut counts beyond the packed 16-bit window format: rescored by the general kernel
         // (same tiling, list mode; exits at once when the list is empty)
         ScoreParams q = p;
+        q.wh_max = wh_max;
         q.tile_list = p.redo_list;
         q.n_list = p.redo_count;
         const size_t gsmem = score_smem_bytes(hw, q.uniform != 0);
@@ -452,6 +489,16 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
             CU(launch_score(ctx->stream, q, (int)rgrid));
         }
         ctx->launches++;
+        if (defer) {
+            ProfScope ps(ctx, FPT_KERNEL_DIRECT_FIX);
+            CU(launch_direct_fix(ctx->stream, p, ctx->sm_count));
+            ctx->launches++;
+        }
+        if (windows && !inwin) {
+            ProfScope ps(ctx, FPT_KERNEL_WINDOW_FAST);
+            CU(launch_window_fast(ctx->stream, wq, ctx->sm_count));
+            ctx->launches++;
+        }
         return FPT_OK;
     }
     WindowParams wp;

@@ -40,44 +40,6 @@ namespace fpt {
 
 namespace {
 
-// Stouffer p-values of 4 consecutive positions at one half-width (windowing.h:53-67 with the edge
-// rule of windowing.pyx:51-54) and their stores into every output row that asked for this width.
-// edge4 holds, per position, min(t, len-1-t, 255) with t the interval-local index.
-__device__ __noinline__ void emit_scale(double a0, double a1, double a2, double a3, int h, double cneg, unsigned rows,
-                                        unsigned winp_vec, double *winp_out, long long total, unsigned edge4,
-                                        long long f0, unsigned omask) {
-    // four independent evaluations, interleaved by the compiler (no per-element branches)
-    const double av[4] = {a0 * cneg, a1 * cneg, a2 * cneg, a3 * cneg};
-    double res[4];
-    bool slow = false;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const double t = fabs(av[e]);
-        slow |= !(t < 26.0);
-        const double tail = ndtr_tail_core(fmin(t, 26.0));
-        res[e] = av[e] > 0.0 ? 1.0 - tail : tail;
-    }
-    if (slow) {  // |a| >= 26, infinite or NaN: the Cephes replica (rare)
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (!(fabs(av[e]) < 26.0)) res[e] = ndtr_slow(av[e]);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-        if ((int)((edge4 >> (8 * e)) & 0xFFu) < h) res[e] = 1.0;  // closer than h to an interval end
-    for (unsigned m = rows; m; m &= m - 1) {
-        const int s = __ffs(m) - 1;
-        double *dst = winp_out + (size_t)s * total + f0;
-        if (omask == 0xFu && ((winp_vec >> s) & 1u)) {
-            st256(dst, res[0], res[1], res[2], res[3]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((omask >> e) & 1u) dst[e] = res[e];
-        }
-    }
-}
-
 __device__ __forceinline__ void ld256(const double *p, double &a, double &b, double &c, double &d) {
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
@@ -87,29 +49,75 @@ __device__ __forceinline__ void ld256(const double *p, double &a, double &b, dou
 // both sides and 32-byte aligned; a thread owns 4 consecutive positions and reads its +-8 halo with
 // five 256-bit loads (neighbouring threads overlap in L1). Windows never need interval geometry:
 // a window that would cross an interval end is exactly the one the edge rule sets to 1.0.
-__global__ void __launch_bounds__(256, 3) window_fast_kernel(const WindowParams W) {
+__global__ void __launch_bounds__(256, 2) window_fast_kernel(const WindowParams W) {
     const long long ngroups = (W.total + 3) >> 2;
+    unsigned want = 0;
+#pragma unroll
+    for (int h = 0; h <= kFastMaxScaleHalfWin; ++h)
+        if (W.h_rows[h]) want |= 1u << h;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups;
          g += (long long)gridDim.x * blockDim.x) {
         const long long f0 = g << 2;
-        double z[20];  // z[8 + e] is element e
-#pragma unroll
-        for (int q = 0; q < 5; ++q) ld256(W.z + f0 - 8 + 4 * q, z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
         const unsigned edge4 = __ldg(reinterpret_cast<const unsigned *>(W.edge) + g);
         const long long left = W.total - f0;
         const unsigned omask = left >= 4 ? 0xFu : ((1u << (int)left) - 1u);
-        double acc[4] = {z[8], z[9], z[10], z[11]};
-        // sums grow outward from the centre: S_h = S_{h-1} + z[-h] + z[+h]
+        // up to three requested half-widths per pass: their sums first (z dead afterwards), then the
+        // normal tails, four positions interleaved (ndtr4)
+        unsigned pending = want;
+        while (pending) {
+            int hq[3];
 #pragma unroll
-        for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
-            if (h > W.wh_max) break;
-            if (h > 0) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
+            for (int k = 0; k < 3; ++k) {
+                hq[k] = pending ? (__ffs(pending) - 1) : -1;
+                pending &= pending - 1;
             }
-            if (W.h_rows[h])
-                emit_scale(acc[0], acc[1], acc[2], acc[3], h, -W.inv_sqrt_k[h], W.h_rows[h], W.winp_vec, W.winp_out,
-                           W.total, edge4, f0, omask);
+            const int hlast = hq[2] >= 0 ? hq[2] : (hq[1] >= 0 ? hq[1] : hq[0]);
+            double A[3][4];
+            {
+                double z[20];  // z[8 + e] is element e
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    ld256(W.z + f0 - 8 + 4 * q, z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+                double acc[4] = {z[8], z[9], z[10], z[11]};
+                // sums grow outward from the centre: S_h = S_{h-1} + (z[-h] + z[+h])
+#pragma unroll
+                for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
+                    if (h > hlast) break;
+                    if (h > 0) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (hq[k] == h) {
+                            const double cneg = -W.inv_sqrt_k[h];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) A[k][e] = acc[e] * cneg;
+                        }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (hq[k] < 0) break;
+                const int h = hq[k];
+                double res[4];
+                ndtr4(A[k], res);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((int)((edge4 >> (8 * e)) & 0xFFu) < h) res[e] = 1.0;  // closer than h to an interval end
+                for (unsigned m = W.h_rows[h]; m; m &= m - 1) {
+                    const int s = __ffs(m) - 1;
+                    double *dst = W.winp_out + (size_t)s * W.total + f0;
+                    if (omask == 0xFu && ((W.winp_vec >> s) & 1u)) {
+                        reinterpret_cast<double2 *>(dst)[0] = make_double2(res[0], res[1]);
+                        reinterpret_cast<double2 *>(dst)[1] = make_double2(res[2], res[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if ((omask >> e) & 1u) dst[e] = res[e];
+                    }
+                }
+            }
         }
     }
 }

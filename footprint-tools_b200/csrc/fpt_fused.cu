@@ -76,29 +76,31 @@ __device__ __noinline__ double ftrimmed_mean_packed(const uint32_t *wcw, int str
     return __ddiv_rn(t, (double)(w - 2 * k));
 }
 
-// The reference's own operation order for one strand of one output position (predict.h:41-63).
-// j: track coordinate of the strand position, slot: its slot in wcw (same slot for both strands).
-__device__ __noinline__ double fexpected_packed(SeqView P, const double *tab, const uint32_t *wcw, int shw, long long j,
-                                                int slot, int strand) {
-    constexpr int hw = kFastHalfWin;
-    const int off = strand ? 2 : 3;
+// The reference's own operation order for one strand of one output position (predict.h:41-63), from
+// what the calling thread already holds: kw / rcw / nw = the 18-base window (codes, reverse complement, N
+// bits) whose k-mer m starts at base g0-8+m, e = element (0..3), T = its exact trimmed window sum.
+// The ten propensities of the window are k-mers e .. e+9, the position's own is k-mer e+5.
+__device__ __noinline__ double fexpected_packed(const double *tab, double dflt, int uniform, unsigned long long kw,
+                                                unsigned long long rcw, unsigned nw, int e, int strand, unsigned T,
+                                                const uint32_t *wcw, int slot, int shw) {
+    double pd[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int m = e + i;
+        const unsigned km = strand ? (unsigned)(rcw >> (24 - 2 * m)) & 0xFFFu : (unsigned)(kw >> (2 * m)) & 0xFFFu;
+        pd[i] = uniform ? 1.0 : (((nw >> m) & 0x3Fu) ? dflt : __ldg(tab + km));
+    }
     double wp = 0.0;
-    for (int m = -hw; m < hw; ++m) wp = __dadd_rn(wp, fkmer_prop(P, tab, j + m - off, strand));
-    const double ratio = __ddiv_rn(fkmer_prop(P, tab, j - off, strand), wp);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) wp = __dadd_rn(wp, pd[i]);
+    const double ratio = __ddiv_rn(pd[5], wp);
     double sm;
     if (shw == 0) {
-        sm = (double)(strand ? hi16(wcw[slot]) : lo16(wcw[slot]));
+        sm = (double)T;
     } else {
-        const int w = 2 * shw + 1;
-        unsigned sum = 0, mn = 0xFFFFFFFFu, mx = 0;
-        for (int m = -shw; m <= shw; ++m) {
-            const unsigned v = strand ? hi16(wcw[slot + m]) : lo16(wcw[slot + m]);
-            sum += v; mn = min(mn, v); mx = max(mx, v);
-        }
         // second tier: everything but the trimmed sum is in the reference's own order; the integer
         // trimmed sum differs from the reference's float one by < 1e-14 relative (tie weights)
-        const bool quirk = (sum - mn) == (unsigned)(w - 1) * mx;
-        const unsigned T = quirk ? (sum - mn) : (sum - mn - mx);
+        const int w = 2 * shw + 1;
         const double v = __dmul_rn(ratio, __ddiv_rn((double)T, (double)(w - 2)));
         const double rr = rint(v), av = fabs(v);
         if ((av < 4.0e15) && (fabs(v - rr) < fma(av, -4e-12, 0.5 - 4e-12))) return rr;
@@ -107,38 +109,41 @@ __device__ __noinline__ double fexpected_packed(SeqView P, const double *tab, co
     return round(__dmul_rn(ratio, sm));
 }
 
-// Stouffer p-values of 4 consecutive positions at one half-width (windowing.h:53-67 with the edge
-// rule of windowing.pyx:51-54) and their stores into every output row that asked for this width.
-// dl: interval-local index of element 0; dr: len - 1 - dl.
-__device__ __noinline__ void emit_scale_fused(double a0, double a1, double a2, double a3, int h, double cneg,
-                                              unsigned rows, unsigned winp_vec, double *winp_out, long long total,
-                                              long long dl, long long dr, long long f0, unsigned omask) {
-    const double av[4] = {a0 * cneg, a1 * cneg, a2 * cneg, a3 * cneg};
-    double res[4];
-    bool slow = false;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const double t = fabs(av[e]);
-        slow |= !(t < 26.0);
-        const double tail = ndtr_tail_core(fmin(t, 26.0));
-        res[e] = av[e] > 0.0 ? 1.0 - tail : tail;
+// NB p-values (and their z) of the positions whose (exp, obs) the table does not hold, deferred by the
+// scoring kernel so that a multi-thousand-instruction evaluation never stalls a whole CTA at a barrier.
+// Same device functions as the inline evaluation (dispersion.pyx:291-316 -> nbinom.pyx:121-138 -> incbet.c).
+__global__ void __launch_bounds__(128) direct_fix_kernel(const int4 *__restrict__ list, const int *__restrict__ count,
+                                                         int cap, const double *__restrict__ dm, double *pval_out,
+                                                         double *z_out) {
+    int n = *count;
+    if (n > cap) n = cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 v = list[i];
+        const long long f = (long long)(unsigned)v.x | ((long long)v.y << 32);
+        const double ex = (double)v.z;
+        const double rr = fit_r(dm + 9, ex), mu = fit_mu(dm, ex);
+        const double pv = nb_cdf(v.w, nb_prob(rr, mu), rr);
+        if (pval_out) pval_out[f] = pv;
+        if (z_out) z_out[f] = ndtri_fn(1.0 - pv);
     }
-    if (slow) {  // |a| >= 26, infinite or NaN: the Cephes replica (rare)
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (!(fabs(av[e]) < 26.0)) res[e] = ndtr_slow(av[e]);
-    }
-    if (dl < h + 0 || dr < h + 3) {  // some element is closer than h to an interval end
+}
+
+// Stores of one half-width's 4 results into every output row that asked for it, after the edge rule of
+// windowing.pyx:51-54 (positions closer than h to an interval end are 1.0).
+// dl: interval-local index of element 0 (clamped), dr: len - 1 - dl (clamped).
+__device__ __forceinline__ void store_scale(double (&res)[4], int h, unsigned rows, const ScoreParams &P, int dl, int dr,
+                                            long long f0, unsigned omask) {
+    if (dl < h || dr < h + 3) {
 #pragma unroll
         for (int e = 0; e < 4; ++e)
             if (dl + e < h || dr - e < h) res[e] = 1.0;
     }
     for (unsigned m = rows; m; m &= m - 1) {
         const int s = __ffs(m) - 1;
-        double *dst = winp_out + (size_t)s * total + f0;
-        if (omask == 0xFu && ((winp_vec >> s) & 1u)) {
+        double *dst = P.winp_out + (size_t)s * P.total + f0;
+        if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) {
             // two 128-bit stores: ptxas 12.9 was seen to drop three of the four values of a predicated
-            // st.global.v4.f64 in this function when compiled for the 80-register variant of the kernel
+            // st.global.v4.f64 here when compiling the 80-register variant of the kernel
             reinterpret_cast<double2 *>(dst)[0] = make_double2(res[0], res[1]);
             reinterpret_cast<double2 *>(dst)[1] = make_double2(res[2], res[3]);
         } else {
@@ -149,12 +154,77 @@ __device__ __noinline__ void emit_scale_fused(double a0, double a1, double a2, d
     }
 }
 
+constexpr int kZS = kFT + 4;  // row stride of the transposed z array: zsT[e * kZS + 2 + t] = z[4 t + e]
+
+// Multi-scale Stouffer windows (windowing.h:53-67) of the 4 positions 4*tid .. 4*tid+3 from the tile's z in
+// shared memory. z is stored transposed (element index major) so that lane-consecutive threads read
+// consecutive doubles: every access is a conflict-free LDS.64. Sums grow outward from the centre,
+// S_h = S_{h-1} + (z[-h] + z[+h]), each step needing one new value per side; up to three requested
+// half-widths are carried per pass so that the sums are the only live values while the normal tails
+// are evaluated.
+__device__ __forceinline__ void window_phase(const double *zsT, int tid, const ScoreParams &P, int dl, int dr,
+                                             long long f0, unsigned omask) {
+    unsigned pending = 0;
+#pragma unroll
+    for (int h = 0; h <= kFastMaxScaleHalfWin; ++h)
+        if (P.h_rows[h]) pending |= 1u << h;
+    const double *zt = zsT + 2 + tid;
+    while (pending) {
+        int hq[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            hq[k] = pending ? (__ffs(pending) - 1) : -1;
+            pending &= pending - 1;
+        }
+        const int hlast = hq[2] >= 0 ? hq[2] : (hq[1] >= 0 ? hq[1] : hq[0]);
+        double A[3][4];
+        {
+            double acc[4], Lw[4], Rw[4];  // Lw[e] = z[e - h], Rw[e] = z[e + h]
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = Lw[e] = Rw[e] = zt[e * kZS];
+#pragma unroll
+            for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
+                if (h > hlast) break;
+                if (h > 0) {
+                    // element index j = -h on the left, 3 + h on the right: row j & 3, thread offset j >> 2
+                    const double zl = zt[((-h) & 3) * kZS + ((-h) >> 2)];
+                    const double zr = zt[((3 + h) & 3) * kZS + ((3 + h) >> 2)];
+                    Lw[3] = Lw[2]; Lw[2] = Lw[1]; Lw[1] = Lw[0]; Lw[0] = zl;
+                    Rw[0] = Rw[1]; Rw[1] = Rw[2]; Rw[2] = Rw[3]; Rw[3] = zr;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[e] += Lw[e] + Rw[e];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (hq[k] == h) {
+                        const double cneg = -P.inv_sqrt_k[h];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) A[k][e] = acc[e] * cneg;
+                    }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (hq[k] < 0) break;
+            double res[4];
+            ndtr4(A[k], res);
+            store_scale(res, hq[k], P.h_rows[hq[k]], P, dl, dr, f0, omask);
+        }
+    }
+}
+
 #ifndef FPT_FUSED_CTAS
-#define FPT_FUSED_CTAS 3
+#define FPT_FUSED_CTAS 3   // CTAs per SM the in-kernel-window variant is compiled for (80 registers)
+#endif
+#ifndef FPT_SPLIT_CTAS
+#define FPT_SPLIT_CTAS 2   // same for the variant that leaves the windows to the streaming kernel
 #endif
 
-template <bool SMOOTH>
-__global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const ScoreParams P) {
+// SMOOTH: smoothing half-width 50 with one value trimmed per side (else no smoothing).
+// INWIN:  evaluate the Stouffer windows inside this kernel from shared-memory z (else write z and the edge
+//         distances for the streaming window kernel of fpt_fast.cu, which follows on the stream).
+template <bool SMOOTH, bool INWIN>
+__global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) score_fused_kernel(const ScoreParams P) {
     constexpr int HW = kFastHalfWin;
     constexpr int SHW = SMOOTH ? 50 : 0;
     constexpr int WSM = 2 * SHW + 1;
@@ -166,15 +236,16 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
     uint32_t *wcw = cw + kXCap + 2 * kXPad;                                           // packed 10-wide sums
     uint4 *GA = reinterpret_cast<uint4 *>(wcw + kXCap + kXPad);                       // group aggregates
     uint4 *GB = GA + kNG + kGPad;
-    double *zs = reinterpret_cast<double *>(GB) + 8;                                  // aliases GB (dead by then)
     double *dmp = reinterpret_cast<double *>(GB + kNG + kGPad);                       // 24
     FastRegions *Rbuf = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);         // double-buffered
-    int *badflag = reinterpret_cast<int *>(Rbuf + 2);                                 // [2]
+    int *badflag = reinterpret_cast<int *>(Rbuf + 2);                                 // [2] (+ pad to 16 bytes)
+    double *zsT = reinterpret_cast<double *>(badflag + 4);                            // INWIN only: z of the tile, transposed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int WH = P.wh_max;
-    const bool want_win = P.winp_out != nullptr && P.n_scales > 0;
-    const bool want_p = (P.pval_out != nullptr) || want_win;
+    const int WH = INWIN ? P.wh_max : 0;
+    const bool want_win = INWIN && P.winp_out != nullptr && P.n_scales > 0;
+    const bool want_z = !INWIN && P.z_out != nullptr;
+    const bool want_p = (P.pval_out != nullptr) || want_win || want_z;
     const float dWf = SMOOTH ? (float)(WSM - 2) : 1.0f;
 
     if (!P.uniform)
@@ -189,6 +260,7 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
         GB[kNG + i] = make_uint4(0, 0, 0, 0);
     }
     if (tid < 2) badflag[tid] = 0;
+    if (INWIN && tid < 16) zsT[(tid >> 2) * kZS + ((tid & 2) ? kFT + 2 : 0) + (tid & 1)] = 0.0;  // the 2 + 2 pad entries of each row
 
     // ---- sub-tile walk: (tile, cur, k) is the sub-tile being scored, its table is Rbuf[buf] ---
     long long tile = blockIdx.x;
@@ -200,57 +272,152 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
         build_regions(P, &Rbuf[0], tile * (long long)P.tile, hi, P.tile_first_iv[tile], lane, WH, PADX, PADR);
     __syncthreads();
 
+    // Work carried across the loop's barrier, so that global-memory latency is never waited for right in
+    // front of one:
+    //  * the p-value table look-ups of a sub-tile are issued at the end of its phase 4 and their values
+    //    stored (p, z, edge distances) at the top of the next iteration;
+    //  * INWIN: the Stouffer windows of a sub-tile are evaluated at the top of the next iteration too.
+    unsigned pend_omask = 0;
+    int pend_dl = 0, pend_dr = 0;
+    long long pend_f0 = 0;
+    double pend_p[4] = {1.0, 1.0, 1.0, 1.0}, pend_z[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned pend_edge4 = 0;
+    const int c0 = tid << 2;
+    const float dflt_f = (float)P.dflt;
+
     for (;;) {
         FastRegions *R = &Rbuf[buf];
         const int nreg = R->nreg;
-        long long ncur = R->next_cur, nk = R->next_k, ntile = tile, nhi = hi;
+        long long ncur = R->next_cur, ntile = tile, nhi = hi;
         if (ncur >= hi) {
             ntile = tile + gridDim.x;
             if (ntile < P.n_tiles) {
                 ncur = ntile * (long long)P.tile;
                 nhi = (ntile + 1) * (long long)P.tile < P.total ? (ntile + 1) * (long long)P.tile : P.total;
-                nk = P.tile_first_iv[ntile];
             }
         }
         const bool more = ntile < P.n_tiles;
         const int NX = R->xblk[nreg], NC = R->cblk[nreg];
         const int NXG = NX >> 2;
 
-        // ---- phase 1: stage the packed cut counts -------------------------------------------------
-        {
-            unsigned seen = 0;
-            for (int r = 0; r < nreg; ++r) {
-                const int xb = R->xblk[r], xe = R->xblk[r + 1];
-                const long long g0r = R->G0[r];
-                const long long ga = g0r + xb;
-                if (P.cuts_vec && ((ga & 3) == 0) && ga >= 1 && g0r + xe <= P.n_track) {
-                    // 16-byte loads: 4 slots per thread, minus strand shifted by one position
-                    for (int x = xb + 4 * tid; x < xe; x += 4 * kFT) {
-                        const long long g = g0r + x;
-                        const uint4 a = ldg128(P.cuts_p + g);
-                        const uint4 b = ldg128(P.cuts_m + g);
-                        const unsigned bm1 = __ldg(P.cuts_m + g - 1);
-                        seen |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | bm1);
-                        uint4 w;
-                        w.x = __byte_perm(a.x, bm1, 0x5410);
-                        w.y = __byte_perm(a.y, b.x, 0x5410);
-                        w.z = __byte_perm(a.z, b.y, 0x5410);
-                        w.w = __byte_perm(a.w, b.z, 0x5410);
-                        *reinterpret_cast<uint4 *>(cw + x) = w;
-                    }
+        // ---- phase 0: this thread's 4 positions of the sub-tile and their 18-base sequence window; the
+        //      global loads are issued here and consumed in phase 4 ------------------------------------
+        const bool active = c0 < NC;
+        int r = 0;
+        unsigned vmask = 0;   // elements that are computed positions
+        unsigned omask = 0;   // elements that are outputs of this region
+        unsigned long long kw = 0;  // 2-bit codes of bases g0-8 .. g0+9 (k-mer m starts at base g0-8+m)
+        unsigned nw = 0;            // N bits of the same 18 bases
+        if (active) {
+            r = fregion_of(R->cblk, nreg, c0);
+            const int cb = R->cb[r], cn = R->cn[r];
+            const long long F0 = R->F0[r], rfa = R->fa[r], rfb = R->fb[r];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = c0 + e;
+                if (c >= cb && c < cb + cn) {
+                    vmask |= 1u << e;
+                    const long long f = F0 + c;
+                    if (f >= rfa && f < rfb) omask |= 1u << e;
+                }
+            }
+            if (vmask && !P.uniform) {
+                const long long b0 = c0 + R->D[r] + R->G0[r] - 8;
+                if (b0 >= 0 && b0 + 18 <= P.n_track) {
+                    const long long nw2 = (P.n_track + 15) >> 4;
+                    const long long w = b0 >> 4;
+                    const int sh = (int)(b0 & 15) * 2;
+                    const unsigned q0 = __ldg(P.seq2 + w);
+                    const unsigned q1 = (w + 1 < nw2) ? __ldg(P.seq2 + w + 1) : 0u;
+                    const unsigned q2 = (w + 2 < nw2) ? __ldg(P.seq2 + w + 2) : 0u;
+                    const unsigned lo32 = __funnelshift_r(q0, q1, sh);
+                    const unsigned hi32 = __funnelshift_r(q1, q2, sh);
+                    kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
+                    nw = ffetch_bits(P.nmask, (P.n_track + 31) >> 5, b0, 18);
                 } else {
-                    for (int x = xb + tid; x < xe; x += kFT) {
-                        const long long g = g0r + x;
-                        const unsigned a = (g >= 0 && g < P.n_track) ? __ldg(P.cuts_p + g) : 0u;
-                        const unsigned b = (g >= 1 && g - 1 < P.n_track) ? __ldg(P.cuts_m + g - 1) : 0u;
-                        seen |= a | b;
-                        cw[x] = __byte_perm(a, b, 0x5410);
+                    const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
+                    for (int j = 0; j < 18; ++j) {
+                        const long long q = b0 + j;
+                        if (q >= 0 && q < P.n_track) {
+                            kw |= (unsigned long long)ffetch_bits(P.seq2, nw2, 2 * q, 2) << (2 * j);
+                            nw |= ffetch_bits(P.nmask, nwm, q, 1) << j;
+                        } else {
+                            nw |= 1u << j;
+                        }
                     }
                 }
             }
+        }
+
+        // ---- previous sub-tile: stores of its p-values / z / edge distances, or (INWIN) its windows -----
+        if (pend_omask) {
+            if (INWIN) {
+                window_phase(zsT, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
+            } else {
+                if (pend_omask == 0xFu && P.vec_ok) {
+                    if (P.pval_out) st256(P.pval_out + pend_f0, pend_p[0], pend_p[1], pend_p[2], pend_p[3]);
+                    if (want_z) {
+                        st256(P.z_out + pend_f0, pend_z[0], pend_z[1], pend_z[2], pend_z[3]);
+                        *reinterpret_cast<unsigned *>(P.edge_out + pend_f0) = pend_edge4;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((pend_omask >> e) & 1u) {
+                            if (P.pval_out) P.pval_out[pend_f0 + e] = pend_p[e];
+                            if (want_z) {
+                                P.z_out[pend_f0 + e] = pend_z[e];
+                                P.edge_out[pend_f0 + e] = (unsigned char)((pend_edge4 >> (8 * e)) & 0xFFu);
+                            }
+                        }
+                }
+            }
+            pend_omask = 0;
+        }
+
+        // ---- phase 1: stage the packed cut counts (two groups of 4 slots per thread) -----------------
+        {
+            unsigned seen = 0;
+#pragma unroll
+            for (int rd = 0; rd < 2; ++rd) {
+                const int xg = tid + rd * kFT;
+                if (xg >= NXG) break;
+                const int x = xg << 2;
+                const int rx = fregion_of(R->xblk, nreg, x);
+                const long long g = R->G0[rx] + x;
+                uint4 w;
+                if (P.cuts_vec && ((g & 3) == 0) && g >= 1 && g + 4 <= P.n_track) {
+                    // 16-byte loads; the minus strand is shifted by one position (slot x pairs + at x with - at x-1)
+                    const uint4 a = ldg128(P.cuts_p + g);
+                    const uint4 b = ldg128(P.cuts_m + g);
+                    const unsigned bm1 = __ldg(P.cuts_m + g - 1);
+                    seen |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | bm1);
+                    w.x = __byte_perm(a.x, bm1, 0x5410);
+                    w.y = __byte_perm(a.y, b.x, 0x5410);
+                    w.z = __byte_perm(a.z, b.y, 0x5410);
+                    w.w = __byte_perm(a.w, b.z, 0x5410);
+                } else {
+                    unsigned a[4], b[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const long long ge = g + e;
+                        a[e] = (ge >= 0 && ge < P.n_track) ? __ldg(P.cuts_p + ge) : 0u;
+                        b[e] = (ge >= 1 && ge - 1 < P.n_track) ? __ldg(P.cuts_m + ge - 1) : 0u;
+                        seen |= a[e] | b[e];
+                    }
+                    w.x = __byte_perm(a[0], b[0], 0x5410);
+                    w.y = __byte_perm(a[1], b[1], 0x5410);
+                    w.z = __byte_perm(a[2], b[2], 0x5410);
+                    w.w = __byte_perm(a[3], b[3], 0x5410);
+                }
+                *reinterpret_cast<uint4 *>(cw + x) = w;
+            }
             if (seen & ~kPackedCutLimit) badflag[buf] = 1;
         }
-        if (warp == 0 && more) build_regions(P, &Rbuf[buf ^ 1], ncur, nhi, nk, lane, WH, PADX, PADR);
+        if (warp == 0 && more) {
+            const long long nk = (ncur >= hi || R->next_cur >= hi) ? (long long)P.tile_first_iv[ntile] : R->next_k;
+            build_regions(P, &Rbuf[buf ^ 1], ncur, nhi, nk, lane, WH, PADX, PADR);
+        }
         __syncthreads();
         const bool bad = badflag[buf] != 0;
         if (tid == 0) {
@@ -259,6 +426,20 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
                 marked = tile;
                 const int slot = atomicAdd(P.redo_count, 1);
                 P.redo_list[slot] = (int)tile;
+            }
+        }
+        // L2 prefetch of the next sub-tile's cut counts (one 128-byte line per thread and strand): a whole
+        // iteration ahead of their staging loads
+        if (more) {
+            const FastRegions *Rn = &Rbuf[buf ^ 1];
+            const int nr = Rn->nreg;
+            if (tid < (Rn->xblk[nr] + 31) >> 5) {
+                const int x = tid << 5;
+                const int rx = fregion_of(Rn->xblk, nr, x);
+                long long g = Rn->G0[rx] + x;
+                g = g < 0 ? 0 : (g < P.n_track ? g : P.n_track - 1);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cuts_p + g));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cuts_m + g));
             }
         }
 
@@ -282,9 +463,9 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
                 w.w = vadd2(vadd2(core, p34), c[15]);
                 *reinterpret_cast<uint4 *>(wcw + x0) = w;
                 if (SMOOTH) {
-                    const unsigned s = vadd2(vadd2(w.x, w.y), vadd2(w.z, w.w));  // <= 4 * 10230 per half
+                    const unsigned sg = vadd2(vadd2(w.x, w.y), vadd2(w.z, w.w));  // <= 4 * 10230 per half
                     GA[xg] = make_uint4(vmin2(vmin2(w.x, w.y), vmin2(w.z, w.w)), vmax2(vmax2(w.x, w.y), vmax2(w.z, w.w)),
-                                        lo16(s), hi16(s));
+                                        lo16(sg), hi16(sg));
                 }
             }
             __syncthreads();
@@ -302,31 +483,10 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
             }
 
             // ---- phase 4: expected counts, strand combine, p-value (c-space, 4 per thread) ----------
-            const int c0 = tid << 2;
-            const bool active = c0 < NC;
-            int r = 0;
-            long long F0 = 0, T0 = 0, ivlen = 0;
-            unsigned vmask = 0;   // elements that are computed positions
-            unsigned omask = 0;   // elements that are outputs of this region
             double zv[4] = {0.0, 0.0, 0.0, 0.0};
-            if (active) {
-                r = fregion_of(R->cblk, nreg, c0);
-                const int cb = R->cb[r], cn = R->cn[r];
-                F0 = R->F0[r]; T0 = R->T0[r]; ivlen = R->len[r];
-                const long long rfa = R->fa[r], rfb = R->fb[r];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = c0 + e;
-                    if (c >= cb && c < cb + cn) {
-                        vmask |= 1u << e;
-                        const long long f = F0 + c;
-                        if (f >= rfa && f < rfb) omask |= 1u << e;
-                    }
-                }
-            }
             if (vmask) {
                 const int x0 = c0 + R->D[r];
-                const long long g0 = x0 + R->G0[r];  // track coordinate of element 0 (plus strand)
+                const long long F0 = R->F0[r], T0 = R->T0[r], ivlen = R->len[r];
 
                 // -- trimmed window sums T[strand][e] (exact integers)
                 unsigned Tl[4], Th[4];
@@ -379,43 +539,16 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
                     }
                 }
 
-                // -- k-mer windows: the 13 k-mers starting at bases g0-8 .. g0+4 serve both strands:
-                //    plus-strand position g0-5+m and minus-strand position g0-6+m use k-mer m
-                unsigned long long kw = 0;  // 2-bit codes of bases g0-8 .. g0+9
-                unsigned long long rcw = 0; // reverse complement of the same 18 bases
-                unsigned nw = 0;            // N bits of the same 18 bases
+                // -- the 13 k-mers starting at bases g0-8 .. g0+4 serve both strands: plus-strand position
+                //    g0-5+m and minus-strand position g0-6+m use k-mer m; rcw = reverse complement of kw
+                unsigned long long rcw = 0;
                 if (!P.uniform) {
-                    const long long b0 = g0 - 8;
-                    if (b0 >= 0 && b0 + 18 <= P.n_track) {
-                        const long long nw2 = (P.n_track + 15) >> 4;
-                        const long long w = b0 >> 4;
-                        const int sh = (int)(b0 & 15) * 2;
-                        const unsigned q0 = __ldg(P.seq2 + w);
-                        const unsigned q1 = (w + 1 < nw2) ? __ldg(P.seq2 + w + 1) : 0u;
-                        const unsigned q2 = (w + 2 < nw2) ? __ldg(P.seq2 + w + 2) : 0u;
-                        const unsigned lo32 = __funnelshift_r(q0, q1, sh);
-                        const unsigned hi32 = __funnelshift_r(q1, q2, sh);
-                        kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
-                        nw = ffetch_bits(P.nmask, (P.n_track + 31) >> 5, b0, 18);
-                    } else {
-                        const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
-                        for (int j = 0; j < 18; ++j) {
-                            const long long q = b0 + j;
-                            if (q >= 0 && q < P.n_track) {
-                                kw |= (unsigned long long)ffetch_bits(P.seq2, nw2, 2 * q, 2) << (2 * j);
-                                nw |= ffetch_bits(P.nmask, nwm, q, 1) << j;
-                            } else {
-                                nw |= 1u << j;
-                            }
-                        }
-                    }
                     unsigned long long t = __brevll(kw) >> 28;
                     t = ((t & 0xAAAAAAAAAull) >> 1) | ((t & 0x555555555ull) << 1);
                     rcw = t ^ 0xFFFFFFFFFull;
                 }
                 int exi[4] = {0, 0, 0, 0};  // plus[t+1] + minus[t] (cli/detect.py:121-122)
                 unsigned redo = 0;          // bit 4*s + e: strand s of element e needs the out-of-line evaluation
-                const float dflt_f = (float)P.dflt;
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     float Pv[13];
@@ -461,8 +594,9 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
                 if (redo) {  // rare; kept out of the loops above so that nothing is live across the calls
                     for (unsigned m = redo; m; m &= m - 1) {
                         const int b = __ffs(m) - 1, s = b >> 2, e = b & 3;
-                        const double res = fexpected_packed(SeqView{P.seq2, P.nmask, P.n_track, P.dflt, P.uniform}, P.bias,
-                                                            wcw, SHW, g0 + e - s, x0 + e, s);
+                        const unsigned Te = s ? (e == 0 ? Th[0] : e == 1 ? Th[1] : e == 2 ? Th[2] : Th[3])
+                                              : (e == 0 ? Tl[0] : e == 1 ? Tl[1] : e == 2 ? Tl[2] : Tl[3]);
+                        const double res = fexpected_packed(P.bias, P.dflt, P.uniform, kw, rcw, nw, e, s, Te, wcw, x0 + e, SHW);
                         const int ri = (int)res;
                         if (e == 0) exi[0] += ri;
                         else if (e == 1) exi[1] += ri;
@@ -470,17 +604,16 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
                         else exi[3] += ri;
                     }
                 }
-                // -- observed counts and p-values
+                // -- observed counts; the p-value table look-ups are issued here and (unless INWIN) consumed
+                //    after the loop's barrier
                 const uint4 cq = lds128(cw + x0);
                 const unsigned cwv[4] = {cq.x, cq.y, cq.z, cq.w};
                 int obi[4];
-                double exv[4], obv[4], pvv[4];
+                double pvv[4];
                 unsigned direct = 0;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     obi[e] = (int)(lo16(cwv[e]) + hi16(cwv[e]));
-                    exv[e] = (double)exi[e];
-                    obv[e] = (double)obi[e];
                     pvv[e] = 1.0;
                     if (want_p && ((vmask >> e) & 1u)) {
                         if (exi[e] < P.lut_e && obi[e] < P.lut_o) {
@@ -491,11 +624,50 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
                         }
                     }
                 }
+                const long long f0 = F0 + c0;
+                {
+                    const double exv[4] = {(double)exi[0], (double)exi[1], (double)exi[2], (double)exi[3]};
+                    const double obv[4] = {(double)obi[0], (double)obi[1], (double)obi[2], (double)obi[3]};
+                    if (omask == 0xFu && P.vec_ok) {
+                        if (P.exp_out) st256(P.exp_out + f0, exv[0], exv[1], exv[2], exv[3]);
+                        if (P.obs_out) st256(P.obs_out + f0, obv[0], obv[1], obv[2], obv[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if ((omask >> e) & 1u) {
+                                if (P.exp_out) P.exp_out[f0 + e] = exv[e];
+                                if (P.obs_out) P.obs_out[f0 + e] = obv[e];
+                            }
+                    }
+                }
+                if (P.hist) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (((omask >> e) & 1u) && exi[e] < P.hist_d0 && obi[e] < P.hist_d1)
+                            atomicAdd(P.hist + (size_t)exi[e] * P.hist_d1 + obi[e], 1ULL);
+                }
+                if (!INWIN && direct) {
+                    // hand the evaluation to direct_fix_kernel (z is only needed for outputs in this mode)
+                    direct &= omask;
+                    if (P.direct_list) {
+#pragma unroll 1
+                        for (int e = 0; e < 4; ++e) {
+                            if (!((direct >> e) & 1u)) continue;
+                            const int slot = atomicAdd(P.direct_count, 1);
+                            if (slot >= P.direct_cap) continue;  // list full: evaluated inline below
+                            const long long f = f0 + e;
+                            const int ex = e == 0 ? exi[0] : e == 1 ? exi[1] : e == 2 ? exi[2] : exi[3];
+                            const int ob = e == 0 ? obi[0] : e == 1 ? obi[1] : e == 2 ? obi[2] : obi[3];
+                            P.direct_list[slot] = make_int4((int)(unsigned)(f & 0xFFFFFFFFll), (int)(f >> 32), ex, ob);
+                            direct &= ~(1u << e);
+                        }
+                    }
+                }
                 if (direct) {
 #pragma unroll 1
                     for (int e = 0; e < 4; ++e) {
                         if (!((direct >> e) & 1u)) continue;
-                        const double ex = e == 0 ? exv[0] : e == 1 ? exv[1] : e == 2 ? exv[2] : exv[3];
+                        const double ex = (double)(e == 0 ? exi[0] : e == 1 ? exi[1] : e == 2 ? exi[2] : exi[3]);
                         const int kobs = e == 0 ? obi[0] : e == 1 ? obi[1] : e == 2 ? obi[2] : obi[3];
                         const double rr = fit_r(dmp + 9, ex), mu = fit_mu(dmp, ex);
                         const double pv = nb_cdf(kobs, nb_prob(rr, mu), rr);
@@ -506,92 +678,101 @@ __global__ void __launch_bounds__(kFT, FPT_FUSED_CTAS) score_fused_kernel(const 
                         else { pvv[3] = pv; zv[3] = z; }
                     }
                 }
-                if (P.hist) {
+                if (omask && (P.pval_out || want_z || want_win)) {
+                    const long long dl = T0 + c0, dr = ivlen - 1 - dl;
+                    pend_omask = omask;
+                    pend_f0 = f0;
+                    if (INWIN) {
+                        pend_dl = (int)(dl < 255 ? dl : 255);
+                        pend_dr = (int)(dr < 255 ? dr : 255);
+                        if (P.pval_out) {  // p is stored right away in this variant
+                            if (omask == 0xFu && P.vec_ok) st256(P.pval_out + f0, pvv[0], pvv[1], pvv[2], pvv[3]);
+                            else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (((omask >> e) & 1u) && exi[e] < P.hist_d0 && obi[e] < P.hist_d1)
-                            atomicAdd(P.hist + (size_t)exi[e] * P.hist_d1 + obi[e], 1ULL);
-                }
-                // -- stores: one 256-bit store per array when the whole group is output
-                const long long f0 = F0 + c0;
-                if (omask == 0xFu && P.vec_ok) {
-                    if (P.exp_out) st256(P.exp_out + f0, exv[0], exv[1], exv[2], exv[3]);
-                    if (P.obs_out) st256(P.obs_out + f0, obv[0], obv[1], obv[2], obv[3]);
-                    if (P.pval_out) st256(P.pval_out + f0, pvv[0], pvv[1], pvv[2], pvv[3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if ((omask >> e) & 1u) {
-                            if (P.exp_out) P.exp_out[f0 + e] = exv[e];
-                            if (P.obs_out) P.obs_out[f0 + e] = obv[e];
-                            if (P.pval_out) P.pval_out[f0 + e] = pvv[e];
+                                for (int e = 0; e < 4; ++e)
+                                    if ((omask >> e) & 1u) P.pval_out[f0 + e] = pvv[e];
+                            }
                         }
+                        if (!want_win) pend_omask = 0;
+                    } else {
+                        unsigned edge4 = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const long long d = min(dl + e, dr - e);  // negative for the non-output slots of a partial group
+                            edge4 |= (unsigned)(d < 0 ? 0 : (d < 255 ? d : 255)) << (8 * e);
+                            pend_p[e] = pvv[e]; pend_z[e] = zv[e];
+                        }
+                        pend_edge4 = edge4;
+                    }
                 }
             }
-
-            // ---- phase 5: multi-scale Stouffer windows over the tile's z in shared memory -----------
-            if (want_win) {
-                if (active) {
-                    *reinterpret_cast<double2 *>(zs + c0) = make_double2(zv[0], zv[1]);
-                    *reinterpret_cast<double2 *>(zs + c0 + 2) = make_double2(zv[2], zv[3]);
-                }
-                __syncthreads();
-                if (omask) {
-                    double z[20];  // z[8 + e] is element e
+            if (want_win && active) {  // INWIN: publish z for the windows evaluated at the top of the next iteration
 #pragma unroll
-                    for (int q = 0; q < 10; ++q) {
-                        const double2 t2 = *reinterpret_cast<const double2 *>(zs + c0 - 8 + 2 * q);
-                        z[2 * q] = t2.x; z[2 * q + 1] = t2.y;
-                    }
-                    const long long dl = T0 + c0, dr = ivlen - 1 - dl;
-                    const long long f0 = F0 + c0;
-                    double acc[4] = {z[8], z[9], z[10], z[11]};
-#pragma unroll
-                    for (int h = 0; h <= kFastMaxScaleHalfWin; ++h) {
-                        if (h > WH) break;
-                        if (h > 0) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
-                        }
-                        if (P.h_rows[h])
-                            emit_scale_fused(acc[0], acc[1], acc[2], acc[3], h, -P.inv_sqrt_k[h], P.h_rows[h], P.winp_vec,
-                                             P.winp_out, P.total, dl, dr, f0, omask);
-                    }
-                }
+                for (int e = 0; e < 4; ++e) zsT[e * kZS + 2 + tid] = zv[e];
             }
         }
         __syncthreads();
         if (!more) break;
         tile = ntile; hi = nhi; buf ^= 1;
     }
+    // the last sub-tile's deferred work
+    if (pend_omask) {
+        if (INWIN) {
+            window_phase(zsT, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((pend_omask >> e) & 1u) {
+                    if (P.pval_out) P.pval_out[pend_f0 + e] = pend_p[e];
+                    if (want_z) {
+                        P.z_out[pend_f0 + e] = pend_z[e];
+                        P.edge_out[pend_f0 + e] = (unsigned char)((pend_edge4 >> (8 * e)) & 0xFFu);
+                    }
+                }
+        }
+    }
 }
 
 }  // namespace
 
-size_t score_fused_smem_bytes() {
+size_t score_fused_smem_bytes(bool inwin) {
     size_t b = 4096 * sizeof(float);
     b += (size_t)(2 * kXCap + 4 * kXPad) * sizeof(uint32_t);  // [pad | cw | pad][pad | wcw | pad]
     b += (size_t)2 * (kNG + kGPad) * sizeof(uint4);
-    b += sizeof(double) * kModelDoubles + 2 * sizeof(FastRegions) + 64;
+    b += sizeof(double) * kModelDoubles + 2 * sizeof(FastRegions) + 16;
+    if (inwin) b += (size_t)4 * kZS * sizeof(double);  // z of the tile, transposed
     return b;
 }
 
-cudaError_t score_fused_prepare(size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(score_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(score_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t score_fused_prepare() {
+    const void *k[4] = {(const void *)score_fused_kernel<true, true>, (const void *)score_fused_kernel<false, true>,
+                        (const void *)score_fused_kernel<true, false>, (const void *)score_fused_kernel<false, false>};
+    for (int i = 0; i < 4; ++i) {
+        cudaError_t e = cudaFuncSetAttribute(k[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)score_fused_smem_bytes(i < 2));
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
-int score_fused_blocks_per_sm(size_t smem, bool smooth) {
+int score_fused_blocks_per_sm(bool smooth, bool inwin) {
     int n = 0;
-    cudaError_t e = smooth ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_fused_kernel<true>, kFT, smem)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, score_fused_kernel<false>, kFT, smem);
-    return e == cudaSuccess ? n : 0;
+    const void *k = smooth ? (inwin ? (const void *)score_fused_kernel<true, true> : (const void *)score_fused_kernel<true, false>)
+                           : (inwin ? (const void *)score_fused_kernel<false, true> : (const void *)score_fused_kernel<false, false>);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kFT, score_fused_smem_bytes(inwin)) == cudaSuccess ? n : 0;
 }
 
-cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth) {
-    if (smooth) score_fused_kernel<true><<<grid, kFT, score_fused_smem_bytes(), st>>>(p);
-    else score_fused_kernel<false><<<grid, kFT, score_fused_smem_bytes(), st>>>(p);
+cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth, bool inwin) {
+    const size_t smem = score_fused_smem_bytes(inwin);
+    if (smooth && inwin) score_fused_kernel<true, true><<<grid, kFT, smem, st>>>(p);
+    else if (smooth) score_fused_kernel<true, false><<<grid, kFT, smem, st>>>(p);
+    else if (inwin) score_fused_kernel<false, true><<<grid, kFT, smem, st>>>(p);
+    else score_fused_kernel<false, false><<<grid, kFT, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_direct_fix(cudaStream_t st, const ScoreParams &p, int sm_count) {
+    direct_fix_kernel<<<sm_count * 2, 128, 0, st>>>(p.direct_list, p.direct_count, p.direct_cap, p.dm, p.pval_out, p.z_out);
     return cudaGetLastError();
 }
 

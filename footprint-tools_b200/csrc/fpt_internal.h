@@ -64,6 +64,9 @@ struct ScoreParams {
     unsigned winp_vec;                          // bit s: row s of winp_out is 32-byte aligned
     unsigned h_rows[kFastMaxScaleHalfWin + 1];  // bit s of h_rows[h]: output row s has half-width h
     double inv_sqrt_k[kFastMaxScaleHalfWin + 1];  // 1/sqrt(2h+1)
+    int4 *direct_list;         // (f lo, f hi, exp, obs) of outputs whose NB p-value direct_fix_kernel evaluates
+    int *direct_count;
+    int direct_cap;
     // general kernel in list mode: score tiles tile_list[0 .. *n_list) instead of 0 .. n_tiles
     const int *tile_list;
     const int *n_list;
@@ -88,10 +91,12 @@ cudaError_t launch_score(cudaStream_t st, const ScoreParams &p, int grid);
 cudaError_t score_kernel_prepare(size_t smem);
 int score_kernel_blocks_per_sm(size_t smem);
 
-size_t score_fused_smem_bytes();
-cudaError_t score_fused_prepare(size_t smem);
-int score_fused_blocks_per_sm(size_t smem, bool smooth);
-cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth);
+size_t score_fused_smem_bytes(bool inwin);
+cudaError_t score_fused_prepare();
+int score_fused_blocks_per_sm(bool smooth, bool inwin);
+cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth, bool inwin);
+
+cudaError_t launch_direct_fix(cudaStream_t st, const ScoreParams &p, int sm_count);
 
 size_t score_fast_smem_bytes();
 cudaError_t score_fast_prepare(size_t smem);

@@ -536,6 +536,11 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
                         zv = ndtri_fn(1.0 - pv);
                     }
                     if (is_out && P.pval_out) P.pval_out[f] = pv;
+                    if (is_out && P.z_out) {  // hand-off to the streaming window kernel (list mode behind the fused kernel)
+                        const long long t = R->t0[r] + q, d = min(t, R->ivlen[r] - 1 - t);
+                        P.z_out[f] = zv;
+                        P.edge_out[f] = (unsigned char)(d < 255 ? d : 255);
+                    }
                     zreg[rd] = zv;
                 }
             }

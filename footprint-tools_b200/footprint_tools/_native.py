@@ -19,7 +19,7 @@ MEM_DEVICE, MEM_HOST = 0, 1
 WIN_SUM, WIN_PRODUCT, WIN_FISHER, WIN_STOUFFER, WIN_WSTOUFFER = range(5)
 NB_CDF, NB_PMF, NB_LOGPMF = range(3)
 MAX_SCALES = 8
-DEFAULT_LUT = (256, 512)
+DEFAULT_LUT = (512, 2048)
 
 c_dp = C.POINTER(C.c_double)
 c_u32p = C.POINTER(C.c_uint32)
@@ -182,7 +182,7 @@ class Context(object):
     def launches(self):
         return int(lib().fpt_ctx_launch_count(self._h))
 
-    KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo")
+    KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo", "direct_fix")
 
     def profile(self, enable=True):
         """Turn the per-kernel CUDA-event timers on or off (fpt_ctx_profile)."""

@@ -83,7 +83,8 @@ int64_t fpt_ctx_launch_count(const fpt_ctx *ctx);
 #define FPT_KERNEL_SCORE_GENERAL 3 /* scoring kernel, any geometry */
 #define FPT_KERNEL_SCORE_FUSED 4   /* single-launch scoring + windows kernel of the detect/learn_dm geometry */
 #define FPT_KERNEL_REDO 5          /* general kernel over the tiles the fused kernel handed back */
-#define FPT_KERNEL_COUNT 6
+#define FPT_KERNEL_DIRECT_FIX 6    /* NB p-values of the positions outside the (exp, obs) table */
+#define FPT_KERNEL_COUNT 7
 int fpt_ctx_profile(fpt_ctx *ctx, int enable);
 int fpt_ctx_profile_read(fpt_ctx *ctx, double *total_ms, int64_t *launches);
 
