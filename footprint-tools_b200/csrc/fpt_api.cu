@@ -87,6 +87,10 @@ struct fpt_ctx {
     // scratch
     DevBuf plan, scratch;
     DevBuf h_in[8], h_out[8];  // staging for FPT_MEM_HOST calls
+    // pipelined FPT_MEM_HOST scoring: copy-in / copy-out streams and per-chunk events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_comp, ev_out;
+    int pipeline = 1;  // FPT_B200_PIPELINE=0: single-shot staging (copy in, score, copy out)
     // per-kernel CUDA-event timers (fpt_ctx_profile)
     bool prof = false;
     struct ProfSlot { cudaEvent_t a, b; int kid; };
@@ -202,6 +206,8 @@ int fpt_ctx_create(int device, fpt_ctx **out) {
     const char *path = getenv("FPT_B200_PATH");
     if (path && !strcmp(path, "general")) c->force_general = 1;
     if (path && !strcmp(path, "fast")) c->allow_fused = 0;
+    const char *pl = getenv("FPT_B200_PIPELINE");
+    c->pipeline = (pl && pl[0] == '0') ? 0 : 1;
     const char *inw = getenv("FPT_B200_FUSED_WIN");
     c->fused_inwin = (inw && inw[0] == '1') ? 1 : 0;
     *out = c;
@@ -224,6 +230,11 @@ int fpt_ctx_destroy(fpt_ctx *ctx) {
     for (auto &b : ctx->h_out) b.release();
     for (auto &s : ctx->prof_pending) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto e : ctx->ev_in) cudaEventDestroy(e);
+    for (auto e : ctx->ev_comp) cudaEventDestroy(e);
+    for (auto e : ctx->ev_out) cudaEventDestroy(e);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FPT_OK;
@@ -574,6 +585,147 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     return FPT_OK;
 }
 
+// FPT_MEM_HOST scoring of a large batch as a three-stage pipeline over chunks of whole intervals:
+// copy-in stream (the track, piece by piece) -> compute stream (the scoring kernels of one chunk, into
+// one of two device output sets) -> copy-out stream (that chunk's outputs to the caller's arrays).
+// Chunks are independent batches over the shared device track, so the kernels are unchanged; with
+// pinned host arrays the three stages overlap and the call runs at PCIe speed in the slower direction.
+static int score_host_pipelined(fpt_ctx *ctx, const fpt_score_args *a, int n_chunks) {
+    const size_t nt = (size_t)a->n_track, tot = (size_t)a->total, niv = (size_t)a->n_iv;
+    const int pad = a->half_win_width + a->smoothing_half_win_width;
+    const size_t mult = a->combine_strands ? 1 : 2;
+    if (!ctx->s_in) {
+        CU(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    }
+    auto grow = [](std::vector<cudaEvent_t> &v, size_t n) -> cudaError_t {
+        while (v.size() < n) {
+            cudaEvent_t e;
+            cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            if (rc != cudaSuccess) return rc;
+            v.push_back(e);
+        }
+        return cudaSuccess;
+    };
+    CU(grow(ctx->ev_in, n_chunks)); CU(grow(ctx->ev_comp, n_chunks)); CU(grow(ctx->ev_out, n_chunks));
+
+    // chunk boundaries (interval indices) at equal shares of the scored positions
+    std::vector<int64_t> first(n_chunks + 1, 0);
+    {
+        int64_t k = 0;
+        for (int c = 1; c < n_chunks; ++c) {
+            const int64_t want = (int64_t)((double)tot * c / n_chunks);
+            while (k < (int64_t)niv && a->out_off[k] < want) ++k;
+            first[c] = k;
+        }
+        first[n_chunks] = (int64_t)niv;
+    }
+    // track pieces: with intervals in track order chunk c needs the track up to piece_end[c] only
+    bool monotone = true;
+    for (size_t k = 1; k < niv && monotone; ++k) monotone = a->iv_start[k] >= a->iv_start[k - 1];
+    std::vector<int64_t> piece_end(n_chunks, (int64_t)nt);
+    if (monotone) {
+        for (int c = 0; c + 1 < n_chunks; ++c) {
+            int64_t e = 0;
+            if (first[c + 1] > first[c]) {
+                const int64_t j = first[c + 1] - 1;
+                e = a->iv_start[j] + (a->out_off[j + 1] - a->out_off[j]) + pad + 64;
+            }
+            e = (e + 31) / 32 * 32;
+            if (c > 0 && e < piece_end[c - 1]) e = piece_end[c - 1];
+            piece_end[c] = e < (int64_t)nt ? (e < 0 ? 0 : e) : (int64_t)nt;
+        }
+    }
+    // rebased output offsets, chunk after chunk (n_c + 1 entries each)
+    std::vector<int64_t> reb(niv + n_chunks);
+    size_t max_tot = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t o0 = a->out_off[first[c]];
+        for (int64_t j = first[c]; j <= first[c + 1]; ++j) reb[(size_t)(j + c)] = a->out_off[j] - o0;
+        const size_t tc = (size_t)(a->out_off[first[c + 1]] - o0);
+        if (tc > max_tot) max_tot = tc;
+    }
+    const size_t w2 = (nt + 15) / 16 * 4, wm = (nt + 31) / 32 * 4;
+    CU(ctx->h_in[0].need(w2 ? w2 : 4)); CU(ctx->h_in[1].need(wm ? wm : 4));
+    CU(ctx->h_in[2].need(nt * 4 + 4)); CU(ctx->h_in[3].need(nt * 4 + 4));
+    CU(ctx->h_in[4].need(niv * 8)); CU(ctx->h_in[5].need(reb.size() * 8));
+    struct OutSpec { double *host; size_t rows; DevBuf *buf; };
+    OutSpec outs[5] = {{a->exp_out, mult, &ctx->h_out[0]}, {a->obs_out, mult, &ctx->h_out[1]},
+                       {a->win_out, mult, &ctx->h_out[2]}, {a->pval_out, 1, &ctx->h_out[3]},
+                       {a->winp_out, (size_t)a->n_scales, &ctx->h_out[4]}};
+    const size_t set_stride = (max_tot + 3) & ~(size_t)3;  // doubles per row of one output set
+    for (auto &o : outs)
+        if (o.host && o.rows) CU(o.buf->need(2 * o.rows * set_stride * sizeof(double)));
+    int64_t *d_hist = nullptr;
+    const size_t hb = a->hist ? (size_t)a->hist_d0 * a->hist_d1 * sizeof(int64_t) : 0;
+    // all streams start after whatever is queued on the compute stream
+    CU(cudaEventRecord(ctx->ev_comp[0], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[0], 0));
+    CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[0], 0));
+    CU(cudaMemcpyAsync(ctx->h_in[4].p, a->iv_start, niv * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    CU(cudaMemcpyAsync(ctx->h_in[5].p, reb.data(), reb.size() * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    if (a->hist) {
+        CU(ctx->h_out[5].need(hb));
+        d_hist = ctx->h_out[5].as<int64_t>();
+        CU(cudaMemcpyAsync(d_hist, a->hist, hb, cudaMemcpyHostToDevice, ctx->s_in));
+    }
+    int64_t done = 0;  // track positions already queued for upload
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t e = piece_end[c];
+        if (e > done) {
+            const size_t b0 = (size_t)done, b1 = (size_t)e;
+            CU(cudaMemcpyAsync((char *)ctx->h_in[2].p + b0 * 4, a->cuts_plus + b0, (b1 - b0) * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            CU(cudaMemcpyAsync((char *)ctx->h_in[3].p + b0 * 4, a->cuts_minus + b0, (b1 - b0) * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            if (a->seq2) {
+                const size_t s0 = b0 / 16, s1 = b1 == nt ? (nt + 15) / 16 : b1 / 16;
+                const size_t m0 = b0 / 32, m1 = b1 == nt ? (nt + 31) / 32 : b1 / 32;
+                CU(cudaMemcpyAsync((uint32_t *)ctx->h_in[0].p + s0, a->seq2 + s0, (s1 - s0) * 4, cudaMemcpyHostToDevice, ctx->s_in));
+                CU(cudaMemcpyAsync((uint32_t *)ctx->h_in[1].p + m0, a->nmask + m0, (m1 - m0) * 4, cudaMemcpyHostToDevice, ctx->s_in));
+            }
+            done = e;
+        }
+        CU(cudaEventRecord(ctx->ev_in[c], ctx->s_in));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t f0 = first[c], f1 = first[c + 1];
+        const int64_t o0 = a->out_off[f0];
+        const size_t tc = (size_t)(a->out_off[f1] - o0);
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[c], 0));
+        if (c >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[c - 2], 0));  // its output set is free again
+        if (tc > 0) {
+            fpt_score_args d = *a;
+            d.seq2 = a->seq2 ? ctx->h_in[0].as<uint32_t>() : nullptr;
+            d.nmask = a->nmask ? ctx->h_in[1].as<uint32_t>() : nullptr;
+            d.cuts_plus = ctx->h_in[2].as<uint32_t>();
+            d.cuts_minus = ctx->h_in[3].as<uint32_t>();
+            d.iv_start = ctx->h_in[4].as<int64_t>() + f0;
+            d.out_off = ctx->h_in[5].as<int64_t>() + f0 + c;
+            d.n_iv = f1 - f0;
+            d.total = (int64_t)tc;
+            double **dev[5] = {&d.exp_out, &d.obs_out, &d.win_out, &d.pval_out, &d.winp_out};
+            for (int i = 0; i < 5; ++i)
+                *dev[i] = (outs[i].host && outs[i].rows) ? outs[i].buf->as<double>() + (size_t)(c & 1) * outs[i].rows * set_stride
+                                                         : nullptr;
+            d.hist = d_hist;
+            // rows of one set are tc apart on the device (the kernels use `total` as the row stride)
+            int rc = score_device(ctx, &d);
+            if (rc != FPT_OK) return rc;
+            CU(cudaEventRecord(ctx->ev_comp[c], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[c], 0));
+            for (int i = 0; i < 5; ++i) {
+                if (!*dev[i]) continue;
+                for (size_t r = 0; r < outs[i].rows; ++r)
+                    CU(cudaMemcpyAsync(outs[i].host + r * tot + (size_t)o0, *dev[i] + r * tc, tc * sizeof(double),
+                                       cudaMemcpyDeviceToHost, ctx->s_out));
+            }
+        }
+        CU(cudaEventRecord(ctx->ev_out[c], ctx->s_out));
+    }
+    if (a->hist) CU(cudaMemcpyAsync(a->hist, d_hist, hb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->s_out));
+    return check_status(ctx, "fpt_score");
+}
+
 int fpt_score(fpt_ctx *ctx, const fpt_score_args *a, int mem) {
     if (!ctx || !a) return fail(FPT_ERR_ARG, "fpt_score: NULL argument");
     if (!ctx->has_bias) return fail(FPT_ERR_STATE, "fpt_score: no bias model uploaded (fpt_bias_upload)");
@@ -609,6 +761,11 @@ int fpt_score(fpt_ctx *ctx, const fpt_score_args *a, int mem) {
 
     // ---- host buffers: stage in, run, stage out ---------------------------------------------------
     if (a->out_off[a->n_iv] != a->total) return fail(FPT_ERR_ARG, "fpt_score: total != out_off[n_iv]");
+    if (ctx->pipeline && a->total >= (int64_t)4 << 20 && a->n_iv >= 64) {
+        int n_chunks = (int)(a->total / ((int64_t)3 << 20));
+        if (n_chunks > 48) n_chunks = 48;
+        if (n_chunks >= 2) return score_host_pipelined(ctx, a, n_chunks);
+    }
     fpt_score_args d = *a;
     const size_t nt = (size_t)a->n_track, tot = (size_t)a->total, niv = (size_t)a->n_iv;
     const size_t w2 = (nt + 15) / 16 * 4, wm = (nt + 31) / 32 * 4;

@@ -299,3 +299,76 @@ def _slice_batch(batch, lo, hi):
                                 np.ascontiguousarray(batch.cuts_plus[t0:t1]), np.ascontiguousarray(batch.cuts_minus[t0:t1]),
                                 t1 - t0, batch.iv_start[lo:hi] - t0, batch.out_off[lo:hi + 1] - batch.out_off[lo],
                                 batch.block_off[lo:hi + 1] - t0)
+
+
+def _ctx_with_env(**env):
+    """A fresh context created under the given environment (the library reads its switches at creation)."""
+    import os
+
+    from footprint_tools import _native
+
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return _native.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("shuffled", [False, True])
+def test_host_pipeline_equals_single_shot(table, shuffled):
+    """FPT_MEM_HOST on a batch large enough for the chunked copy-in / score / copy-out pipeline gives the
+    same bytes as the single-shot staging path, also when the intervals are not in track order."""
+    batch, _ = synth.make_batch(16000, 55, seed=61, table=table)
+    if shuffled:
+        perm = np.random.Generator(np.random.PCG64(3)).permutation(batch.n_iv)
+        lens = np.diff(batch.out_off)[perm]
+        out_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        batch = engine.IntervalBatch(batch.seq2, batch.nmask, batch.cuts_plus, batch.cuts_minus, batch.n_track,
+                                     batch.iv_start[perm], out_off, batch.block_off)
+    assert batch.total >= 4 << 20
+    res = {}
+    for name, env in (("pipe", {"FPT_B200_PIPELINE": 1}), ("single", {"FPT_B200_PIPELINE": 0})):
+        c = _ctx_with_env(**env)
+        c.set_bias(table, 1e-6)
+        c.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+        hist = np.zeros((200, 1000), dtype=np.int64)
+        out = engine.score_host(c, batch, 5, 50, 0.01, (3, 5, 7), hist=hist)
+        out["hist"] = hist
+        res[name] = out
+        c.close()
+    for k in res["pipe"]:
+        assert np.array_equal(res["pipe"][k], res["single"][k], equal_nan=True), k
+
+
+def test_scoring_paths_agree(table, oracle):
+    """The general kernel, the two-kernel throughput path and the fused kernel (windows streamed or in
+    the kernel) give identical exp / obs / p / histogram and windowed p-values within the parity bar; a
+    batch with cut counts beyond the fused kernel's packed range exercises its hand-back to the general
+    kernel."""
+    for depth in (1.0, 30.0):
+        batch, info = synth.make_batch(1500, 55, seed=71, table=table, depth_scale=depth)
+        outs = {}
+        for name, env in (("general", {"FPT_B200_PATH": "general"}), ("fast", {"FPT_B200_PATH": "fast"}),
+                          ("fused", {"FPT_B200_PATH": "auto", "FPT_B200_FUSED_WIN": 0}),
+                          ("fused_inwin", {"FPT_B200_PATH": "auto", "FPT_B200_FUSED_WIN": 1})):
+            c = _ctx_with_env(**env)
+            c.set_bias(table, 1e-6)
+            c.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+            hist = np.zeros((200, 1000), dtype=np.int64)
+            o = engine.score_host(c, batch, 5, 50, 0.01, (3, 5, 7), hist=hist)
+            o["hist"] = hist
+            outs[name] = o
+            c.close()
+        ref = outs["general"]
+        for name in ("fast", "fused", "fused_inwin"):
+            for k in ("exp", "obs", "pval", "hist"):
+                assert np.array_equal(outs[name][k], ref[k], equal_nan=True), (name, k, depth)
+            assert_pvalues_close(outs[name]["winp"], ref["winp"], "%s winp depth %g" % (name, depth))
+        # the streamed and the in-kernel windows use the same arithmetic: same bits
+        assert np.array_equal(outs["fused"]["winp"], outs["fused_inwin"]["winp"], equal_nan=True)
+        assert np.array_equal(outs["fused"]["winp"], outs["fast"]["winp"], equal_nan=True)
