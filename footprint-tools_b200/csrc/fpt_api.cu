@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fpt_internal.h"
@@ -90,7 +92,12 @@ struct fpt_ctx {
     // pipelined FPT_MEM_HOST scoring: copy-in / copy-out streams and per-chunk events
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_comp, ev_out;
+    int64_t last_h2d = 0, last_d2h = 0;  // bytes the last FPT_MEM_HOST fpt_score moved over PCIe
     int pipeline = 1;  // FPT_B200_PIPELINE=0: single-shot staging (copy in, score, copy out)
+    int narrow = 1;    // FPT_B200_NARROW=0: expected / observed counts cross PCIe as float64 instead of uint32
+    uint32_t *pin_counts = nullptr;  // pinned host staging of the uint32 counts (2 x rows x total)
+    size_t pin_cap = 0;
+    DevBuf d_counts;                 // device side of the same (two chunk sets)
     // per-kernel CUDA-event timers (fpt_ctx_profile)
     bool prof = false;
     struct ProfSlot { cudaEvent_t a, b; int kid; };
@@ -208,6 +215,8 @@ int fpt_ctx_create(int device, fpt_ctx **out) {
     if (path && !strcmp(path, "fast")) c->allow_fused = 0;
     const char *pl = getenv("FPT_B200_PIPELINE");
     c->pipeline = (pl && pl[0] == '0') ? 0 : 1;
+    const char *nr = getenv("FPT_B200_NARROW");
+    c->narrow = (nr && nr[0] == '0') ? 0 : 1;
     const char *inw = getenv("FPT_B200_FUSED_WIN");
     c->fused_inwin = (inw && inw[0] == '1') ? 1 : 0;
     *out = c;
@@ -233,6 +242,8 @@ int fpt_ctx_destroy(fpt_ctx *ctx) {
     for (auto e : ctx->ev_in) cudaEventDestroy(e);
     for (auto e : ctx->ev_comp) cudaEventDestroy(e);
     for (auto e : ctx->ev_out) cudaEventDestroy(e);
+    if (ctx->pin_counts) cudaFreeHost(ctx->pin_counts);
+    ctx->d_counts.release();
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->own_stream);
@@ -254,6 +265,13 @@ int fpt_ctx_sync(fpt_ctx *ctx) {
 }
 
 int64_t fpt_ctx_launch_count(const fpt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fpt_ctx_last_transfer(const fpt_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_ctx_last_transfer: ctx is NULL");
+    if (h2d_bytes) *h2d_bytes = ctx->last_h2d;
+    if (d2h_bytes) *d2h_bytes = ctx->last_d2h;
+    return FPT_OK;
+}
 
 int fpt_ctx_profile(fpt_ctx *ctx, int enable) {
     if (!ctx) return fail(FPT_ERR_ARG, "fpt_ctx_profile: ctx is NULL");
@@ -658,6 +676,53 @@ static int score_host_pipelined(fpt_ctx *ctx, const fpt_score_args *a, int n_chu
         if (o.host && o.rows) CU(o.buf->need(2 * o.rows * set_stride * sizeof(double)));
     int64_t *d_hist = nullptr;
     const size_t hb = a->hist ? (size_t)a->hist_d0 * a->hist_d1 * sizeof(int64_t) : 0;
+    // Expected / observed counts are integers: they are narrowed to uint32 on the device, cross PCIe as 4
+    // bytes each, land in pinned staging and are widened into the caller's float64 arrays by host
+    // threads while later chunks are still in flight (format conversion only, like fpt_pack_sequence).
+    const bool narrow = ctx->narrow && (a->exp_out || a->obs_out);
+    const size_t nrows = 2 * mult;  // staging rows: exp rows then obs rows, each `tot` long
+    if (narrow) {
+        const size_t need = nrows * tot;
+        if (need > ctx->pin_cap) {
+            if (ctx->pin_counts) cudaFreeHost(ctx->pin_counts);
+            ctx->pin_counts = nullptr; ctx->pin_cap = 0;
+            CU(cudaHostAlloc((void **)&ctx->pin_counts, (need + need / 8) * sizeof(uint32_t), cudaHostAllocDefault));
+            ctx->pin_cap = need + need / 8;
+        }
+        CU(ctx->d_counts.need(2 * nrows * set_stride * sizeof(uint32_t)));
+    }
+    std::atomic<int> enqueued{0};
+    std::atomic<bool> aborted{false};
+    std::vector<std::thread> workers;
+    const int n_workers = narrow ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 0;
+    if (narrow) {
+        double *hosts[2] = {a->exp_out, a->obs_out};
+        uint32_t *pin = ctx->pin_counts;
+        for (int w = 0; w < n_workers; ++w)
+            workers.emplace_back([&, w, pin, hosts]() {
+                for (int c = 0; c < n_chunks; ++c) {
+                    while (enqueued.load(std::memory_order_acquire) <= c) {
+                        if (aborted.load(std::memory_order_acquire)) return;
+                        std::this_thread::yield();
+                    }
+                    cudaEventSynchronize(ctx->ev_out[c]);
+                    const size_t o0 = (size_t)a->out_off[first[c]], o1 = (size_t)a->out_off[first[c + 1]];
+                    const size_t len = o1 - o0, lo = o0 + len * w / n_workers, hi = o0 + len * (w + 1) / n_workers;
+                    for (int which = 0; which < 2; ++which) {
+                        if (!hosts[which]) continue;
+                        for (size_t r = 0; r < mult; ++r) {
+                            const uint32_t *src = pin + ((size_t)which * mult + r) * tot;
+                            double *dst = hosts[which] + r * tot;
+                            for (size_t i = lo; i < hi; ++i) dst[i] = (double)src[i];
+                        }
+                    }
+                }
+            });
+    }
+    struct Joiner {  // the workers are always released and joined, also on an error return
+        std::atomic<bool> &ab; std::vector<std::thread> &ws;
+        ~Joiner() { ab.store(true, std::memory_order_release); for (auto &t : ws) if (t.joinable()) t.join(); }
+    } joiner{aborted, workers};
     // all streams start after whatever is queued on the compute stream
     CU(cudaEventRecord(ctx->ev_comp[0], ctx->stream));
     CU(cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[0], 0));
@@ -710,19 +775,39 @@ static int score_host_pipelined(fpt_ctx *ctx, const fpt_score_args *a, int n_chu
             // rows of one set are tc apart on the device (the kernels use `total` as the row stride)
             int rc = score_device(ctx, &d);
             if (rc != FPT_OK) return rc;
+            uint32_t *dcnt = narrow ? ctx->d_counts.as<uint32_t>() + (size_t)(c & 1) * nrows * set_stride : nullptr;
+            if (narrow) {
+                for (int which = 0; which < 2; ++which)
+                    if (*dev[which])
+                        CU(launch_counts_to_u32(ctx->stream, *dev[which], (long long)(mult * tc),
+                                                dcnt + (size_t)which * mult * set_stride, ctx->sm_count));
+            }
             CU(cudaEventRecord(ctx->ev_comp[c], ctx->stream));
             CU(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[c], 0));
             for (int i = 0; i < 5; ++i) {
                 if (!*dev[i]) continue;
+                if (narrow && i < 2) {
+                    for (size_t r = 0; r < mult; ++r)
+                        CU(cudaMemcpyAsync(ctx->pin_counts + ((size_t)i * mult + r) * tot + (size_t)o0,
+                                           dcnt + (size_t)i * mult * set_stride + r * tc, tc * sizeof(uint32_t),
+                                           cudaMemcpyDeviceToHost, ctx->s_out));
+                    continue;
+                }
                 for (size_t r = 0; r < outs[i].rows; ++r)
                     CU(cudaMemcpyAsync(outs[i].host + r * tot + (size_t)o0, *dev[i] + r * tc, tc * sizeof(double),
                                        cudaMemcpyDeviceToHost, ctx->s_out));
             }
         }
         CU(cudaEventRecord(ctx->ev_out[c], ctx->s_out));
+        enqueued.store(c + 1, std::memory_order_release);
     }
     if (a->hist) CU(cudaMemcpyAsync(a->hist, d_hist, hb, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->last_h2d = (int64_t)(nt * 8 + (a->seq2 ? w2 + wm : 0) + niv * 8 + reb.size() * 8 + hb);
+    ctx->last_d2h = (int64_t)hb;
+    for (int i = 0; i < 5; ++i)
+        if (outs[i].host && outs[i].rows) ctx->last_d2h += (int64_t)(outs[i].rows * tot * ((narrow && i < 2) ? 4 : 8));
     CU(cudaStreamSynchronize(ctx->s_out));
+    for (auto &t : workers) t.join();
     return check_status(ctx, "fpt_score");
 }
 
@@ -804,8 +889,13 @@ int fpt_score(fpt_ctx *ctx, const fpt_score_args *a, int mem) {
     }
     int rc = score_device(ctx, &d);
     if (rc != FPT_OK) return rc;
+    ctx->last_h2d = (int64_t)(nt * 8 + (a->seq2 ? w2 + wm : 0) + niv * 16 + 8);
+    ctx->last_d2h = 0;
     for (int i = 0; i < 5; ++i)
-        if (*outs[i].dev) CU(cudaMemcpyAsync(outs[i].host, *outs[i].dev, outs[i].n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (*outs[i].dev) {
+            CU(cudaMemcpyAsync(outs[i].host, *outs[i].dev, outs[i].n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            ctx->last_d2h += (int64_t)(outs[i].n * sizeof(double));
+        }
     if (a->hist)
         CU(cudaMemcpyAsync(a->hist, d.hist, (size_t)a->hist_d0 * a->hist_d1 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     return check_status(ctx, "fpt_score");

@@ -109,6 +109,7 @@ cudaError_t launch_nb_values(cudaStream_t st, const double *dm, const double *e,
                              int what, int model_index, long long row_len, int model_stride, double *out);
 cudaError_t launch_window(cudaStream_t st, const double *x, const double *w, long long n, const long long *seg_off,
                           long long n_seg, int hw, int op, double *scratch, double *out);
+cudaError_t launch_counts_to_u32(cudaStream_t st, const double *x, long long n, uint32_t *out, int sm_count);
 cudaError_t launch_hist2d(cudaStream_t st, const double *e, const double *o, long long n, unsigned long long *hist,
                           int d0, int d1);
 cudaError_t launch_posterior(cudaStream_t st, const double *dm, const double *obs, const double *exp,

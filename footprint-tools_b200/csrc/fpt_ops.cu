@@ -336,6 +336,26 @@ cudaError_t launch_window(cudaStream_t st, const double *x, const double *w, lon
     return cudaGetLastError();
 }
 
+// Integer-valued doubles (expected / observed counts) -> uint32, for the host pipeline's copy-out: the
+// counts cross PCIe as 4 bytes and are widened back to float64 by the host (fpt_api.cu).
+__global__ void counts_to_u32_kernel(const double *__restrict__ x, long long n, uint32_t *__restrict__ out) {
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const double2 a = reinterpret_cast<const double2 *>(x)[2 * i], b = reinterpret_cast<const double2 *>(x)[2 * i + 1];
+        reinterpret_cast<uint4 *>(out)[i] = make_uint4((unsigned)a.x, (unsigned)a.y, (unsigned)b.x, (unsigned)b.y);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(n4 << 2) + threadIdx.x] = (unsigned)x[(n4 << 2) + threadIdx.x];
+}
+
+cudaError_t launch_counts_to_u32(cudaStream_t st, const double *x, long long n, uint32_t *out, int sm_count) {
+    if (n <= 0) return cudaSuccess;
+    long long blocks = ((n >> 2) + 255) / 256;
+    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    counts_to_u32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_hist2d(cudaStream_t st, const double *e, const double *o, long long n, unsigned long long *hist,
                           int d0, int d1) {
     if (n <= 0) return cudaSuccess;

@@ -66,6 +66,7 @@ SIGNATURES = {
     "fpt_ctx_sync": (C.c_int, [C.c_void_p]),
     "fpt_ctx_check": (C.c_int, [C.c_void_p]),
     "fpt_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "fpt_ctx_last_transfer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fpt_ctx_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "fpt_ctx_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fpt_bias_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
@@ -181,6 +182,12 @@ class Context(object):
     @property
     def launches(self):
         return int(lib().fpt_ctx_launch_count(self._h))
+
+    def last_transfer(self):
+        """(h2d_bytes, d2h_bytes) of the last FPT_MEM_HOST score call."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(lib().fpt_ctx_last_transfer(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo", "direct_fix")
 

@@ -86,6 +86,9 @@ int64_t fpt_ctx_launch_count(const fpt_ctx *ctx);
 #define FPT_KERNEL_DIRECT_FIX 6    /* NB p-values of the positions outside the (exp, obs) table */
 #define FPT_KERNEL_COUNT 7
 int fpt_ctx_profile(fpt_ctx *ctx, int enable);
+/* Bytes the last FPT_MEM_HOST fpt_score call copied host->device and device->host (expected and
+ * observed counts cross as uint32 and are widened to float64 on the host in the pipelined path). */
+int fpt_ctx_last_transfer(const fpt_ctx *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int fpt_ctx_profile_read(fpt_ctx *ctx, double *total_ms, int64_t *launches);
 
 /* ---- models ------------------------------------------------------------------------------- */
