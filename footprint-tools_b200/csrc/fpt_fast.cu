@@ -50,6 +50,9 @@ __device__ __forceinline__ void ld256(const double *p, double &a, double &b, dou
 // five 256-bit loads (neighbouring threads overlap in L1). Windows never need interval geometry:
 // a window that would cross an interval end is exactly the one the edge rule sets to 1.0.
 __global__ void __launch_bounds__(256, 2) window_fast_kernel(const WindowParams W) {
+    __shared__ double s4[4];
+    ndtr4_table_init(s4, threadIdx.x);
+    __syncthreads();
     const long long ngroups = (W.total + 3) >> 2;
     unsigned want = 0;
 #pragma unroll
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(256, 2) window_fast_kernel(const WindowParams 
                 if (hq[k] < 0) break;
                 const int h = hq[k];
                 double res[4];
-                ndtr4(A[k], res);
+                ndtr4(A[k], s4, res);
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     if ((int)((edge4 >> (8 * e)) & 0xFFu) < h) res[e] = 1.0;  // closer than h to an interval end
@@ -119,6 +122,94 @@ __global__ void __launch_bounds__(256, 2) window_fast_kernel(const WindowParams 
                 }
             }
         }
+    }
+}
+
+// Same windows with the half-widths fixed at compile time (H0 < H1 < H2, -1 = absent): the combinations the
+// reference's programs ask for (`ftd detect` uses 3, cli/detect.py:84; the multi-scale configuration 3/5/7).
+// Nothing is predicated on the scale list: the instruction stream is the 2*H sums, the normal tails and the
+// stores. Software-pipelined over the grid-stride loop: once the sums of a group are formed its z values are
+// dead, so the 256-bit loads of the thread's NEXT group are issued into those registers before the normal
+// tails of the current one are evaluated — HBM latency is covered by ~800 instructions of arithmetic instead
+// of being waited for at the top of each iteration. Same arithmetic in the same order as window_fast_kernel,
+// hence the same bits.
+#ifndef FPT_WIN_CTAS
+#define FPT_WIN_CTAS 2  // CTAs per SM the fixed-scale window kernel is compiled for
+#endif
+#ifndef FPT_WIN_PIPE
+#define FPT_WIN_PIPE 1
+#endif
+#ifndef FPT_WIN_WAVES
+#define FPT_WIN_WAVES 4
+#endif
+template <int H0, int H1, int H2>
+__global__ void __launch_bounds__(256, FPT_WIN_CTAS) window_fixed_kernel(const WindowParams W) {
+    constexpr int HMAX = H2 >= 0 ? H2 : (H1 >= 0 ? H1 : H0);
+    constexpr int QLO = (8 - HMAX) / 4, QHI = (11 + HMAX) / 4;  // 256-bit loads q covering z[-HMAX .. 3 + HMAX]
+    __shared__ double s4[4];
+    ndtr4_table_init(s4, threadIdx.x);
+    __syncthreads();
+    const long long ngroups = (W.total + 3) >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double c0 = -W.inv_sqrt_k[H0], c1 = H1 >= 0 ? -W.inv_sqrt_k[H1 >= 0 ? H1 : 0] : 0.0,
+                 c2 = H2 >= 0 ? -W.inv_sqrt_k[H2 >= 0 ? H2 : 0] : 0.0;
+    long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    double z[20];  // z[8 + e] is element e of the group being summed
+    unsigned edge4;
+    auto load = [&](long long gg) {
+#pragma unroll
+        for (int q = QLO; q <= QHI; ++q)
+            ld256(W.z + (gg << 2) - 8 + 4 * q, z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+        edge4 = __ldg(reinterpret_cast<const unsigned *>(W.edge) + gg);
+    };
+    load(g);
+    for (; g < ngroups; g += stride) {
+        const long long f0 = g << 2;
+        const long long left = W.total - f0;
+        const unsigned omask = left >= 4 ? 0xFu : ((1u << (int)left) - 1u);
+        const unsigned edge_cur = edge4;
+        double A[3][4];
+        {
+            double acc[4] = {z[8], z[9], z[10], z[11]};
+#pragma unroll
+            for (int h = 0; h <= HMAX; ++h) {
+                if (h > 0) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[e] += z[8 + e - h] + z[8 + e + h];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (h == H0) A[0][e] = acc[e] * c0;
+                    if (h == H1) A[1][e] = acc[e] * c1;
+                    if (h == H2) A[2][e] = acc[e] * c2;
+                }
+            }
+        }
+        if (FPT_WIN_PIPE && g + stride < ngroups) load(g + stride);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int h = k == 0 ? H0 : (k == 1 ? H1 : H2);
+            if (h < 0) break;
+            double res[4];
+            ndtr4(A[k], s4, res);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((int)((edge_cur >> (8 * e)) & 0xFFu) < h) res[e] = 1.0;  // closer than h to an interval end
+            for (unsigned m = W.h_rows[h]; m; m &= m - 1) {
+                const int s = __ffs(m) - 1;
+                double *dst = W.winp_out + (size_t)s * W.total + f0;
+                if (omask == 0xFu && ((W.winp_vec >> s) & 1u)) {
+                    reinterpret_cast<double2 *>(dst)[0] = make_double2(res[0], res[1]);
+                    reinterpret_cast<double2 *>(dst)[1] = make_double2(res[2], res[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((omask >> e) & 1u) dst[e] = res[e];
+                }
+            }
+        }
+        if (!FPT_WIN_PIPE && g + stride < ngroups) load(g + stride);
     }
 }
 
@@ -652,7 +743,18 @@ cudaError_t launch_window_fast(cudaStream_t st, const WindowParams &w, int sm_co
     long long blocks = (ngroups + 255) / 256;
     const long long cap = (long long)sm_count * 16;
     if (blocks > cap) blocks = cap;
-    window_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(w);
+    // requested half-widths, ascending
+    int hs[kFastMaxScaleHalfWin + 1], nh = 0;
+    for (int h = 0; h <= kFastMaxScaleHalfWin; ++h)
+        if (w.h_rows[h]) hs[nh++] = h;
+    // fixed-scale kernels: a whole number of waves of FPT_WIN_CTAS CTAs per SM
+    long long pgrid = (long long)sm_count * FPT_WIN_CTAS * FPT_WIN_WAVES;
+    if (pgrid > blocks) pgrid = blocks;
+    if (nh == 3 && hs[0] == 3 && hs[1] == 5 && hs[2] == 7) window_fixed_kernel<3, 5, 7><<<(unsigned)pgrid, 256, 0, st>>>(w);
+    else if (nh == 1 && hs[0] == 3) window_fixed_kernel<3, -1, -1><<<(unsigned)pgrid, 256, 0, st>>>(w);
+    else if (nh == 1 && hs[0] == 5) window_fixed_kernel<5, -1, -1><<<(unsigned)pgrid, 256, 0, st>>>(w);
+    else if (nh == 1 && hs[0] == 7) window_fixed_kernel<7, -1, -1><<<(unsigned)pgrid, 256, 0, st>>>(w);
+    else window_fast_kernel<<<(unsigned)blocks, 256, 0, st>>>(w);
     return cudaGetLastError();
 }
 

@@ -162,7 +162,7 @@ constexpr int kZS = kFT + 4;  // row stride of the transposed z array: zsT[e * k
 // S_h = S_{h-1} + (z[-h] + z[+h]), each step needing one new value per side; up to three requested
 // half-widths are carried per pass so that the sums are the only live values while the normal tails
 // are evaluated.
-__device__ __forceinline__ void window_phase(const double *zsT, int tid, const ScoreParams &P, int dl, int dr,
+__device__ __forceinline__ void window_phase(const double *zsT, const double *s4, int tid, const ScoreParams &P, int dl, int dr,
                                              long long f0, unsigned omask) {
     unsigned pending = 0;
 #pragma unroll
@@ -207,7 +207,7 @@ __device__ __forceinline__ void window_phase(const double *zsT, int tid, const S
         for (int k = 0; k < 3; ++k) {
             if (hq[k] < 0) break;
             double res[4];
-            ndtr4(A[k], res);
+            ndtr4(A[k], s4, res);
             store_scale(res, hq[k], P.h_rows[hq[k]], P, dl, dr, f0, omask);
         }
     }
@@ -242,6 +242,8 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     double *zsT = reinterpret_cast<double *>(badflag + 4);                            // INWIN only: z of the tile, transposed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double q4tab[4];  // 2^(j/4) for ndtr4 (INWIN)
+    if (INWIN) ndtr4_table_init(q4tab, tid);
     const int WH = INWIN ? P.wh_max : 0;
     const bool want_win = INWIN && P.winp_out != nullptr && P.n_scales > 0;
     const bool want_z = !INWIN && P.z_out != nullptr;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
         // ---- previous sub-tile: stores of its p-values / z / edge distances, or (INWIN) its windows -----
         if (pend_omask) {
             if (INWIN) {
-                window_phase(zsT, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
+                window_phase(zsT, q4tab, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
             } else {
                 if (pend_omask == 0xFu && P.vec_ok) {
                     if (P.pval_out) st256(P.pval_out + pend_f0, pend_p[0], pend_p[1], pend_p[2], pend_p[3]);
@@ -718,7 +720,7 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     // the last sub-tile's deferred work
     if (pend_omask) {
         if (INWIN) {
-            window_phase(zsT, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
+            window_phase(zsT, q4tab, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)

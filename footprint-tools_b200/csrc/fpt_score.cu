@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
 
     if (P.tile_list && (long long)blockIdx.x >= (long long)*P.n_list) return;  // list mode: nothing for this CTA
     const int tid = threadIdx.x;
+    __shared__ double q4tab[4];  // 2^(j/4) for ndtr_fast1 (list mode; published by the kernel's first barrier)
+    ndtr4_table_init(q4tab, tid);
     const int lane = tid & 31, warp = tid >> 5;
     const int hw = P.hw, shw = P.shw, ktrim = P.ktrim;
     const int pad = hw + shw;
@@ -577,8 +579,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
                             const double a = acc * (-P.inv_sqrt_k[h]);
                             const double ta = fabs(a);
                             if (ta < 26.0) {
-                                const double tail = ndtr_tail_core(fmin(ta, 26.0));
-                                res = a > 0.0 ? 1.0 - tail : tail;
+                                res = ndtr_fast1(a, q4tab);
                             } else {
                                 res = ndtr_slow(a);
                             }

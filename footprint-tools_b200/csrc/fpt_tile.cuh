@@ -62,90 +62,155 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 // ---- normal lower tail for the Stouffer windows ------------------------------------------------
-// ndtr(a) = Phi(a) (reference: hcephes_ndtr, ndtr.c:34-59). For |a| < 26 it is evaluated as
-//   Q(t) = exp(-t^2/2) * F(u),  t = |a|,  u = (t - 5)/(t + 5),  F = 0.5*erfcx(t/sqrt 2)
-// with F a degree-16 polynomial (Chebyshev fit generated by tools/fit_ndtr.py against mpmath; max
-// relative error of Q over [0, 26]: 3.5e-13, i.e. < 2e-13 on -log10 p — the bar is 1e-9) and a
-// table-free exp (Cody-Waite reduction + degree-11 Taylor polynomial, |r| <= ln2/2). One branch-free
-// path for every lane instead of Cephes' three ranges. |a| >= 26 (p < 1e-149), infinities and NaN
-// go to the branch-for-branch Cephes replica ndtr_fn (fpt_math.cuh), which also reproduces the
-// reference's denormal exp(-a^2) behaviour above |a| = 26.6 and its NaN for infinite arguments.
-__constant__ double kNdF[17] = {8.34755278698498880e-08,  1.85387184289488118e-07,  -7.05646170130192722e-07,
-                                -1.23208123023565909e-06, 6.67121890420153935e-06,  9.47978503161857321e-07,
-                                -6.04384263432253854e-05, 1.34279562238030851e-04,  2.19553084872871904e-04,
-                                -2.37884470097069183e-03, 8.99137029253909911e-03,  -2.34139004594596037e-02,
-                                4.78553522966640513e-02,  -8.08838772654492111e-02, 1.16068811885835940e-01,
-                                -1.43457555263989955e-01, 7.69193049750059588e-02};
-__constant__ double kExpT[12] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0,
-                                 1.0 / 120.0,      1.0 / 24.0,      1.0 / 6.0,      0.5,           1.0,          1.0};
-
 __device__ __noinline__ double ndtr_slow(double a) { return ndtr_fn(a); }
 
-// branch-free core: Phi(-t) for 0 <= t < 26 (callers clamp; the clamped lanes are recomputed by ndtr_slow)
-__device__ __forceinline__ double ndtr_tail_core(double t) {
-    double r;
-    {
-        const double d = t + 5.0;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-        const double e = fma(-d, r, 1.0);
-        r = fma(r, e, r);  // 1/(t+5), relative error ~1e-14
+// ndtr(a) = Phi(a) (reference: hcephes_ndtr, ndtr.c:34-59) as the Stouffer windows of the throughput paths
+// evaluate it: one branch-free path for |a| < 26 instead of Cephes' three ranges, cut so that the FP64 pipe (64
+// lanes per SM, the unit the window arithmetic saturates) carries only the digits that need it:
+//   Q(t) = exp(-t^2/2) * G(u) / (t + 5),   G(u) = (t + 5) * 0.5 * erfcx(t / sqrt 2),  u = 1 - 10/(t + 5)
+//  * G is a degree-13 polynomial (Chebyshev fit against mpmath, tools/fit_ndtr.py --mixed); its seven
+//    highest-order coefficients (|c| <= 3e-3, contribution to G below 4e-3) are summed in FP32, the rest in
+//    FP64 — the FP32 rounding reaches G at 2e-11 relative;
+//  * exp(y) = 2^(n/4) * exp(q), |q| <= ln2/8: q^3/6 .. q^6/720 in FP32 (below 1.1e-4, i.e. 1e-11 of the result),
+//    1 + q + q^2/2 in FP64, 2^(j/4) from a 4-entry shared-memory table (one conflict-free LDS.64);
+//  * range test and sign handling on the high word (integer pipe).
+// Max relative error of Q over [0, 26]: 6e-11 (tools/fit_ndtr.py replays this exact operation order
+// against mpmath), i.e. <= 2.6e-11 absolute on -log10 p; the parity bar is 1e-9 relative. 24 FP64 operations
+// per value instead of 38. |a| >= 26, infinities and NaN go to the Cephes replica as before.
+// s4 = {1, 2^(1/4), 2^(1/2), 2^(3/4)} in shared memory (ndtr4_table_init).
+__device__ __forceinline__ void ndtr4_table_init(double *s4, int tid) {
+    if (tid < 4) {
+        s4[tid] = tid == 0 ? 1.0 : tid == 1 ? 1.18920711500272103e+00 : tid == 2 ? 1.41421356237309515e+00
+                                                                                  : 1.68179283050742900e+00;
     }
-    const double u = fma(-10.0, r, 1.0);
-    const double F = cpoly<17>(u, kNdF);
-    // exp(-t^2/2)
-    const double y = -0.5 * (t * t);
-    const double kf = fma(y, 1.4426950408889634, 6755399441055744.0);
-    const int n = __double2loint(kf);
-    const double nf = kf - 6755399441055744.0;
-    double q = fma(nf, -6.93147180369123816490e-01, y);
-    q = fma(nf, -1.90821492927058770002e-10, q);
-    const double pe = cpoly<12>(q, kExpT);
-    const double E = __hiloint2double(__double2hiint(pe) + (n << 20), __double2loint(pe));
-    return E * F;
 }
 
-// Phi(a) for 4 values at once (reference: hcephes_ndtr, ndtr.c:34-59; see ndtr_tail_core in fpt_tile.cuh for
-// the approximation). The four evaluations are written interleaved — two Horner chains per value, eight
-// independent dependency chains in flight — because a single chain leaves the FP64 pipe idle for most of
-// its latency. Same operations in the same order per value as ndtr_tail_core, hence the same bits.
-__device__ __forceinline__ void ndtr4(const double (&a)[4], double (&res)[4]) {
-    double u[4], q[4], F[4], pe[4];
+// Phi(a) for one value, |a| < 26: the same operations in the same order as one lane of ndtr4 (same bits)
+__device__ __forceinline__ double ndtr_fast1(double a, const double *s4) {
+    const double t = fabs(a);
+    const double d = __dadd_rn(t, 5.0);
+    double rr;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(d));
+    const double er = fma(-d, rr, 1.0);
+    rr = fma(rr, er, rr);
+    const double u = fma(-10.0, rr, 1.0);
+    const float uf = __double2float_rn(u);
+    const double y = __dmul_rn(-0.5, __dmul_rn(t, t));
+    const double kf = fma(y, 5.77078016355585355e+00, 6755399441055744.0);
+    const int n = __double2loint(kf);
+    const double nf = __dadd_rn(kf, -6755399441055744.0);
+    const double qq = fma(nf, -1.73286795092280954123e-01, y);
+    const double q = fma(nf, -4.77053732317646925005e-11, qq);
+    const float qf = __double2float_rn(q);
+    float Gf = fmaf(6.153616596e-06f, uf, 1.409234847e-05f);
+    Gf = fmaf(Gf, uf, -5.337512994e-05f);
+    Gf = fmaf(Gf, uf, -5.887623411e-05f);
+    Gf = fmaf(Gf, uf, 5.470084143e-04f);
+    Gf = fmaf(Gf, uf, -7.975917542e-04f);
+    Gf = fmaf(Gf, uf, -2.993954578e-03f);
+    float Rf = fmaf(1.0f / 720.0f, qf, 1.0f / 120.0f);
+    Rf = fmaf(Rf, qf, 1.0f / 24.0f);
+    Rf = fmaf(Rf, qf, 1.0f / 6.0f);
+    double G = fma((double)Gf, u, 2.07949308206693863e-02);
+    G = fma(G, u, -6.91185624438261093e-02);
+    G = fma(G, u, 1.65020386126410318e-01);
+    G = fma(G, u, -3.13533160990166759e-01);
+    G = fma(G, u, 4.95305615008850841e-01);
+    G = fma(G, u, -6.65382502818922417e-01);
+    G = fma(G, u, 7.69193049757243230e-01);
+    double pe = fma((double)Rf, q, 0.5);
+    pe = fma(pe, q, 1.0);
+    pe = fma(pe, q, 1.0);
+    pe = __dmul_rn(pe, s4[n & 3]);
+    const double E = __hiloint2double(__double2hiint(pe) + ((n >> 2) << 20), __double2loint(pe));
+    const double erq = __dmul_rn(E, rr);
+    return __double2hiint(a) < 0 ? __dmul_rn(erq, G) : __fma_rn(-erq, G, 1.0);
+}
+
+// Phi(a) for 4 values at once: four ndtr_fast1 evaluations written interleaved (two FP64 and two FP32
+// Horner chains per value in flight), because a single chain leaves the pipes idle for most of its latency.
+__device__ __forceinline__ void ndtr4(const double (&a)[4], const double *s4, double (&res)[4]) {
+    double u[4], q[4], r[4];
+    float uf[4], qf[4], Gf[4], Rf[4];
     int n[4];
     bool slow = false;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const double ta = fabs(a[e]);
-        slow |= !(ta < 26.0);
-        const double t = fmin(ta, 26.0);
-        const double d = t + 5.0;
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-        const double er = fma(-d, r, 1.0);
-        r = fma(r, er, r);
-        u[e] = fma(-10.0, r, 1.0);
-        const double y = -0.5 * (t * t);
-        const double kf = fma(y, 1.4426950408889634, 6755399441055744.0);
+        const unsigned ahi = (unsigned)__double2hiint(a[e]) & 0x7FFFFFFFu;
+        slow |= ahi >= 0x403A0000u;  // |a| >= 26, infinite or NaN (recomputed below; the values computed here are unused)
+        const double t = __hiloint2double((int)ahi, __double2loint(a[e]));
+        const double d = __dadd_rn(t, 5.0);
+        double rr;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(d));
+        const double er = fma(-d, rr, 1.0);
+        rr = fma(rr, er, rr);  // 1/(t+5), relative error < 1e-12
+        r[e] = rr;
+        u[e] = fma(-10.0, rr, 1.0);
+        uf[e] = __double2float_rn(u[e]);
+        const double y = __dmul_rn(-0.5, __dmul_rn(t, t));
+        const double kf = fma(y, 5.77078016355585355e+00, 6755399441055744.0);  // rint(y * 4/ln2) in the low word
         n[e] = __double2loint(kf);
-        const double nf = kf - 6755399441055744.0;
-        double qq = fma(nf, -6.93147180369123816490e-01, y);
-        q[e] = fma(nf, -1.90821492927058770002e-10, qq);
-        F[e] = kNdF[0];
-        pe[e] = kExpT[0];
-    }
-#pragma unroll
-    for (int i = 1; i < 17; ++i) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) F[e] = fma(F[e], u[e], kNdF[i]);
-        if (i < 12) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pe[e] = fma(pe[e], q[e], kExpT[i]);
-        }
+        const double nf = __dadd_rn(kf, -6755399441055744.0);
+        const double qq = fma(nf, -1.73286795092280954123e-01, y);  // ln2/4 split: the high part has 32 significant bits
+        q[e] = fma(nf, -4.77053732317646925005e-11, qq);
+        qf[e] = __double2float_rn(q[e]);
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const double E = __hiloint2double(__double2hiint(pe[e]) + (n[e] << 20), __double2loint(pe[e]));
-        const double tail = E * F[e];
-        res[e] = a[e] > 0.0 ? 1.0 - tail : tail;
+        Gf[e] = fmaf(6.153616596e-06f, uf[e], 1.409234847e-05f);
+        Rf[e] = fmaf(1.0f / 720.0f, qf[e], 1.0f / 120.0f);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        Gf[e] = fmaf(Gf[e], uf[e], -5.337512994e-05f);
+        Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 24.0f);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        Gf[e] = fmaf(Gf[e], uf[e], -5.887623411e-05f);
+        Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 6.0f);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], 5.470084143e-04f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -7.975917542e-04f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -2.993954578e-03f);
+    double G[4], pe[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        G[e] = fma((double)Gf[e], u[e], 2.07949308206693863e-02);
+        pe[e] = fma((double)Rf[e], q[e], 0.5);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        G[e] = fma(G[e], u[e], -6.91185624438261093e-02);
+        pe[e] = fma(pe[e], q[e], 1.0);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        G[e] = fma(G[e], u[e], 1.65020386126410318e-01);
+        pe[e] = fma(pe[e], q[e], 1.0);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        G[e] = fma(G[e], u[e], -3.13533160990166759e-01);
+        pe[e] = __dmul_rn(pe[e], s4[n[e] & 3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], 4.95305615008850841e-01);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], -6.65382502818922417e-01);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], 7.69193049757243230e-01);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double E = __hiloint2double(__double2hiint(pe[e]) + ((n[e] >> 2) << 20), __double2loint(pe[e]));
+        // explicit operations: an implicit contraction of 1 - tail would differ between the kernels that inline this
+        const double er = __dmul_rn(E, r[e]);
+        const double tail = __dmul_rn(er, G[e]);
+        const double up = __fma_rn(-er, G[e], 1.0);
+        res[e] = __double2hiint(a[e]) < 0 ? tail : up;
     }
     if (slow) {  // |a| >= 26, infinite or NaN: the Cephes replica (rare)
 #pragma unroll
