@@ -220,7 +220,7 @@ __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gs
 }
 
 #ifndef FPT_FAST_CTAS
-#define FPT_FAST_CTAS 2
+#define FPT_FAST_CTAS (512 / FPT_FAST_THREADS)
 #endif
 template <int HW>
 __global__ void __launch_bounds__(kFT, FPT_FAST_CTAS) score_fast_kernel(const ScoreParams P) {

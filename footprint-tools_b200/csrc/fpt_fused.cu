@@ -45,6 +45,49 @@ __device__ __forceinline__ unsigned hi16(unsigned w) { return w >> 16; }
 __device__ __forceinline__ uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 __device__ __forceinline__ uint4 ldg128(const uint32_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 
+// Asynchronous global -> shared copies (LDGSTS): the data never passes through registers, so a thread can have
+// a whole sub-tile's worth of cut counts in flight while it computes. src_bytes < size zero-fills the rest.
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// Issues the copies of one sub-tile's cut counts into the raw staging arrays: rawP[x] = cuts+[G0 + x],
+// rawM[x] = cuts-[G0 + x], lead[x / 4] = cuts-[G0 + x - 1] for the first slot x of each group of 4 (the
+// minus strand is paired one position to the left, cli/detect.py:121-122). Positions outside the track read 0.
+__device__ __forceinline__ void stage_cuts_async(const ScoreParams &P, const FastRegions *R, uint32_t *rawP,
+                                                 uint32_t *rawM, uint32_t *lead, int tid) {
+    const int nreg = R->nreg;
+    const int NXG = R->xblk[nreg] >> 2;
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+        const int xg = tid + rd * kFT;
+        if (xg >= NXG) break;
+        const int x = xg << 2;
+        const int rx = fregion_of(R->xblk, nreg, x);
+        const long long g = R->G0[rx] + x;
+        if (P.cuts_vec && ((g & 3) == 0) && g >= 0 && g + 4 <= P.n_track) {
+            cp_async_16(rawP + x, P.cuts_p + g, 16);
+            cp_async_16(rawM + x, P.cuts_m + g, 16);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long ge = g + e;
+                const bool ok = ge >= 0 && ge < P.n_track;
+                cp_async_4(rawP + x + e, P.cuts_p + (ok ? ge : 0), ok ? 4 : 0);
+                cp_async_4(rawM + x + e, P.cuts_m + (ok ? ge : 0), ok ? 4 : 0);
+            }
+        }
+        const bool okl = g >= 1 && g - 1 < P.n_track;
+        cp_async_4(lead + xg, P.cuts_m + (okl ? g - 1 : 0), okl ? 4 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __device__ __forceinline__ uint4 agg(const uint4 a, const uint4 b) {
     return make_uint4(vmin2(a.x, b.x), vmax2(a.y, b.y), a.z + b.z, a.w + b.w);
 }
@@ -214,10 +257,10 @@ __device__ __forceinline__ void window_phase(const double *zsT, const double *s4
 }
 
 #ifndef FPT_FUSED_CTAS
-#define FPT_FUSED_CTAS 3   // CTAs per SM the in-kernel-window variant is compiled for (80 registers)
+#define FPT_FUSED_CTAS (768 / FPT_FAST_THREADS)   // CTAs per SM the in-kernel-window variant is compiled for (80 registers)
 #endif
 #ifndef FPT_SPLIT_CTAS
-#define FPT_SPLIT_CTAS 2   // same for the variant that leaves the windows to the streaming kernel
+#define FPT_SPLIT_CTAS (512 / FPT_FAST_THREADS)   // same for the variant that leaves the windows to the streaming kernel (128 registers)
 #endif
 
 // SMOOTH: smoothing half-width 50 with one value trimmed per side (else no smoothing).
@@ -239,7 +282,10 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     double *dmp = reinterpret_cast<double *>(GB + kNG + kGPad);                       // 24
     FastRegions *Rbuf = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);         // double-buffered
     int *badflag = reinterpret_cast<int *>(Rbuf + 2);                                 // [2] (+ pad to 16 bytes)
-    double *zsT = reinterpret_cast<double *>(badflag + 4);                            // INWIN only: z of the tile, transposed
+    uint32_t *rawP = reinterpret_cast<uint32_t *>(badflag + 4);                       // raw cut counts of the sub-tile being
+    uint32_t *rawM = rawP + kXCap;                                                    //   copied in (cp.async), per strand
+    uint32_t *lead = rawM + kXCap;                                                    // cuts-[g - 1] of each group's first slot
+    double *zsT = reinterpret_cast<double *>(lead + kNG);                             // INWIN only: z of the tile, transposed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double q4tab[4];  // 2^(j/4) for ndtr4 (INWIN)
@@ -273,6 +319,7 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     if (warp == 0)
         build_regions(P, &Rbuf[0], tile * (long long)P.tile, hi, P.tile_first_iv[tile], lane, WH, PADX, PADR);
     __syncthreads();
+    stage_cuts_async(P, &Rbuf[0], rawP, rawM, lead, tid);
 
     // Work carried across the loop's barrier, so that global-memory latency is never waited for right in
     // front of one:
@@ -310,6 +357,8 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
         unsigned omask = 0;   // elements that are outputs of this region
         unsigned long long kw = 0;  // 2-bit codes of bases g0-8 .. g0+9 (k-mer m starts at base g0-8+m)
         unsigned nw = 0;            // N bits of the same 18 bases
+        unsigned sraw[5] = {0, 0, 0, 0, 0};  // raw sequence / N-mask words the window is cut from in phase 4
+        int seq_sh = -1;                     // bit offset of the window in the N-mask words (-1: kw / nw are final)
         if (active) {
             r = fregion_of(R->cblk, nreg, c0);
             const int cb = R->cb[r], cn = R->cn[r];
@@ -326,16 +375,16 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
             if (vmask && !P.uniform) {
                 const long long b0 = c0 + R->D[r] + R->G0[r] - 8;
                 if (b0 >= 0 && b0 + 18 <= P.n_track) {
-                    const long long nw2 = (P.n_track + 15) >> 4;
-                    const long long w = b0 >> 4;
-                    const int sh = (int)(b0 & 15) * 2;
-                    const unsigned q0 = __ldg(P.seq2 + w);
-                    const unsigned q1 = (w + 1 < nw2) ? __ldg(P.seq2 + w + 1) : 0u;
-                    const unsigned q2 = (w + 2 < nw2) ? __ldg(P.seq2 + w + 2) : 0u;
-                    const unsigned lo32 = __funnelshift_r(q0, q1, sh);
-                    const unsigned hi32 = __funnelshift_r(q1, q2, sh);
-                    kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
-                    nw = ffetch_bits(P.nmask, (P.n_track + 31) >> 5, b0, 18);
+                    // the words are only loaded here; they are shifted into kw / nw at the top of phase 4, so that
+                    // nothing waits on these loads before the sub-tile's barriers
+                    const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
+                    const long long w = b0 >> 4, wm = b0 >> 5;
+                    sraw[0] = __ldg(P.seq2 + w);
+                    sraw[1] = (w + 1 < nw2) ? __ldg(P.seq2 + w + 1) : 0u;
+                    sraw[2] = (w + 2 < nw2) ? __ldg(P.seq2 + w + 2) : 0u;
+                    sraw[3] = __ldg(P.nmask + wm);
+                    sraw[4] = (wm + 1 < nwm) ? __ldg(P.nmask + wm + 1) : 0u;
+                    seq_sh = (int)(b0 & 31);
                 } else {
                     const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
                     for (int j = 0; j < 18; ++j) {
@@ -377,7 +426,10 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
             pend_omask = 0;
         }
 
-        // ---- phase 1: stage the packed cut counts (two groups of 4 slots per thread) -----------------
+        // ---- phase 1: pack the cut counts of this sub-tile (copied in asynchronously while the previous one
+        //      was being scored) into the strand-packed slots: lo16 = cuts+[x], hi16 = cuts-[x-1] -------------
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
         {
             unsigned seen = 0;
 #pragma unroll
@@ -385,33 +437,15 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                 const int xg = tid + rd * kFT;
                 if (xg >= NXG) break;
                 const int x = xg << 2;
-                const int rx = fregion_of(R->xblk, nreg, x);
-                const long long g = R->G0[rx] + x;
+                const uint4 a = lds128(rawP + x);
+                const uint4 b = lds128(rawM + x);
+                const unsigned bm1 = lead[xg];
+                seen |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | bm1);
                 uint4 w;
-                if (P.cuts_vec && ((g & 3) == 0) && g >= 1 && g + 4 <= P.n_track) {
-                    // 16-byte loads; the minus strand is shifted by one position (slot x pairs + at x with - at x-1)
-                    const uint4 a = ldg128(P.cuts_p + g);
-                    const uint4 b = ldg128(P.cuts_m + g);
-                    const unsigned bm1 = __ldg(P.cuts_m + g - 1);
-                    seen |= (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | bm1);
-                    w.x = __byte_perm(a.x, bm1, 0x5410);
-                    w.y = __byte_perm(a.y, b.x, 0x5410);
-                    w.z = __byte_perm(a.z, b.y, 0x5410);
-                    w.w = __byte_perm(a.w, b.z, 0x5410);
-                } else {
-                    unsigned a[4], b[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const long long ge = g + e;
-                        a[e] = (ge >= 0 && ge < P.n_track) ? __ldg(P.cuts_p + ge) : 0u;
-                        b[e] = (ge >= 1 && ge - 1 < P.n_track) ? __ldg(P.cuts_m + ge - 1) : 0u;
-                        seen |= a[e] | b[e];
-                    }
-                    w.x = __byte_perm(a[0], b[0], 0x5410);
-                    w.y = __byte_perm(a[1], b[1], 0x5410);
-                    w.z = __byte_perm(a[2], b[2], 0x5410);
-                    w.w = __byte_perm(a[3], b[3], 0x5410);
-                }
+                w.x = __byte_perm(a.x, bm1, 0x5410);
+                w.y = __byte_perm(a.y, b.x, 0x5410);
+                w.z = __byte_perm(a.z, b.y, 0x5410);
+                w.w = __byte_perm(a.w, b.z, 0x5410);
                 *reinterpret_cast<uint4 *>(cw + x) = w;
             }
             if (seen & ~kPackedCutLimit) badflag[buf] = 1;
@@ -430,20 +464,8 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                 P.redo_list[slot] = (int)tile;
             }
         }
-        // L2 prefetch of the next sub-tile's cut counts (one 128-byte line per thread and strand): a whole
-        // iteration ahead of their staging loads
-        if (more) {
-            const FastRegions *Rn = &Rbuf[buf ^ 1];
-            const int nr = Rn->nreg;
-            if (tid < (Rn->xblk[nr] + 31) >> 5) {
-                const int x = tid << 5;
-                const int rx = fregion_of(Rn->xblk, nr, x);
-                long long g = Rn->G0[rx] + x;
-                g = g < 0 ? 0 : (g < P.n_track ? g : P.n_track - 1);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cuts_p + g));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.cuts_m + g));
-            }
-        }
+        // the next sub-tile's cut counts start their way into shared memory now: a whole scoring pass ahead of use
+        if (more) stage_cuts_async(P, &Rbuf[buf ^ 1], rawP, rawM, lead, tid);
 
         if (nreg > 0 && !bad) {
             // ---- phase 2: 10-wide window sums of both strands, group aggregates ---------------------
@@ -544,6 +566,13 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                 // -- the 13 k-mers starting at bases g0-8 .. g0+4 serve both strands: plus-strand position
                 //    g0-5+m and minus-strand position g0-6+m use k-mer m; rcw = reverse complement of kw
                 unsigned long long rcw = 0;
+                if (seq_sh >= 0) {
+                    const int sh = (seq_sh & 15) * 2;
+                    const unsigned lo32 = __funnelshift_r(sraw[0], sraw[1], sh);
+                    const unsigned hi32 = __funnelshift_r(sraw[1], sraw[2], sh);
+                    kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
+                    nw = __funnelshift_r(sraw[3], sraw[4], seq_sh) & 0x3FFFFu;
+                }
                 if (!P.uniform) {
                     unsigned long long t = __brevll(kw) >> 28;
                     t = ((t & 0xAAAAAAAAAull) >> 1) | ((t & 0x555555555ull) << 1);
@@ -742,6 +771,7 @@ size_t score_fused_smem_bytes(bool inwin) {
     b += (size_t)(2 * kXCap + 4 * kXPad) * sizeof(uint32_t);  // [pad | cw | pad][pad | wcw | pad]
     b += (size_t)2 * (kNG + kGPad) * sizeof(uint4);
     b += sizeof(double) * kModelDoubles + 2 * sizeof(FastRegions) + 16;
+    b += (size_t)(2 * kXCap + kNG) * sizeof(uint32_t);  // rawP, rawM, lead
     if (inwin) b += (size_t)4 * kZS * sizeof(double);  // z of the tile, transposed
     return b;
 }

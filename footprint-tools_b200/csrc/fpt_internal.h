@@ -21,7 +21,10 @@ constexpr int kMaxSmoothHalfWin = 100;            // smoothing_half_win_width li
 constexpr int kMaxScaleHalfWin = 32;              // Stouffer half-width limit
 
 // Throughput kernel (fpt_fast.cu): one CTA = kFastThreads threads, 4 consecutive positions each.
-constexpr int kFastThreads = 256;
+#ifndef FPT_FAST_THREADS
+#define FPT_FAST_THREADS 128  // 4 CTAs of 4 warps per SM beat 2 of 8: a barrier holds up half as many warps
+#endif
+constexpr int kFastThreads = FPT_FAST_THREADS;
 constexpr int kFastCCap = 4 * kFastThreads;       // computed positions per sub-tile
 constexpr int kFastXCap = 8 * kFastThreads;       // staged slots per sub-tile
 constexpr int kFastHalfWin = 5;                   // half_win_width it is instantiated for
