@@ -43,7 +43,6 @@ __device__ __forceinline__ unsigned lo16(unsigned w) { return w & 0xFFFFu; }
 __device__ __forceinline__ unsigned hi16(unsigned w) { return w >> 16; }
 
 __device__ __forceinline__ uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ uint4 ldg128(const uint32_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 
 // Asynchronous global -> shared copies (LDGSTS): the data never passes through registers, so a thread can have
 // a whole sub-tile's worth of cut counts in flight while it computes. src_bytes < size zero-fills the rest.
@@ -86,6 +85,23 @@ __device__ __forceinline__ void stage_cuts_async(const ScoreParams &P, const Fas
         cp_async_4(lead + xg, P.cuts_m + (okl ? g - 1 : 0), okl ? 4 : 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Interval metadata of the sub-tile after next, copied in asynchronously by warp 0 at the top of an iteration and
+// turned into a region table at its end: the table of sub-tile i+2 is built during sub-tile i, so no barrier
+// ever waits for out_off / iv_start / tile_first_iv to arrive from global memory.
+struct alignas(16) Ahead {
+    long long o[kFReg + 2];  // out_off[k .. k + kFReg]
+    long long s[kFReg];      // iv_start[k .. k + kFReg)
+    long long cur, hi, k;    // the sub-tile the metadata belongs to
+    long long tfi_tile;      // tile whose first interval `tfi` holds (-1: none)
+    int tfi;
+    int have;                // a table is to be built from this at the end of the iteration
+};
+
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
 __device__ __forceinline__ uint4 agg(const uint4 a, const uint4 b) {
@@ -280,8 +296,9 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     uint4 *GA = reinterpret_cast<uint4 *>(wcw + kXCap + kXPad);                       // group aggregates
     uint4 *GB = GA + kNG + kGPad;
     double *dmp = reinterpret_cast<double *>(GB + kNG + kGPad);                       // 24
-    FastRegions *Rbuf = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);         // double-buffered
-    int *badflag = reinterpret_cast<int *>(Rbuf + 2);                                 // [2] (+ pad to 16 bytes)
+    FastRegions *Rbuf = reinterpret_cast<FastRegions *>(dmp + kModelDoubles);         // tables of sub-tiles i, i+1, i+2
+    Ahead *AH = reinterpret_cast<Ahead *>(Rbuf + 3);
+    int *badflag = reinterpret_cast<int *>(AH + 1);                                   // [2] (+ pad to 16 bytes)
     uint32_t *rawP = reinterpret_cast<uint32_t *>(badflag + 4);                       // raw cut counts of the sub-tile being
     uint32_t *rawM = rawP + kXCap;                                                    //   copied in (cp.async), per strand
     uint32_t *lead = rawM + kXCap;                                                    // cuts-[g - 1] of each group's first slot
@@ -314,10 +331,35 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     long long tile = blockIdx.x;
     if (tile >= P.n_tiles) return;
     long long hi = (tile + 1) * (long long)P.tile < P.total ? (tile + 1) * (long long)P.tile : P.total;
-    int buf = 0;
+    int buf = 0;             // parity of the sub-tile (bad flags)
+    int tb = 0;              // Rbuf[tb] is the table of the sub-tile being scored, (tb+1)%3 the next, (tb+2)%3 the one after
     long long marked = -1;  // thread 0: last tile appended to the redo list
-    if (warp == 0)
+    // (tile, cur, hi, first interval) of the sub-tile that follows the one table R describes
+    auto advance = [&](const FastRegions *R, long long t, long long h, long long &nt, long long &nc, long long &nh,
+                       bool &newtile) {
+        nt = t; nc = R->next_cur; nh = h;
+        newtile = nc >= h;
+        if (newtile) {
+            nt = t + gridDim.x;
+            if (nt < P.n_tiles) {
+                nc = nt * (long long)P.tile;
+                nh = (nt + 1) * (long long)P.tile < P.total ? (nt + 1) * (long long)P.tile : P.total;
+            }
+        }
+    };
+    if (warp == 0) {
+        // the first two tables are built synchronously
         build_regions(P, &Rbuf[0], tile * (long long)P.tile, hi, P.tile_first_iv[tile], lane, WH, PADX, PADR);
+        __syncwarp();
+        long long t1, c1, h1;
+        bool nt1;
+        advance(&Rbuf[0], tile, hi, t1, c1, h1, nt1);
+        if (t1 < P.n_tiles) {
+            const long long k1 = nt1 ? (long long)P.tile_first_iv[t1] : Rbuf[0].next_k;
+            build_regions(P, &Rbuf[1], c1, h1, k1, lane, WH, PADX, PADR);
+        }
+        if (lane == 0) { AH->tfi_tile = -1; AH->have = 0; }
+    }
     __syncthreads();
     stage_cuts_async(P, &Rbuf[0], rawP, rawM, lead, tid);
 
@@ -335,17 +377,42 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     const float dflt_f = (float)P.dflt;
 
     for (;;) {
-        FastRegions *R = &Rbuf[buf];
+        FastRegions *R = &Rbuf[tb];
+        FastRegions *Rn = &Rbuf[tb == 2 ? 0 : tb + 1];
         const int nreg = R->nreg;
-        long long ncur = R->next_cur, ntile = tile, nhi = hi;
-        if (ncur >= hi) {
-            ntile = tile + gridDim.x;
-            if (ntile < P.n_tiles) {
-                ncur = ntile * (long long)P.tile;
-                nhi = (ntile + 1) * (long long)P.tile < P.total ? (ntile + 1) * (long long)P.tile : P.total;
-            }
-        }
+        long long ncur, ntile, nhi;
+        bool newtile;
+        advance(R, tile, hi, ntile, ncur, nhi, newtile);
         const bool more = ntile < P.n_tiles;
+        // warp 0: metadata of the sub-tile after next starts its way into shared memory (used at the end of this
+        // iteration); the first interval of the tile after that one is fetched along with it
+        if (warp == 0) {
+            bool have = false;
+            if (more) {
+                long long t2, c2, h2;
+                bool nt2;
+                advance(Rn, ntile, nhi, t2, c2, h2, nt2);
+                if (t2 < P.n_tiles) {
+                    have = true;
+                    long long k2 = Rn->next_k;
+                    if (nt2) {
+                        k2 = (AH->tfi_tile == t2) ? (long long)AH->tfi : (long long)__ldg(P.tile_first_iv + t2);
+                        __syncwarp();  // every lane has read AH->tfi before it is overwritten
+                        const long long t3 = t2 + gridDim.x;
+                        if (lane == 0) {
+                            AH->tfi_tile = t3 < P.n_tiles ? t3 : -1;
+                            if (t3 < P.n_tiles) cp_async_4(&AH->tfi, P.tile_first_iv + t3, 4);
+                        }
+                    }
+                    const long long kk = k2 + lane;
+                    if (lane <= kFReg) cp_async_8(&AH->o[lane], P.out_off + (kk <= P.n_iv ? kk : 0), kk <= P.n_iv ? 8 : 0);
+                    if (lane < kFReg) cp_async_8(&AH->s[lane], P.iv_start + (kk < P.n_iv ? kk : 0), kk < P.n_iv ? 8 : 0);
+                    if (lane == 0) { AH->cur = c2; AH->hi = h2; AH->k = k2; }
+                }
+            }
+            if (lane == 0) AH->have = have ? 1 : 0;
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         const int NX = R->xblk[nreg], NC = R->cblk[nreg];
         const int NXG = NX >> 2;
 
@@ -428,7 +495,8 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
 
         // ---- phase 1: pack the cut counts of this sub-tile (copied in asynchronously while the previous one
         //      was being scored) into the strand-packed slots: lo16 = cuts+[x], hi16 = cuts-[x-1] -------------
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (warp == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");  // all but the metadata copies just issued
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         {
             unsigned seen = 0;
@@ -450,10 +518,6 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
             }
             if (seen & ~kPackedCutLimit) badflag[buf] = 1;
         }
-        if (warp == 0 && more) {
-            const long long nk = (ncur >= hi || R->next_cur >= hi) ? (long long)P.tile_first_iv[ntile] : R->next_k;
-            build_regions(P, &Rbuf[buf ^ 1], ncur, nhi, nk, lane, WH, PADX, PADR);
-        }
         __syncthreads();
         const bool bad = badflag[buf] != 0;
         if (tid == 0) {
@@ -465,7 +529,7 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
             }
         }
         // the next sub-tile's cut counts start their way into shared memory now: a whole scoring pass ahead of use
-        if (more) stage_cuts_async(P, &Rbuf[buf ^ 1], rawP, rawM, lead, tid);
+        if (more) stage_cuts_async(P, Rn, rawP, rawM, lead, tid);
 
         if (nreg > 0 && !bad) {
             // ---- phase 2: 10-wide window sums of both strands, group aggregates ---------------------
@@ -742,9 +806,21 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                 for (int e = 0; e < 4; ++e) zsT[e * kZS + 2 + tid] = zv[e];
             }
         }
+        // warp 0: the table of the sub-tile after next, from the metadata fetched at the top of this iteration
+        if (warp == 0) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but this iteration's cut-count copies
+            __syncwarp();
+            if (AH->have) {
+                const long long k2 = AH->k;
+                const bool valid = lane < kFReg && k2 + lane < P.n_iv;
+                const long long o0 = valid ? AH->o[lane] : 0, o1 = valid ? AH->o[lane + 1] : 0, st = valid ? AH->s[lane] : 0;
+                build_regions_core(P, &Rbuf[tb == 0 ? 2 : tb - 1], AH->cur, AH->hi, k2, lane, WH, PADX, PADR, o0, o1, st);
+            }
+        }
         __syncthreads();
         if (!more) break;
         tile = ntile; hi = nhi; buf ^= 1;
+        tb = tb == 2 ? 0 : tb + 1;
     }
     // the last sub-tile's deferred work
     if (pend_omask) {
@@ -770,7 +846,7 @@ size_t score_fused_smem_bytes(bool inwin) {
     size_t b = 4096 * sizeof(float);
     b += (size_t)(2 * kXCap + 4 * kXPad) * sizeof(uint32_t);  // [pad | cw | pad][pad | wcw | pad]
     b += (size_t)2 * (kNG + kGPad) * sizeof(uint4);
-    b += sizeof(double) * kModelDoubles + 2 * sizeof(FastRegions) + 16;
+    b += sizeof(double) * kModelDoubles + 3 * sizeof(FastRegions) + sizeof(Ahead) + 16;
     b += (size_t)(2 * kXCap + kNG) * sizeof(uint32_t);  // rawP, rawM, lead
     if (inwin) b += (size_t)4 * kZS * sizeof(double);  // z of the tile, transposed
     return b;

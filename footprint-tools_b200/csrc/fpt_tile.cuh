@@ -389,6 +389,12 @@ __device__ __noinline__ double fexpected_exact(SeqView P, const double *tab, con
 
 // Region table of one sub-tile, built by warp 0 (lane l <-> interval k + l) for the sub-tile that
 // starts at flat index `cur` of tile [.., hi).
+// build_regions_core takes the interval metadata of lane l (out_off[k + l], out_off[k + l + 1], iv_start[k + l])
+// as arguments, so that a caller can have fetched them ahead of time (fpt_fused.cu).
+__device__ __forceinline__ void build_regions_core(const ScoreParams &P, FastRegions *R, long long cur, long long hi,
+                                                   long long k, int lane, int WH, int PADX, int PADR, long long o0,
+                                                   long long o1, long long st);
+
 __device__ __forceinline__ void build_regions(const ScoreParams &P, FastRegions *R, long long cur, long long hi,
                                               long long k, int lane, int WH, int PADX, int PADR) {
     const long long kk = k + lane;
@@ -399,6 +405,14 @@ __device__ __forceinline__ void build_regions(const ScoreParams &P, FastRegions 
         o1 = __ldg(P.out_off + kk + 1);
         st = __ldg(P.iv_start + kk);
     }
+    build_regions_core(P, R, cur, hi, k, lane, WH, PADX, PADR, o0, o1, st);
+}
+
+__device__ __forceinline__ void build_regions_core(const ScoreParams &P, FastRegions *R, long long cur, long long hi,
+                                                   long long k, int lane, int WH, int PADX, int PADR, long long o0,
+                                                   long long o1, long long st) {
+    const long long kk = k + lane;
+    const bool valid = lane < kFReg && kk < P.n_iv;
     long long fa = o0 > cur ? o0 : cur;
     long long fb = o1 < hi ? o1 : hi;
     bool has = valid && fa < fb;
