@@ -305,6 +305,9 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     double *zsT = reinterpret_cast<double *>(lead + kNG);                             // INWIN only: z of the tile, transposed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the warp that fetches interval metadata and builds the region tables: the last one, whose threads own the
+    // c-space positions beyond the tile (P.tile < kCCap) and therefore have the least scoring work
+    const bool builder = warp == kFT / 32 - 1;
     __shared__ double q4tab[4];  // 2^(j/4) for ndtr4 (INWIN)
     if (INWIN) ndtr4_table_init(q4tab, tid);
     const int WH = INWIN ? P.wh_max : 0;
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
             }
         }
     };
-    if (warp == 0) {
+    if (builder) {
         // the first two tables are built synchronously
         build_regions(P, &Rbuf[0], tile * (long long)P.tile, hi, P.tile_first_iv[tile], lane, WH, PADX, PADR);
         __syncwarp();
@@ -384,9 +387,9 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
         bool newtile;
         advance(R, tile, hi, ntile, ncur, nhi, newtile);
         const bool more = ntile < P.n_tiles;
-        // warp 0: metadata of the sub-tile after next starts its way into shared memory (used at the end of this
+        // builder warp: metadata of the sub-tile after next starts its way into shared memory (used at the end of this
         // iteration); the first interval of the tile after that one is fetched along with it
-        if (warp == 0) {
+        if (builder) {
             bool have = false;
             if (more) {
                 long long t2, c2, h2;
@@ -467,35 +470,9 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
             }
         }
 
-        // ---- previous sub-tile: stores of its p-values / z / edge distances, or (INWIN) its windows -----
-        if (pend_omask) {
-            if (INWIN) {
-                window_phase(zsT, q4tab, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
-            } else {
-                if (pend_omask == 0xFu && P.vec_ok) {
-                    if (P.pval_out) st256(P.pval_out + pend_f0, pend_p[0], pend_p[1], pend_p[2], pend_p[3]);
-                    if (want_z) {
-                        st256(P.z_out + pend_f0, pend_z[0], pend_z[1], pend_z[2], pend_z[3]);
-                        *reinterpret_cast<unsigned *>(P.edge_out + pend_f0) = pend_edge4;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if ((pend_omask >> e) & 1u) {
-                            if (P.pval_out) P.pval_out[pend_f0 + e] = pend_p[e];
-                            if (want_z) {
-                                P.z_out[pend_f0 + e] = pend_z[e];
-                                P.edge_out[pend_f0 + e] = (unsigned char)((pend_edge4 >> (8 * e)) & 0xFFu);
-                            }
-                        }
-                }
-            }
-            pend_omask = 0;
-        }
-
         // ---- phase 1: pack the cut counts of this sub-tile (copied in asynchronously while the previous one
         //      was being scored) into the strand-packed slots: lo16 = cuts+[x], hi16 = cuts-[x-1] -------------
-        if (warp == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");  // all but the metadata copies just issued
+        if (builder) asm volatile("cp.async.wait_group 1;" ::: "memory");  // all but the metadata copies just issued
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         {
@@ -530,6 +507,34 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
         }
         // the next sub-tile's cut counts start their way into shared memory now: a whole scoring pass ahead of use
         if (more) stage_cuts_async(P, Rn, rawP, rawM, lead, tid);
+
+        // ---- previous sub-tile: stores of its p-values / z / edge distances, or (INWIN) its windows. The table
+        //      look-ups behind them were issued at the end of its phase 4; they have had phases 0 and 1 to arrive ---
+        if (pend_omask) {
+            if (INWIN) {
+                window_phase(zsT, q4tab, tid, P, pend_dl, pend_dr, pend_f0, pend_omask);
+            } else {
+                if (pend_omask == 0xFu && P.vec_ok) {
+                    if (P.pval_out) st256(P.pval_out + pend_f0, pend_p[0], pend_p[1], pend_p[2], pend_p[3]);
+                    if (want_z) {
+                        st256(P.z_out + pend_f0, pend_z[0], pend_z[1], pend_z[2], pend_z[3]);
+                        *reinterpret_cast<unsigned *>(P.edge_out + pend_f0) = pend_edge4;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((pend_omask >> e) & 1u) {
+                            if (P.pval_out) P.pval_out[pend_f0 + e] = pend_p[e];
+                            if (want_z) {
+                                P.z_out[pend_f0 + e] = pend_z[e];
+                                P.edge_out[pend_f0 + e] = (unsigned char)((pend_edge4 >> (8 * e)) & 0xFFu);
+                            }
+                        }
+                }
+            }
+            pend_omask = 0;
+        }
+
 
         if (nreg > 0 && !bad) {
             // ---- phase 2: 10-wide window sums of both strands, group aggregates ---------------------
@@ -571,7 +576,12 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
             }
 
             // ---- phase 4: expected counts, strand combine, p-value (c-space, 4 per thread) ----------
-            double zv[4] = {0.0, 0.0, 0.0, 0.0};
+            // p / z of this sub-tile live in the carried registers from the moment they are loaded (no copies that
+            // would wait for the look-ups at the end of the phase)
+            double (&pvv)[4] = pend_p;
+            double (&zv)[4] = pend_z;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { pvv[e] = 1.0; zv[e] = 0.0; }
             if (vmask) {
                 const int x0 = c0 + R->D[r];
                 const long long F0 = R->F0[r], T0 = R->T0[r], ivlen = R->len[r];
@@ -704,7 +714,6 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                 const uint4 cq = lds128(cw + x0);
                 const unsigned cwv[4] = {cq.x, cq.y, cq.z, cq.w};
                 int obi[4];
-                double pvv[4];
                 unsigned direct = 0;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -795,7 +804,6 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                         for (int e = 0; e < 4; ++e) {
                             const long long d = min(dl + e, dr - e);  // negative for the non-output slots of a partial group
                             edge4 |= (unsigned)(d < 0 ? 0 : (d < 255 ? d : 255)) << (8 * e);
-                            pend_p[e] = pvv[e]; pend_z[e] = zv[e];
                         }
                         pend_edge4 = edge4;
                     }
@@ -806,8 +814,8 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                 for (int e = 0; e < 4; ++e) zsT[e * kZS + 2 + tid] = zv[e];
             }
         }
-        // warp 0: the table of the sub-tile after next, from the metadata fetched at the top of this iteration
-        if (warp == 0) {
+        // builder warp: the table of the sub-tile after next, from the metadata fetched at the top of this iteration
+        if (builder) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but this iteration's cut-count copies
             __syncwarp();
             if (AH->have) {
