@@ -67,7 +67,7 @@ __device__ __forceinline__ void stage_cuts_async(const ScoreParams &P, const Fas
         const int xg = tid + rd * kFT;
         if (xg >= NXG) break;
         const int x = xg << 2;
-        const int rx = fregion_of(R->xblk, nreg, x);
+        const int rx = fregion_fast(R->xq, R->xblk, nreg, x);
         const long long g = R->G0[rx] + x;
         if (P.cuts_vec && ((g & 3) == 0) && g >= 0 && g + 4 <= P.n_track) {
             cp_async_16(rawP + x, P.cuts_p + g, 16);
@@ -430,18 +430,15 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
         unsigned sraw[5] = {0, 0, 0, 0, 0};  // raw sequence / N-mask words the window is cut from in phase 4
         int seq_sh = -1;                     // bit offset of the window in the N-mask words (-1: kw / nw are final)
         if (active) {
-            r = fregion_of(R->cblk, nreg, c0);
-            const int cb = R->cb[r], cn = R->cn[r];
-            const long long F0 = R->F0[r], rfa = R->fa[r], rfb = R->fb[r];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = c0 + e;
-                if (c >= cb && c < cb + cn) {
-                    vmask |= 1u << e;
-                    const long long f = F0 + c;
-                    if (f >= rfa && f < rfb) omask |= 1u << e;
-                }
-            }
+            r = fregion_fast(R->cq, R->cblk, nreg, c0);
+            // elements e with lo <= c0 + e < hi
+            auto range4 = [&](int lo, int hi) {
+                const int a = max(lo - c0, 0), b = min(hi - c0, 4);
+                return b > a ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+            };
+            const int cb = R->cb[r];
+            vmask = range4(cb, cb + R->cn[r]);
+            omask = vmask & range4(R->oa[r], R->oz[r]);
             if (vmask && !P.uniform) {
                 const long long b0 = c0 + R->D[r] + R->G0[r] - 8;
                 if (b0 >= 0 && b0 + 18 <= P.n_track) {
@@ -799,11 +796,14 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                         }
                         if (!want_win) pend_omask = 0;
                     } else {
+                        // min(t, len - 1 - t) clamped to [0, 255], in 32-bit arithmetic (negative for the non-output
+                        // slots of a partial group: clamped to 0)
+                        const int dli = (int)(dl < -8 ? -8 : (dl > 4096 ? 4096 : dl)), dri = (int)(dr < -8 ? -8 : (dr > 4096 ? 4096 : dr));
                         unsigned edge4 = 0;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const long long d = min(dl + e, dr - e);  // negative for the non-output slots of a partial group
-                            edge4 |= (unsigned)(d < 0 ? 0 : (d < 255 ? d : 255)) << (8 * e);
+                            const int d = min(dli + e, dri - e);
+                            edge4 |= (unsigned)min(max(d, 0), 255) << (8 * e);
                         }
                         pend_edge4 = edge4;
                     }

@@ -30,6 +30,9 @@ struct FastRegions {
     int xblk[kFReg + 1];    // x-space block prefix (multiples of 4)
     int cb[kFReg], cn[kFReg];
     int D[kFReg];           // x = c + D  (D % 4 == 0)
+    int oa[kFReg], oz[kFReg];  // c-range [oa, oz) of the region's outputs (fa - F0, fb - F0)
+    alignas(16) int cq[4];  // cblk[1..4] (INT_MAX beyond nreg): one 128-bit load finds the region of a position
+    alignas(16) int xq[4];  // xblk[1..4], likewise
     int nreg;
     long long next_cur, next_k;
     unsigned wtot[2][2][kFT / 32];
@@ -223,6 +226,16 @@ __device__ __forceinline__ int fregion_of(const int *bases, int nreg, int v) {
     int r = 0;
 #pragma unroll 4
     for (int j = 1; j < nreg; ++j) r += (v >= bases[j]) ? 1 : 0;
+    return r;
+}
+
+// same with the first four bounds in one 128-bit word (q = cq / xq of the table)
+__device__ __forceinline__ int fregion_fast(const int *q, const int *bases, int nreg, int v) {
+    const int4 b = *reinterpret_cast<const int4 *>(q);
+    int r = (v >= b.x ? 1 : 0) + (v >= b.y ? 1 : 0) + (v >= b.z ? 1 : 0) + (v >= b.w ? 1 : 0);
+    if (nreg > 5) {
+        for (int j = 5; j < nreg; ++j) r += (v >= bases[j]) ? 1 : 0;
+    }
     return r;
 }
 
@@ -461,6 +474,8 @@ __device__ __forceinline__ void build_regions_core(const ScoreParams &P, FastReg
         R->T0[r] = ta - cb;
         R->len[r] = len;
         R->fa[r] = fa; R->fb[r] = fb;
+        R->oa[r] = (int)(fa - (o0 + ta - cb)); R->oz[r] = (int)(fb - (o0 + ta - cb));
+        if (r >= 1 && r <= 4) { R->cq[r - 1] = cex; R->xq[r - 1] = xex; }
     }
     const int last = incl ? (31 - __clz(incl)) : -1;
     if (lane == (last < 0 ? 0 : last)) {
@@ -472,6 +487,7 @@ __device__ __forceinline__ void build_regions_core(const ScoreParams &P, FastReg
             R->next_cur = (nk >= P.n_iv) ? hi : cur;
         } else {
             R->nreg = nreg;
+            for (int j = nreg; j <= 4; ++j) { R->cq[j - 1] = 0x7FFFFFFF; R->xq[j - 1] = 0x7FFFFFFF; }
             R->cblk[nreg] = cex + cspan;
             R->xblk[nreg] = xex + xspan;
             R->next_cur = fb;
