@@ -50,7 +50,7 @@ __device__ __forceinline__ void ld256(const double *p, double &a, double &b, dou
 // five 256-bit loads (neighbouring threads overlap in L1). Windows never need interval geometry:
 // a window that would cross an interval end is exactly the one the edge rule sets to 1.0.
 __global__ void __launch_bounds__(256, 2) window_fast_kernel(const WindowParams W) {
-    __shared__ double s4[4];
+    __shared__ double s4[kNdTab];
     ndtr4_table_init(s4, threadIdx.x);
     __syncthreads();
     const long long ngroups = (W.total + 3) >> 2;
@@ -146,7 +146,7 @@ template <int H0, int H1, int H2>
 __global__ void __launch_bounds__(256, FPT_WIN_CTAS) window_fixed_kernel(const WindowParams W) {
     constexpr int HMAX = H2 >= 0 ? H2 : (H1 >= 0 ? H1 : H0);
     constexpr int QLO = (8 - HMAX) / 4, QHI = (11 + HMAX) / 4;  // 256-bit loads q covering z[-HMAX .. 3 + HMAX]
-    __shared__ double s4[4];
+    __shared__ double s4[kNdTab];
     ndtr4_table_init(s4, threadIdx.x);
     __syncthreads();
     const long long ngroups = (W.total + 3) >> 2;
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256, FPT_WIN_CTAS) window_fixed_kernel(const W
         const long long left = W.total - f0;
         const unsigned omask = left >= 4 ? 0xFu : ((1u << (int)left) - 1u);
         const unsigned edge_cur = edge4;
+        const bool interior = __vcmpgeu4(edge_cur, 0x01010101u * (unsigned)HMAX) == 0xFFFFFFFFu;  // no edge rule applies
         double A[3][4];
         {
             double acc[4] = {z[8], z[9], z[10], z[11]};
@@ -192,21 +193,30 @@ __global__ void __launch_bounds__(256, FPT_WIN_CTAS) window_fixed_kernel(const W
             const int h = k == 0 ? H0 : (k == 1 ? H1 : H2);
             if (h < 0) break;
             double res[4];
+#if defined(FPT_WIN_NOMATH)
+            res[0] = A[k][0]; res[1] = A[k][1]; res[2] = A[k][2]; res[3] = A[k][3];  // experiment: memory floor
+#else
             ndtr4(A[k], s4, res);
+#endif
+            if (!interior) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((int)((edge_cur >> (8 * e)) & 0xFFu) < h) res[e] = 1.0;  // closer than h to an interval end
+                for (int e = 0; e < 4; ++e)
+                    if ((int)((edge_cur >> (8 * e)) & 0xFFu) < h) res[e] = 1.0;  // closer than h to an interval end
+            }
             for (unsigned m = W.h_rows[h]; m; m &= m - 1) {
                 const int s = __ffs(m) - 1;
                 double *dst = W.winp_out + (size_t)s * W.total + f0;
+#if defined(FPT_WIN_NOSTORE)
+                if (res[0] == 123.456) dst[0] = res[1] + res[2] + res[3];  // experiment: arithmetic floor
+#else
                 if (omask == 0xFu && ((W.winp_vec >> s) & 1u)) {
-                    reinterpret_cast<double2 *>(dst)[0] = make_double2(res[0], res[1]);
-                    reinterpret_cast<double2 *>(dst)[1] = make_double2(res[2], res[3]);
+                    st256(dst, res[0], res[1], res[2], res[3]);  // one full 32-byte sector per thread
                 } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         if ((omask >> e) & 1u) dst[e] = res[e];
                 }
+#endif
             }
         }
         if (!FPT_WIN_PIPE && g + stride < ngroups) load(g + stride);

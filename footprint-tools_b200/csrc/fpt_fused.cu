@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     // the warp that fetches interval metadata and builds the region tables: the last one, whose threads own the
     // c-space positions beyond the tile (P.tile < kCCap) and therefore have the least scoring work
     const bool builder = warp == kFT / 32 - 1;
-    __shared__ double q4tab[4];  // 2^(j/4) for ndtr4 (INWIN)
+    __shared__ double q4tab[kNdTab];  // 2^(j/4) for ndtr4 (INWIN)
     if (INWIN) ndtr4_table_init(q4tab, tid);
     const int WH = INWIN ? P.wh_max : 0;
     const bool want_win = INWIN && P.winp_out != nullptr && P.n_scales > 0;

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
 
     if (P.tile_list && (long long)blockIdx.x >= (long long)*P.n_list) return;  // list mode: nothing for this CTA
     const int tid = threadIdx.x;
-    __shared__ double q4tab[4];  // 2^(j/4) for ndtr_fast1 (list mode; published by the kernel's first barrier)
+    __shared__ double q4tab[kNdTab];  // 2^(j/4) for ndtr_fast1 (list mode; published by the kernel's first barrier)
     ndtr4_table_init(q4tab, tid);
     const int lane = tid & 31, warp = tid >> 5;
     const int hw = P.hw, shw = P.shw, ktrim = P.ktrim;

@@ -81,12 +81,39 @@ __device__ __noinline__ double ndtr_slow(double a) { return ndtr_fn(a); }
 // against mpmath), i.e. <= 2.6e-11 absolute on -log10 p; the parity bar is 1e-9 relative. 24 FP64 operations
 // per value instead of 38. |a| >= 26, infinities and NaN go to the Cephes replica as before.
 // s4 = {1, 2^(1/4), 2^(1/2), 2^(3/4)} in shared memory (ndtr4_table_init).
+#ifndef FPT_ND_EXP64
+#define FPT_ND_EXP64 0  // 1: exp(q) entirely in FP64 (16-entry table, |q| <= ln2/32, degree 5) — no FP32 detour
+#endif
+#ifndef FPT_ND_G64
+#define FPT_ND_G64 0    // 1: all 14 coefficients of G in FP64
+#endif
+constexpr int kNdTab = 16;  // doubles the callers reserve for the 2^(j/N) table
+__constant__ double kPow16[16] = {1.00000000000000000e+00, 1.04427378242741375e+00, 1.09050773266525769e+00, 1.13878863475669156e+00,
+                                  1.18920711500272103e+00, 1.24185781207348400e+00, 1.29683955465100964e+00, 1.35425554693689265e+00,
+                                  1.41421356237309515e+00, 1.47682614593949935e+00, 1.54221082540794074e+00, 1.61049033194925428e+00,
+                                  1.68179283050742900e+00, 1.75625216037329945e+00, 1.83400808640934243e+00, 1.91520656139714740e+00};
 __device__ __forceinline__ void ndtr4_table_init(double *s4, int tid) {
-    if (tid < 4) {
-        s4[tid] = tid == 0 ? 1.0 : tid == 1 ? 1.18920711500272103e+00 : tid == 2 ? 1.41421356237309515e+00
-                                                                                  : 1.68179283050742900e+00;
-    }
+#if FPT_ND_EXP64
+    if (tid < 16) s4[tid] = kPow16[tid];
+#else
+    if (tid < 4) s4[tid] = kPow16[4 * tid];
+#endif
 }
+
+// exp(y) split for one value: n (scaled power of two) and the reduced argument q
+#if FPT_ND_EXP64
+#define FPT_ND_SCALE 2.30831206542234142e+01
+#define FPT_ND_LHI -4.33216987730702385306e-02
+#define FPT_ND_LLO -1.19263433079411731251e-11
+#define FPT_ND_MASK 15
+#define FPT_ND_SHIFT 4
+#else
+#define FPT_ND_SCALE 5.77078016355585355e+00
+#define FPT_ND_LHI -1.73286795092280954123e-01
+#define FPT_ND_LLO -4.77053732317646925005e-11
+#define FPT_ND_MASK 3
+#define FPT_ND_SHIFT 2
+#endif
 
 // Phi(a) for one value, |a| < 26: the same operations in the same order as one lane of ndtr4 (same bits)
 __device__ __forceinline__ double ndtr_fast1(double a, const double *s4) {
@@ -97,44 +124,64 @@ __device__ __forceinline__ double ndtr_fast1(double a, const double *s4) {
     const double er = fma(-d, rr, 1.0);
     rr = fma(rr, er, rr);
     const double u = fma(-10.0, rr, 1.0);
-    const float uf = __double2float_rn(u);
     const double y = __dmul_rn(-0.5, __dmul_rn(t, t));
-    const double kf = fma(y, 5.77078016355585355e+00, 6755399441055744.0);
+    const double kf = fma(y, FPT_ND_SCALE, 6755399441055744.0);
     const int n = __double2loint(kf);
     const double nf = __dadd_rn(kf, -6755399441055744.0);
-    const double qq = fma(nf, -1.73286795092280954123e-01, y);
-    const double q = fma(nf, -4.77053732317646925005e-11, qq);
-    const float qf = __double2float_rn(q);
+    const double qq = fma(nf, FPT_ND_LHI, y);
+    const double q = fma(nf, FPT_ND_LLO, qq);
+#if FPT_ND_G64
+    double G = fma(6.15361678962631613e-06, u, 1.40923486116882261e-05);
+    G = fma(G, u, -5.33751285104347458e-05);
+    G = fma(G, u, -5.88762345240221609e-05);
+    G = fma(G, u, 5.47008438926631780e-04);
+    G = fma(G, u, -7.97591746113601187e-04);
+    G = fma(G, u, -2.99395459275425199e-03);
+    G = fma(G, u, 2.07949308206693863e-02);
+#else
+    const float uf = __double2float_rn(u);
     float Gf = fmaf(6.153616596e-06f, uf, 1.409234847e-05f);
     Gf = fmaf(Gf, uf, -5.337512994e-05f);
     Gf = fmaf(Gf, uf, -5.887623411e-05f);
     Gf = fmaf(Gf, uf, 5.470084143e-04f);
     Gf = fmaf(Gf, uf, -7.975917542e-04f);
     Gf = fmaf(Gf, uf, -2.993954578e-03f);
-    float Rf = fmaf(1.0f / 720.0f, qf, 1.0f / 120.0f);
-    Rf = fmaf(Rf, qf, 1.0f / 24.0f);
-    Rf = fmaf(Rf, qf, 1.0f / 6.0f);
     double G = fma((double)Gf, u, 2.07949308206693863e-02);
+#endif
     G = fma(G, u, -6.91185624438261093e-02);
     G = fma(G, u, 1.65020386126410318e-01);
     G = fma(G, u, -3.13533160990166759e-01);
     G = fma(G, u, 4.95305615008850841e-01);
     G = fma(G, u, -6.65382502818922417e-01);
     G = fma(G, u, 7.69193049757243230e-01);
+#if FPT_ND_EXP64
+    double pe = fma(1.0 / 120.0, q, 1.0 / 24.0);
+    pe = fma(pe, q, 1.0 / 6.0);
+    pe = fma(pe, q, 0.5);
+#else
+    const float qf = __double2float_rn(q);
+    float Rf = fmaf(1.0f / 720.0f, qf, 1.0f / 120.0f);
+    Rf = fmaf(Rf, qf, 1.0f / 24.0f);
+    Rf = fmaf(Rf, qf, 1.0f / 6.0f);
     double pe = fma((double)Rf, q, 0.5);
+#endif
     pe = fma(pe, q, 1.0);
     pe = fma(pe, q, 1.0);
-    pe = __dmul_rn(pe, s4[n & 3]);
-    const double E = __hiloint2double(__double2hiint(pe) + ((n >> 2) << 20), __double2loint(pe));
+    pe = __dmul_rn(pe, s4[n & FPT_ND_MASK]);
+    const double E = __hiloint2double(__double2hiint(pe) + ((n >> FPT_ND_SHIFT) << 20), __double2loint(pe));
+    // Phi(a) = tail for a < 0, 1 - tail otherwise, as one fma(+-E/(t+5), G, 0 or 1): sign and addend are chosen on
+    // the high words (fma(x, y, +0) is the rounded product, so a < 0 gets exactly E/(t+5) * G)
     const double erq = __dmul_rn(E, rr);
-    return __double2hiint(a) < 0 ? __dmul_rn(erq, G) : __fma_rn(-erq, G, 1.0);
+    const int ah = __double2hiint(a);
+    const double ers = __hiloint2double(__double2hiint(erq) ^ (~ah & (int)0x80000000), __double2loint(erq));
+    const double one0 = __hiloint2double(~(ah >> 31) & 0x3FF00000, 0);
+    return __fma_rn(ers, G, one0);
 }
 
 // Phi(a) for 4 values at once: four ndtr_fast1 evaluations written interleaved (two FP64 and two FP32
 // Horner chains per value in flight), because a single chain leaves the pipes idle for most of its latency.
 __device__ __forceinline__ void ndtr4(const double (&a)[4], const double *s4, double (&res)[4]) {
-    double u[4], q[4], r[4];
-    float uf[4], qf[4], Gf[4], Rf[4];
+    double u[4], q[4], r[4], G[4], pe[4];
     int n[4];
     bool slow = false;
 #pragma unroll
@@ -149,71 +196,91 @@ __device__ __forceinline__ void ndtr4(const double (&a)[4], const double *s4, do
         rr = fma(rr, er, rr);  // 1/(t+5), relative error < 1e-12
         r[e] = rr;
         u[e] = fma(-10.0, rr, 1.0);
-        uf[e] = __double2float_rn(u[e]);
         const double y = __dmul_rn(-0.5, __dmul_rn(t, t));
-        const double kf = fma(y, 5.77078016355585355e+00, 6755399441055744.0);  // rint(y * 4/ln2) in the low word
+        const double kf = fma(y, FPT_ND_SCALE, 6755399441055744.0);  // rint(y * N/ln2) in the low word
         n[e] = __double2loint(kf);
         const double nf = __dadd_rn(kf, -6755399441055744.0);
-        const double qq = fma(nf, -1.73286795092280954123e-01, y);  // ln2/4 split: the high part has 32 significant bits
-        q[e] = fma(nf, -4.77053732317646925005e-11, qq);
-        qf[e] = __double2float_rn(q[e]);
+        const double qq = fma(nf, FPT_ND_LHI, y);  // ln2/N split: the high part has 32 significant bits
+        q[e] = fma(nf, FPT_ND_LLO, qq);
+    }
+#if FPT_ND_G64
+    {
+        const double cg[7] = {1.40923486116882261e-05, -5.33751285104347458e-05, -5.88762345240221609e-05, 5.47008438926631780e-04,
+                              -7.97591746113601187e-04, -2.99395459275425199e-03, 2.07949308206693863e-02};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) G[e] = fma(6.15361678962631613e-06, u[e], cg[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], cg[i]);
+        }
+    }
+#else
+    {
+        float uf[4], Gf[4];
+        const float cf[6] = {1.409234847e-05f, -5.337512994e-05f, -5.887623411e-05f, 5.470084143e-04f, -7.975917542e-04f, -2.993954578e-03f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uf[e] = __double2float_rn(u[e]);
+            Gf[e] = fmaf(6.153616596e-06f, uf[e], cf[0]);
+        }
+#pragma unroll
+        for (int i = 1; i < 6; ++i) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], cf[i]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) G[e] = fma((double)Gf[e], u[e], 2.07949308206693863e-02);
+    }
+#endif
+#if FPT_ND_EXP64
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pe[e] = fma(1.0 / 120.0, q[e], 1.0 / 24.0);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pe[e] = fma(pe[e], q[e], 1.0 / 6.0);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pe[e] = fma(pe[e], q[e], 0.5);
+#else
+    {
+        float qf[4], Rf[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            qf[e] = __double2float_rn(q[e]);
+            Rf[e] = fmaf(1.0f / 720.0f, qf[e], 1.0f / 120.0f);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 24.0f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 6.0f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pe[e] = fma((double)Rf[e], q[e], 0.5);
+    }
+#endif
+    {
+        const double cg[6] = {-6.91185624438261093e-02, 1.65020386126410318e-01, -3.13533160990166759e-01,
+                              4.95305615008850841e-01, -6.65382502818922417e-01, 7.69193049757243230e-01};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], cg[i]);
+            if (i < 2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pe[e] = fma(pe[e], q[e], 1.0);
+            }
+            if (i == 2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pe[e] = __dmul_rn(pe[e], s4[n[e] & FPT_ND_MASK]);
+            }
+        }
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        Gf[e] = fmaf(6.153616596e-06f, uf[e], 1.409234847e-05f);
-        Rf[e] = fmaf(1.0f / 720.0f, qf[e], 1.0f / 120.0f);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        Gf[e] = fmaf(Gf[e], uf[e], -5.337512994e-05f);
-        Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 24.0f);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        Gf[e] = fmaf(Gf[e], uf[e], -5.887623411e-05f);
-        Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 6.0f);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], 5.470084143e-04f);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -7.975917542e-04f);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -2.993954578e-03f);
-    double G[4], pe[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        G[e] = fma((double)Gf[e], u[e], 2.07949308206693863e-02);
-        pe[e] = fma((double)Rf[e], q[e], 0.5);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        G[e] = fma(G[e], u[e], -6.91185624438261093e-02);
-        pe[e] = fma(pe[e], q[e], 1.0);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        G[e] = fma(G[e], u[e], 1.65020386126410318e-01);
-        pe[e] = fma(pe[e], q[e], 1.0);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        G[e] = fma(G[e], u[e], -3.13533160990166759e-01);
-        pe[e] = __dmul_rn(pe[e], s4[n[e] & 3]);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], 4.95305615008850841e-01);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], -6.65382502818922417e-01);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], 7.69193049757243230e-01);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const double E = __hiloint2double(__double2hiint(pe[e]) + ((n[e] >> 2) << 20), __double2loint(pe[e]));
-        // explicit operations: an implicit contraction of 1 - tail would differ between the kernels that inline this
+        const double E = __hiloint2double(__double2hiint(pe[e]) + ((n[e] >> FPT_ND_SHIFT) << 20), __double2loint(pe[e]));
         const double er = __dmul_rn(E, r[e]);
-        const double tail = __dmul_rn(er, G[e]);
-        const double up = __fma_rn(-er, G[e], 1.0);
-        res[e] = __double2hiint(a[e]) < 0 ? tail : up;
+        const int ah = __double2hiint(a[e]);
+        const double ers = __hiloint2double(__double2hiint(er) ^ (~ah & (int)0x80000000), __double2loint(er));
+        const double one0 = __hiloint2double(~(ah >> 31) & 0x3FF00000, 0);
+        res[e] = __fma_rn(ers, G[e], one0);  // tail for a < 0, 1 - tail otherwise (see ndtr_fast1)
     }
     if (slow) {  // |a| >= 26, infinite or NaN: the Cephes replica (rare)
 #pragma unroll
