@@ -37,8 +37,9 @@ HW, SHW, CLIP, SCALES = 5, 50, 0.01, (3, 5, 7)
 BYTES_PER_BASE = 8 + 0.5 + 8 * (3 + len(SCALES))  # cuts+- u32, 2-bit base + N bit, exp/obs/p/S windows f64
 METRIC = "scored bases/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the
-# same command (profiles/); None until a capture of the current kernel exists.
-TRAFFIC = {}
+# same command (profiles/), for the default 250 000-interval workload; scaled by the base count otherwise.
+TRAFFIC = {"score_fused": 1.011289e9 + 2.585465e9,   # profiles/r1_score_fused_summary.txt (79.78 M bases per launch)
+           "window_fast": 0.731704e9 + 1.863141e9}   # profiles/r1_window_fixed_summary.txt
 WORKLOAD = ("C3: ftd detect genome-scale, %d synthetic DHS intervals, vierstra 6-mer model, hw=5 shw=50 clip=0.01, "
             "Stouffer window scales 3/5/7")
 
@@ -310,7 +311,7 @@ def main():
                    "nb_cdf": "direct" if args.no_lut else "device-built (exp,obs) table %dx%d + deferred direct evaluation" % _native.DEFAULT_LUT + "",
                    "parallelism": "intervals sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": TRAFFIC.get(dominant), "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs, burst)" % peak_src,
+                     "traffic": (TRAFFIC[dominant] * total / 79778894.0) if dominant in TRAFFIC else None, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs, burst)" % peak_src,
                      "kernel": "fpt::%s_kernel" % dominant,
                      "algorithmic_bytes_per_launch": per_kernel[dominant]["algorithmic_bytes_per_base"] * total,
                      "kernels": per_kernel,
