@@ -937,6 +937,105 @@ int fpt_nb_values(fpt_ctx *ctx, const double *exp, const double *obs, int64_t n,
     return FPT_OK;
 }
 
+int fpt_null_sample(fpt_ctx *ctx, const double *exp, int64_t n, int times, uint64_t seed, int64_t first_index,
+                    int64_t *counts_out, double *pvals_out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_null_sample: ctx is NULL");
+    if (!ctx->d_dm) return fail(FPT_ERR_STATE, "fpt_null_sample: no dispersion model uploaded (fpt_dm_upload)");
+    if (n < 0 || times < 0) return fail(FPT_ERR_ARG, "fpt_null_sample: bad argument");
+    if (n == 0 || times == 0) return FPT_OK;
+    if (!exp) return fail(FPT_ERR_ARG, "fpt_null_sample: NULL array");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_null_sample(st, ctx->d_dm, ctx->d_lut, ctx->lut_e, ctx->lut_o, exp, n, times, seed, first_index,
+                              reinterpret_cast<long long *>(counts_out), pvals_out, ctx->sm_count));
+        ctx->launches++;
+        return FPT_OK;
+    }
+    const size_t ob = (size_t)n * (size_t)times * 8;
+    CU(ctx->h_in[0].need((size_t)n * 8));
+    CU(ctx->h_out[0].need(ob));
+    CU(ctx->h_out[1].need(ob));
+    CU(cudaMemcpyAsync(ctx->h_in[0].p, exp, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(launch_null_sample(st, ctx->d_dm, ctx->d_lut, ctx->lut_e, ctx->lut_o, ctx->h_in[0].as<double>(), n, times, seed,
+                          first_index, counts_out ? ctx->h_out[0].as<long long>() : nullptr,
+                          pvals_out ? ctx->h_out[1].as<double>() : nullptr, ctx->sm_count));
+    ctx->launches++;
+    if (counts_out) CU(cudaMemcpyAsync(counts_out, ctx->h_out[0].p, ob, cudaMemcpyDeviceToHost, st));
+    if (pvals_out) CU(cudaMemcpyAsync(pvals_out, ctx->h_out[1].p, ob, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+static int efdr_common(fpt_ctx *ctx, const char *what, const double *d_exp, const double *d_winp, const long long *d_off,
+                       int64_t n_iv, int64_t max_len, int hw, int times, uint64_t seed, const double *d_nulls, int64_t m,
+                       double *d_out) {
+    {
+        ProfScope ps(ctx, FPT_KERNEL_FDR);
+        CU(launch_efdr(ctx->stream, ctx->d_dm, ctx->d_lut, ctx->lut_e, ctx->lut_o, d_exp, d_winp, d_off, n_iv, (int)max_len,
+                       hw, times, seed, d_nulls, m, d_out, ctx->d_status, ctx->sm_count));
+    }
+    ctx->launches++;
+    (void)what;
+    return FPT_OK;
+}
+
+int fpt_detect_fdr(fpt_ctx *ctx, const double *exp, const double *winp, const int64_t *out_off, int64_t n_iv,
+                   int64_t total, int64_t max_len, int hw, int times, uint64_t seed, double *efdr_out, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_detect_fdr: ctx is NULL");
+    if (!ctx->d_dm) return fail(FPT_ERR_STATE, "fpt_detect_fdr: no dispersion model uploaded (fpt_dm_upload)");
+    if (n_iv < 0 || total < 0 || hw < 0 || hw > kFastMaxScaleHalfWin || times < 1 || max_len < 0)
+        return fail(FPT_ERR_ARG, "fpt_detect_fdr: bad argument (0 <= hw <= %d, times >= 1)", kFastMaxScaleHalfWin);
+    if (n_iv == 0 || total == 0) return FPT_OK;
+    if (!exp || !winp || !out_off || !efdr_out) return fail(FPT_ERR_ARG, "fpt_detect_fdr: NULL array");
+    if (max_len > 4096) return fail(FPT_ERR_ARG, "fpt_detect_fdr: intervals longer than 4096 positions are not supported");
+    if (max_len == 0) return FPT_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (mem == FPT_MEM_DEVICE) {
+        int rc = efdr_common(ctx, "fpt_detect_fdr", exp, winp, reinterpret_cast<const long long *>(out_off), n_iv, max_len, hw,
+                             times, seed, nullptr, 0, efdr_out);
+        return rc;
+    }
+    for (int64_t k = 0; k < n_iv; ++k)
+        if (out_off[k + 1] - out_off[k] > max_len)
+            return fail(FPT_ERR_ARG, "fpt_detect_fdr: interval %lld is longer than max_len", (long long)k);
+    const size_t bytes = (size_t)total * 8, ob = (size_t)(n_iv + 1) * 8;
+    CU(ctx->h_in[0].need(bytes)); CU(ctx->h_in[1].need(bytes)); CU(ctx->h_in[2].need(ob)); CU(ctx->h_out[0].need(bytes));
+    CU(cudaMemcpyAsync(ctx->h_in[0].p, exp, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_in[1].p, winp, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_in[2].p, out_off, ob, cudaMemcpyHostToDevice, st));
+    int rc = efdr_common(ctx, "fpt_detect_fdr", ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(),
+                         ctx->h_in[2].as<long long>(), n_iv, max_len, hw, times, seed, nullptr, 0, ctx->h_out[0].as<double>());
+    if (rc != FPT_OK) return rc;
+    CU(cudaMemcpyAsync(efdr_out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
+int fpt_empirical_fdr(fpt_ctx *ctx, const double *pvals_null, int64_t m, const double *pvals, int64_t n, double *out,
+                      int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: ctx is NULL");
+    if (m < 0 || n < 0) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: bad argument");
+    if (n == 0) return FPT_OK;
+    if (n > 4096) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: more than 4096 observed values are not supported");
+    if (m == 0) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: empty null distribution");
+    if (!pvals_null || !pvals || !out) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: NULL array");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    if (mem == FPT_MEM_DEVICE)
+        return efdr_common(ctx, "fpt_empirical_fdr", nullptr, pvals, nullptr, 1, n, 0, 0, 0, pvals_null, m, out);
+    CU(ctx->h_in[0].need((size_t)m * 8)); CU(ctx->h_in[1].need((size_t)n * 8)); CU(ctx->h_out[0].need((size_t)n * 8));
+    CU(cudaMemcpyAsync(ctx->h_in[0].p, pvals_null, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->h_in[1].p, pvals, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    int rc = efdr_common(ctx, "fpt_empirical_fdr", nullptr, ctx->h_in[1].as<double>(), nullptr, 1, n, 0, 0, 0,
+                         ctx->h_in[0].as<double>(), m, ctx->h_out[0].as<double>());
+    if (rc != FPT_OK) return rc;
+    CU(cudaMemcpyAsync(out, ctx->h_out[0].p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FPT_OK;
+}
+
 int fpt_window(fpt_ctx *ctx, const double *x, const double *w, int64_t n, const int64_t *seg_off, int64_t n_seg,
                int hw, int op, double *out, int mem) {
     if (!ctx) return fail(FPT_ERR_ARG, "fpt_window: ctx is NULL");

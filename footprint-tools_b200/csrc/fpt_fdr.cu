@@ -1,0 +1,328 @@
+// fpt_fdr.cu — the step that follows the scoring path in `ftd detect` (sm_100a):
+// null sampling from the dispersion model, Stouffer windows of every null column and the empirical FDR of
+// the observed windowed p-values, per interval.
+//
+// Reference behaviour (paths relative to /root/reference):
+//   dispersion_model.sample        footprint_tools/modeling/dispersion.pyx:318-355
+//     (np.random.negative_binomial(r, r/(r+mu), times) per position, then nbinom.cdf of every draw)
+//   per-column windows             footprint_tools/cli/detect.py:132-133 (np.apply_along_axis(stouffers_z, 0, ...))
+//   fdr.emperical_fdr              footprint_tools/stats/fdr/__init__.py:12-33
+//   utils.bisect                   footprint_tools/stats/utils.pyx:52-79
+//
+// Design.
+//  * Sampling is inverse-transform on the device-built (exp, obs) table that the scoring kernels gather
+//    from: k = min{k : cdf(k) >= u}. The table row holds cdf(k) and ndtri(1 - cdf(k)) — exactly the null
+//    p-value and the z the windows need — so a draw is a binary search over an L2-resident row and no
+//    gamma/Poisson sampler exists. Expected counts outside the table fall back to the same search over
+//    direct nbinom.cdf evaluations. The draw is an exact sample of NB(r(exp), p(exp)).
+//  * Randomness is counter-based (Philox4x32-10 keyed by the caller's seed, counter = flat position,
+//    sample index): a draw depends on (seed, position, sample) only, not on the grid, the GPU count or the
+//    batch composition. numpy's legacy MT19937 stream cannot be reproduced in parallel: parity with the
+//    reference is statistical and tested as such; everything after the draws is exact.
+//  * One CTA per interval. The interval's observed windowed p-values are sorted once (bitonic, shared
+//    memory); every null value is then located among them by binary search and counted in a bucket; a
+//    prefix sum over the buckets gives, for every observed value, the number of null values <= it —
+//    without ever sorting or storing the n x times null values (the reference sorts all of them).
+//    NaN semantics of np.sort / utils.bisect are reproduced: NaN nulls sort last and are counted only for
+//    observed values no finite null exceeds; a NaN observed value counts everything.
+//  * Null windows use the arithmetic of the streaming window kernel (sums grown outward, ndtr_fast1), so
+//    a null window built from the same z values as an observed one is the same double.
+#include "fpt_tile.cuh"
+
+namespace fpt {
+
+namespace {
+
+constexpr int kFdrThreads = 256;
+
+// ---- Philox4x32-10 (Salmon et al. 2011) ------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// uniform double in (0, 1) for (seed, flat position, sample index): 53 random bits, centred
+__device__ __forceinline__ double null_uniform(unsigned long long seed, long long flat, int j) {
+    const uint4 x = philox4x32_10(make_uint4((unsigned)flat, (unsigned)((unsigned long long)flat >> 32), (unsigned)j, 0x46445231u),
+                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const unsigned long long bits = ((unsigned long long)(x.x >> 5) << 26) | (unsigned long long)(x.y >> 6);
+    return ((double)bits + 0.5) * 1.1102230246251565e-16;  // 2^-53
+}
+
+struct NullDraw {
+    long long k;
+    double p, z;
+};
+
+// One NB draw by inverse transform for expected count `ex`: the smallest k with cdf(k) >= u, its cdf and
+// z = ndtri(1 - cdf) (dispersion.pyx:318-355: the p-value of a sampled count is nbinom.cdf(k, p, r)).
+__device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__restrict__ lut, int lut_e, int lut_o, double ex,
+                                           double u) {
+    NullDraw d;
+    long long lo = 0;
+    const int e = (int)ex;
+    if (lut && ex == (double)e && e >= 0 && e < lut_e) {
+        const double2 *row = lut + (size_t)e * lut_o;
+        if (__ldg(&row[lut_o - 1]).x >= u) {
+            int a = 0, b = lut_o - 1;  // invariant: cdf(b) >= u
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if (__ldg(&row[m]).x >= u) b = m; else a = m + 1;
+            }
+            const double2 v = __ldg(&row[b]);
+            d.k = b; d.p = v.x; d.z = v.y;
+            return d;
+        }
+        lo = lut_o;
+    }
+    // outside the table: the same search over direct evaluations
+    const double rr = fit_r(dm + 9, ex), mu = fit_mu(dm, ex);
+    const double pr = nb_prob(rr, mu);
+    long long hi = lo > 0 ? 2 * lo : (mu > 1.0 ? (long long)mu : 1);
+    while (hi < (1LL << 30) && !(nb_cdf((int)hi, pr, rr) >= u)) {
+        lo = hi + 1;
+        hi = 2 * hi + 1;
+    }
+    while (lo < hi) {
+        const long long m = (lo + hi) >> 1;
+        if (nb_cdf((int)m, pr, rr) >= u) hi = m; else lo = m + 1;
+    }
+    d.k = hi;
+    d.p = nb_cdf((int)hi, pr, rr);
+    d.z = ndtri_fn(1.0 - d.p);
+    return d;
+}
+
+// dispersion_model.sample over a flat array (row-major (n, times) outputs like the reference's)
+__global__ void null_sample_kernel(const double *__restrict__ dm, const double2 *__restrict__ lut, int lut_e, int lut_o,
+                                   const double *__restrict__ ex, long long n, int times, unsigned long long seed,
+                                   long long first_index, long long *__restrict__ counts_out, double *__restrict__ pvals_out) {
+    const long long tot = n * (long long)times;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+        const long long i = q / times;
+        const int j = (int)(q - i * times);
+        const NullDraw d = null_draw(dm, lut, lut_e, lut_o, ex[i], null_uniform(seed, first_index + i, j));
+        if (counts_out) counts_out[q] = d.k;
+        if (pvals_out) pvals_out[q] = d.p;
+    }
+}
+
+// order-preserving map double -> u64; every NaN maps just below the padding sentinel (np.sort: NaN last)
+constexpr unsigned long long kKeyPad = 0xFFFFFFFFFFFFFFFFull, kKeyNaN = 0xFFFFFFFFFFFFFFFEull;
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    if (v != v) return kKeyNaN;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+struct FdrParams {
+    const double *ex, *winp;
+    const long long *off;
+    long long n_iv;
+    int hw, times;
+    unsigned long long seed;
+    double inv_sqrt_k;
+    double *out;
+    const double *dm;
+    const double2 *lut;
+    int lut_e, lut_o;
+    int np;    // power of two >= the longest interval
+    int nmax;  // longest interval
+    int jb;    // null columns generated per pass
+    // given-null mode (one segment): nulls[0 .. m) instead of generated ones
+    const double *nulls;
+    long long m;
+    int *status;  // set to 1 if an interval is longer than nmax
+};
+
+// Empirical FDR of one interval per CTA (grid-stride over intervals).
+__global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);   // np
+    double *zcol = reinterpret_cast<double *>(keys + P.np);                        // jb * nmax
+    int *idx = reinterpret_cast<int *>(zcol + (size_t)P.jb * P.nmax);              // np
+    int *rank_of = idx + P.np;                                                     // nmax
+    unsigned *bucket = reinterpret_cast<unsigned *>(rank_of + P.nmax);             // np + 1
+    __shared__ double s4[kNdTab];
+    __shared__ unsigned part[kFdrThreads];
+    __shared__ unsigned nan_count;
+    const int tid = threadIdx.x;
+    ndtr4_table_init(s4, tid);
+
+    for (long long iv = blockIdx.x; iv < P.n_iv; iv += gridDim.x) {
+        const long long o0 = P.off ? P.off[iv] : 0;
+        const long long len = (P.off ? P.off[iv + 1] : (long long)P.nmax) - o0;
+        if (len <= 0) continue;
+        if (len > P.nmax) {
+            if (tid == 0) *P.status = 1;
+            continue;
+        }
+        const int n = (int)len;
+        int np = 1;
+        while (np < n) np <<= 1;
+        __syncthreads();  // previous interval's reads of shared memory are complete
+        // ---- observed values: sort (key, index) ascending, NaN last -------------------------------
+        for (int i = tid; i < np; i += kFdrThreads) {
+            keys[i] = i < n ? order_key(P.winp[o0 + i]) : kKeyPad;
+            idx[i] = i;
+        }
+        for (int i = tid; i <= np; i += kFdrThreads) bucket[i] = 0;
+        if (tid == 0) nan_count = 0;
+        __syncthreads();
+        for (int k = 2; k <= np; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (np >> 1); t += kFdrThreads) {
+                    const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+                    const int b = a | j;
+                    const bool up = (a & k) == 0;
+                    const unsigned long long ka = keys[a], kb = keys[b];
+                    if ((ka > kb) == up) {
+                        keys[a] = kb; keys[b] = ka;
+                        const int ia = idx[a]; idx[a] = idx[b]; idx[b] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int k = tid; k < n; k += kFdrThreads) rank_of[idx[k]] = k;
+        // (keys[n .. np) are padding: the n real values, NaNs included, sort in front of it)
+
+        // ---- every null value: locate among the sorted observed values, count ----------------------
+        auto count_null = [&](double v) {
+            if (v != v) { atomicAdd(&nan_count, 1u); return; }
+            const unsigned long long kv = order_key(v);
+            int a = 0, b = n;  // first k in [0, n] with keys[k] >= kv
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if (keys[m] >= kv) b = m; else a = m + 1;
+            }
+            atomicAdd(&bucket[a], 1u);
+        };
+        long long M;
+        if (P.nulls) {
+            M = P.m;
+            __syncthreads();
+            for (long long q = tid; q < P.m; q += kFdrThreads) count_null(P.nulls[q]);
+        } else {
+            M = (long long)n * P.times;
+            for (int j0 = 0; j0 < P.times; j0 += P.jb) {
+                const int nj = min(P.jb, P.times - j0);
+                __syncthreads();  // zcol free (and, first pass, the sort visible)
+                for (int q = tid; q < nj * n; q += kFdrThreads) {
+                    const int jj = q / n, i = q - jj * n;
+                    const NullDraw d = null_draw(P.dm, P.lut, P.lut_e, P.lut_o, P.ex[o0 + i], null_uniform(P.seed, o0 + i, j0 + jj));
+                    zcol[jj * P.nmax + i] = d.z;
+                }
+                __syncthreads();
+                for (int q = tid; q < nj * n; q += kFdrThreads) {
+                    const int jj = q / n, i = q - jj * n;
+                    double v = 1.0;  // windowing.pyx:51-54: positions closer than hw to an end
+                    if (i >= P.hw && i < n - P.hw) {
+                        const double *z = zcol + jj * P.nmax + i;
+                        double acc = z[0];
+                        for (int h = 1; h <= P.hw; ++h) acc += z[-h] + z[h];
+                        const double a = acc * (-P.inv_sqrt_k);
+                        v = fabs(a) < 26.0 ? ndtr_fast1(a, s4) : ndtr_slow(a);
+                    }
+                    count_null(v);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- inclusive prefix sum of the buckets (np + 1 entries over kFdrThreads chunks) -----------
+        const int per = (np + 1 + kFdrThreads - 1) / kFdrThreads;
+        const int b0 = tid * per, b1 = min(b0 + per, np + 1);
+        unsigned s = 0;
+        for (int i = b0; i < b1; ++i) s += bucket[i];
+        part[tid] = s;
+        __syncthreads();
+        if (tid < 32) {  // scan of the 256 chunk totals by one warp (8 per lane)
+            unsigned loc[kFdrThreads / 32], run = 0;
+#pragma unroll
+            for (int q = 0; q < kFdrThreads / 32; ++q) { run += part[tid * (kFdrThreads / 32) + q]; loc[q] = run; }
+            unsigned incl = run;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += o;
+            }
+            const unsigned excl = incl - run;
+#pragma unroll
+            for (int q = 0; q < kFdrThreads / 32; ++q) part[tid * (kFdrThreads / 32) + q] = excl + loc[q];  // inclusive
+        }
+        __syncthreads();
+        {
+            unsigned run = tid ? part[tid - 1] : 0u;
+            for (int i = b0; i < b1; ++i) { run += bucket[i]; bucket[i] = run; }
+        }
+        __syncthreads();
+        // ---- utils.bisect semantics + the division and cap of emperical_fdr -----------------------
+        const unsigned nanc = nan_count;
+        const long long finite = M - nanc;
+        for (int i = tid; i < n; i += kFdrThreads) {
+            const int k = rank_of[i];
+            long long c;
+            if (keys[k] == kKeyNaN) c = M;
+            else {
+                c = bucket[k];
+                if (c == finite) c += nanc;  // no finite null above it: the scan runs through the NaNs at the end
+            }
+            const double rate = (double)c / (double)M;
+            P.out[o0 + i] = rate > 1.0 ? 1.0 : rate;
+        }
+    }
+}
+
+}  // namespace
+
+size_t efdr_smem_bytes(int np, int nmax, int jb) {
+    return (size_t)np * 8 + (size_t)jb * nmax * 8 + (size_t)np * 4 + (size_t)nmax * 4 + (size_t)(np + 1) * 4 + 16;
+}
+
+cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 *lut, int lut_e, int lut_o, const double *ex,
+                               long long n, int times, unsigned long long seed, long long first_index, long long *counts_out,
+                               double *pvals_out, int sm_count) {
+    const long long tot = n * (long long)times;
+    if (tot <= 0) return cudaSuccess;
+    long long blocks = (tot + 255) / 256;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    null_sample_kernel<<<(unsigned)blocks, 256, 0, st>>>(dm, lut, lut_e, lut_o, ex, n, times, seed, first_index, counts_out,
+                                                        pvals_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, int lut_e, int lut_o, const double *ex,
+                        const double *winp, const long long *off, long long n_iv, int nmax, int hw, int times,
+                        unsigned long long seed, const double *nulls, long long m, double *out, int *status, int sm_count) {
+    if (n_iv <= 0 || nmax <= 0) return cudaSuccess;
+    FdrParams P;
+    P.ex = ex; P.winp = winp; P.off = off; P.n_iv = n_iv; P.hw = hw; P.times = times; P.seed = seed;
+    P.inv_sqrt_k = 1.0 / sqrt((double)(2 * hw + 1));
+    P.out = out; P.dm = dm; P.lut = lut; P.lut_e = lut_e; P.lut_o = lut_o;
+    P.nmax = nmax;
+    P.np = 1;
+    while (P.np < nmax) P.np <<= 1;
+    P.jb = nulls ? 1 : (4096 / nmax < 1 ? 1 : (4096 / nmax > 8 ? 8 : 4096 / nmax));
+    if (!nulls && P.jb > times) P.jb = times > 0 ? times : 1;
+    P.nulls = nulls; P.m = m; P.status = status;
+    const size_t smem = efdr_smem_bytes(P.np, P.nmax, P.jb);
+    cudaError_t e = cudaFuncSetAttribute(efdr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, efdr_kernel, kFdrThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > n_iv) grid = n_iv;
+    efdr_kernel<<<(unsigned)grid, kFdrThreads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace fpt

@@ -86,6 +86,11 @@ SIGNATURES = {
     "fpt_posterior_delta": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                       C.c_double, C.c_void_p, C.c_int]),
     "fpt_posterior_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "fpt_null_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_int]),
+    "fpt_detect_fdr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                 C.c_int, C.c_uint64, C.c_void_p, C.c_int]),
+    "fpt_empirical_fdr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "fpt_special": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
@@ -189,7 +194,7 @@ class Context(object):
         _check(lib().fpt_ctx_last_transfer(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
-    KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo", "direct_fix")
+    KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo", "direct_fix", "fdr")
 
     def profile(self, enable=True):
         """Turn the per-kernel CUDA-event timers on or off (fpt_ctx_profile)."""
@@ -238,6 +243,37 @@ class Context(object):
 
     def window(self, x, w, n, seg_off, n_seg, hw, op, out, mem):
         _check(lib().fpt_window(self._h, _ptr(x), _ptr(w), n, _ptr(seg_off), n_seg, hw, op, _ptr(out), mem))
+
+    def null_sample(self, exp, times, seed, first_index=0):
+        """dispersion_model.sample on the device: (counts int64 (n, times), pvals float64 (n, times))."""
+        exp = np.ascontiguousarray(exp, dtype=np.float64)
+        n = exp.shape[0]
+        counts = np.zeros((n, times), dtype=np.int64)
+        pvals = np.ones((n, times), dtype=np.float64)
+        _check(lib().fpt_null_sample(self._h, _ptr(exp), n, int(times), int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_index),
+                                     _ptr(counts), _ptr(pvals), MEM_HOST))
+        return counts, pvals
+
+    def detect_fdr(self, exp, winp, out_off, hw, times, seed, out=None, mem=MEM_HOST, max_len=None, n_iv=None, total=None):
+        """Empirical FDR of every interval of a batch from `times` null columns (fpt_detect_fdr)."""
+        if mem == MEM_HOST:
+            exp = np.ascontiguousarray(exp, dtype=np.float64)
+            winp = np.ascontiguousarray(winp, dtype=np.float64)
+            out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+            n_iv, total = len(out_off) - 1, int(out_off[-1])
+            max_len = int(np.max(np.diff(out_off))) if n_iv else 0
+            out = np.empty(total, dtype=np.float64) if out is None else out
+        _check(lib().fpt_detect_fdr(self._h, _ptr(exp), _ptr(winp), _ptr(out_off), int(n_iv), int(total), int(max_len),
+                                    int(hw), int(times), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), mem))
+        return out
+
+    def empirical_fdr(self, pvals_null, pvals):
+        """fdr.emperical_fdr on the device (at most 4096 observed values)."""
+        nulls = np.ascontiguousarray(np.ravel(pvals_null), dtype=np.float64)
+        pvals = np.ascontiguousarray(pvals, dtype=np.float64)
+        out = np.empty(pvals.shape[0], dtype=np.float64)
+        _check(lib().fpt_empirical_fdr(self._h, _ptr(nulls), nulls.shape[0], _ptr(pvals), pvals.shape[0], _ptr(out), MEM_HOST))
+        return out
 
     def hist2d(self, exp, obs, n, hist, d0, d1, mem):
         _check(lib().fpt_hist2d(self._h, _ptr(exp), _ptr(obs), n, _ptr(hist), d0, d1, mem))

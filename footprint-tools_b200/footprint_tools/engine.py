@@ -193,6 +193,16 @@ def score_device(ctx, dbatch, bufs, hw=5, shw=50, clip=0.01, scales=(3,), hist=N
     ctx.score(args, MEM_DEVICE)
 
 
+def detect_fdr_host(ctx, exp, winp, out_off, hw=3, times=50, seed=0):
+    """The FDR step of `ftd detect` for a whole batch (cli/detect.py:132-135, one call instead of one
+    dm.sample + apply_along_axis(stouffers_z) + fdr.emperical_fdr per interval): `times` null columns per
+    interval drawn from the uploaded dispersion model, windowed with half-width `hw`, and the fraction of each
+    interval's null window p-values at or below every observed one. exp / winp: float64[total] laid out by
+    out_off (winp = the hw row of the scored windowed p-values). Draws are counter-based: the same
+    (seed, out_off) gives the same result on any GPU count."""
+    return ctx.detect_fdr(exp, winp, out_off, hw, times, seed)
+
+
 def shard_intervals(lengths, world_size):
     """Bases-balanced partition of an interval list over `world_size` GPUs:
     longest-processing-time-first greedy on the padded lengths; each rank's list keeps the

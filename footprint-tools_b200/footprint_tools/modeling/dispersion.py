@@ -161,6 +161,19 @@ class dispersion_model(object):
         return vals, pvals
 
 
+def _sample_device(self, x, times, seed=0, first_index=0):
+    """Additive, batched variant of sample(): exact inverse-transform NB draws on the device from a
+    counter-based generator (element i, sample j depends on (seed, first_index + i, j) only). Returns
+    (counts int64 (n, times), pvals float64 (n, times)) like sample(); the draws are not numpy's."""
+    x = _f64(x)
+    ctx = _native.default_context(self._device)
+    self.upload(ctx)
+    return ctx.null_sample(x, int(times), seed, first_index)
+
+
+dispersion_model.sample_device = _sample_device
+
+
 def learn_dispersion_model(h, cutoff=250, trim=(2.5, 97.5)):
     """Fit a dispersion model to the (expected x observed) histogram (dispersion.pyx:357-469).
 

@@ -37,7 +37,15 @@ def segment(x, threshold, w=1, decreasing=False):
 
 
 def bisect(a, b):
-    """For sorted a and sorted b: ind[i] = number of elements of a that are <= b[i] (as float64)."""
+    """The reference's single forward scan (utils.pyx:52-79): `lo` only ever advances, and it advances past
+    a[lo] unless b[i] < a[lo]. For a sorted ascending (np.sort: NaNs last) that is, per element of b, the
+    number of leading elements of a that are <= b[i] — running through the trailing NaNs of a when no finite
+    element exceeds b[i] (and for a NaN b[i]) — made non-decreasing along b. Returned as float64."""
     a = np.ascontiguousarray(a, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
-    return np.searchsorted(a, b, side="right").astype(np.float64)
+    nf = a.shape[0] - int(np.isnan(a).sum())
+    c = np.searchsorted(a[:nf], b, side="right")
+    c[(c == nf) | np.isnan(b)] = a.shape[0]
+    if c.shape[0]:
+        c = np.maximum.accumulate(c)
+    return c.astype(np.float64)

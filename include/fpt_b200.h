@@ -84,7 +84,8 @@ int64_t fpt_ctx_launch_count(const fpt_ctx *ctx);
 #define FPT_KERNEL_SCORE_FUSED 4   /* single-launch scoring + windows kernel of the detect/learn_dm geometry */
 #define FPT_KERNEL_REDO 5          /* general kernel over the tiles the fused kernel handed back */
 #define FPT_KERNEL_DIRECT_FIX 6    /* NB p-values of the positions outside the (exp, obs) table */
-#define FPT_KERNEL_COUNT 7
+#define FPT_KERNEL_FDR 7           /* null sampling + windows + empirical FDR, one CTA per interval */
+#define FPT_KERNEL_COUNT 8
 int fpt_ctx_profile(fpt_ctx *ctx, int enable);
 /* Bytes the last FPT_MEM_HOST fpt_score call copied host->device and device->host (expected and
  * observed counts cross as uint32 and are widened to float64 on the host in the pipelined path). */
@@ -201,6 +202,30 @@ int fpt_posterior_delta(fpt_ctx *ctx, const double *obs, const double *exp, cons
                         int n_samples, int64_t m, double cutoff, double *out, int mem);
 int fpt_posterior_logpost(fpt_ctx *ctx, const double *prior, const double *ll_on, const double *ll_off, int64_t n,
                           double *out, int mem);
+
+/* ---- after the scoring path: null sampling and empirical FDR ------------------ */
+
+/* dispersion_model.sample (modeling/dispersion.pyx:318-355): `times` negative-binomial draws per element of
+ * exp (model 0) and the p-value nbinom.cdf of every draw; counts_out / pvals_out are n x times, row-major
+ * (either may be NULL). Draws are exact inverse-transform samples driven by a counter-based generator:
+ * element i, sample j depends on (seed, first_index + i, j) only — the reference's np.random stream cannot be
+ * reproduced in parallel, parity is statistical. */
+int fpt_null_sample(fpt_ctx *ctx, const double *exp, int64_t n, int times, uint64_t seed, int64_t first_index,
+                    int64_t *counts_out, double *pvals_out, int mem);
+
+/* The FDR step of cli/detect.py:132-135 for a batch of intervals, fused: per interval, `times` null columns
+ * are drawn as fpt_null_sample(exp, seed, first_index = out_off[k]) draws them, every column goes through
+ * stouffers_z(., hw) (stats/windowing.pyx:34-58) and efdr_out[i] = emperical_fdr(null windows, winp)[i]
+ * (stats/fdr/__init__.py:12-33): the fraction of the interval's n x times null window p-values <= winp[i],
+ * capped at 1. exp / winp / efdr_out are `total` doubles laid out by out_off; max_len >= the longest
+ * interval (<= 4096). */
+int fpt_detect_fdr(fpt_ctx *ctx, const double *exp, const double *winp, const int64_t *out_off, int64_t n_iv,
+                   int64_t total, int64_t max_len, int hw, int times, uint64_t seed, double *efdr_out, int mem);
+
+/* fdr.emperical_fdr (stats/fdr/__init__.py:12-33 with utils.bisect, stats/utils.pyx:52-79) on explicit
+ * arrays: out[i] = min(1, #{null <= pvals[i]} / m), NaN handling as np.sort / bisect give it. n <= 4096. */
+int fpt_empirical_fdr(fpt_ctx *ctx, const double *pvals_null, int64_t m, const double *pvals, int64_t n, double *out,
+                      int mem);
 
 /* Scalar probes of the device special functions (used by the parity tests; HOST arrays).
  * fn: 0 incbet(a,b,x) 1 gamma(a) 2 lgam(a) 3 ndtr(a) 4 ndtri(a) 5 igamc(a,b) 6 chdtrc(a,b) 7 log1p(a)

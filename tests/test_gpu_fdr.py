@@ -1,0 +1,176 @@
+"""GPU tests of the step after the scoring path: device null sampling, the fused per-interval
+empirical FDR and fdr.emperical_fdr on the device. The draws are counter-based, not numpy's MT19937 stream, so
+the sampler is checked statistically against the exact NB pmf (oracle) and everything downstream of the draws
+exactly, against a numpy restatement of the reference's formula applied to the device's own draws."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from footprint_tools import _native, engine, synth
+from footprint_tools.stats import fdr as fdr_mod
+from parity import assert_pvalues_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _native.Context(0)
+    c.set_bias(synth.vierstra_table(), 1e-6)
+    c.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return oracle_lib.load_oracle()
+
+
+def ref_emperical_fdr(pvals_null, pvals):
+    """numpy restatement of stats/fdr/__init__.py:12-33 + utils.bisect (stats/utils.pyx:52-79)."""
+    a = np.sort(np.ravel(pvals_null))
+    order = np.argsort(pvals)
+    b = pvals[order]
+    counts = np.zeros(len(b))
+    lo, hi = 0, len(a)
+    for i in range(len(b)):
+        while lo < hi:
+            if b[i] < a[lo]:
+                break
+            lo += 1
+        counts[i] = lo
+    rate = counts / len(a)
+    rate[rate > 1] = 1
+    return rate[np.argsort(order)]
+
+
+def test_null_sample_matches_the_exact_distribution(ctx, oracle):
+    """Draws follow NB(r(exp), p(exp)) (chi-square against the oracle's pmf) and every p-value is the cdf of its draw."""
+    times = 60000
+    for ex in (0.0, 3.0, 17.0, 60.0, 180.0):
+        counts, pvals = ctx.null_sample(np.array([ex]), times, seed=1234)
+        k = counts[0]
+        kmax = int(k.max())
+        ks = np.arange(kmax + 1, dtype=np.float64)
+        pmf = oracle.dm_values(synth.MU_PARAMS, synth.R_PARAMS, np.full(kmax + 1, ex), ks, 1)
+        cdf = oracle.dm_values(synth.MU_PARAMS, synth.R_PARAMS, np.full(kmax + 1, ex), ks, 0)
+        assert_pvalues_close(pvals[0], cdf[k], "p-values of the draws at exp=%g" % ex)
+        expd = pmf * times
+        keep = expd >= 8.0  # pooled tail
+        obs_n = np.bincount(k, minlength=kmax + 1).astype(np.float64)
+        o = np.append(obs_n[keep], obs_n[~keep].sum())
+        e = np.append(expd[keep], times - expd[keep].sum())
+        chi2 = float(((o - e) ** 2 / np.maximum(e, 1e-9)).sum())
+        dof = len(o) - 1
+        assert chi2 < dof + 6.0 * np.sqrt(2.0 * dof) + 10.0, "exp=%g: chi2 %.1f for %d dof" % (ex, chi2, dof)
+        # inverse transform: the draw is the smallest k whose cdf reaches u, so cdf(k-1) < cdf(k)
+        assert (np.diff(np.sort(np.unique(pvals[0]))) > 0).all()
+
+
+def test_null_sample_is_counter_based(ctx):
+    """Element i, sample j depends on (seed, first_index + i, j) only; expected counts outside the table (or
+    non-integer ones) are drawn by the same inverse transform over direct evaluations: same draws, same bits."""
+    x = np.array([5.0, 40.0, 5.0, 150.0, 2.5, 199.0])  # 2.5: non-integer -> direct evaluation
+    c0, p0 = ctx.null_sample(x, 7, seed=99)
+    c1, p1 = ctx.null_sample(x[2:], 7, seed=99, first_index=2)
+    assert np.array_equal(c0[2:], c1) and np.array_equal(p0[2:], p1)
+    c2, _ = ctx.null_sample(x, 7, seed=100)
+    assert not np.array_equal(c0, c2)
+    assert ((p0 > 0) & (p0 <= 1)).all() and (c0 >= 0).all()
+    small = _native.Context(0)
+    small.set_dm(synth.MU_PARAMS, synth.R_PARAMS, lut=(32, 64))  # 40, 150, 199 and draws above 63 leave the table
+    c3, p3 = small.null_sample(x, 7, seed=99)
+    small.close()
+    assert np.array_equal(c0, c3) and np.array_equal(p0, p3)
+    assert 60 < c0[3].mean() < 260
+
+
+def test_empirical_fdr_matches_reference_formula(ctx):
+    rng = np.random.default_rng(5)
+    for n, m in ((1, 1), (7, 50), (300, 15000), (1200, 60000), (4096, 9000)):
+        nulls = rng.uniform(0, 1, m)
+        nulls[rng.integers(0, m, max(1, m // 50))] = 1.0
+        pv = rng.uniform(0, 1, n)
+        pv[rng.integers(0, n, max(1, n // 20))] = 1.0
+        if m > 10:
+            pv[: n // 10] = rng.choice(nulls, n // 10)  # exact ties
+        got = ctx.empirical_fdr(nulls, pv)
+        assert np.array_equal(got, ref_emperical_fdr(nulls, pv)), (n, m)
+    # NaN semantics of np.sort / bisect: NaN nulls last, NaN observed values count everything
+    nulls = np.array([0.1, np.nan, 0.5, 0.9, np.nan, 0.3])
+    pv = np.array([0.05, 0.3, np.nan, 0.95, 0.5, 1.0])
+    assert np.array_equal(ctx.empirical_fdr(nulls, pv), ref_emperical_fdr(nulls, pv))
+    assert np.array_equal(fdr_mod.emperical_fdr_device(nulls, pv), fdr_mod.emperical_fdr(nulls, pv))
+
+
+def _ref_fdr(oracle, pn, pobs, out_off, hw, times):
+    """emperical_fdr(stouffers_z of every null column, stouffers_z of the observed p-values) per interval, in the
+    oracle's arithmetic on both sides (ties between null and observed values stay ties)."""
+    ref = np.empty(int(out_off[-1]))
+    for k in range(len(out_off) - 1):
+        a, b = int(out_off[k]), int(out_off[k + 1])
+        wn = np.column_stack([oracle.window(np.ascontiguousarray(pn[a:b, j]), hw, 3) for j in range(times)])
+        ref[a:b] = ref_emperical_fdr(wn, oracle.window(np.ascontiguousarray(pobs[a:b]), hw, 3))
+    return ref
+
+
+def test_detect_fdr_exact_without_neighbour_sums(ctx, oracle):
+    """hw = 0: a window is a monotone map of one discrete z value, so order and ties between null and observed
+    values are the same in the device's and the oracle's arithmetic and the fused kernel (draw <-> flat position
+    mapping, locating, counting, prefix sums, division) must reproduce the reference formula exactly."""
+    table = synth.vierstra_table()
+    for depth in (1.0, 20.0):
+        batch, info = synth.make_batch(40, 55, seed=3, table=table, depth_scale=depth)
+        res = engine.score_host(ctx, batch, 5, 50, 0.01, (0,))
+        exp, pval, winp0 = res["exp"], res["pval"], res["winp"][0]
+        times, seed = 20, 4242
+        got = engine.detect_fdr_host(ctx, exp, winp0, batch.out_off, hw=0, times=times, seed=seed)
+        _, pn = ctx.null_sample(exp, times, seed)
+        ref = _ref_fdr(oracle, pn, pval, batch.out_off, 0, times)
+        assert np.array_equal(got, ref), (depth, int((got != ref).sum()), float(np.abs(got - ref).max()))
+        assert np.array_equal(got, engine.detect_fdr_host(ctx, exp, winp0, batch.out_off, hw=0, times=times, seed=seed))
+
+
+def test_detect_fdr_windowed_agrees_with_formula_up_to_tie_breaking(ctx, oracle):
+    """hw = 3 on a deep library (many distinct counts per position). A window sum of the same z values in another
+    order can differ in its last bit — in the reference's left-to-right sums as in the device's outward ones — so
+    which permuted windows tie is arithmetic-specific (statistical parity); everything else agrees."""
+    table = synth.vierstra_table()
+    batch, info = synth.make_batch(40, 55, seed=5, table=table, depth_scale=30.0)
+    res = engine.score_host(ctx, batch, 5, 50, 0.01, (3,))
+    exp, pval, winp = res["exp"], res["pval"], res["winp"][0]
+    times, seed = 20, 99
+    got = engine.detect_fdr_host(ctx, exp, winp, batch.out_off, hw=3, times=times, seed=seed)
+    _, pn = ctx.null_sample(exp, times, seed)
+    ref = _ref_fdr(oracle, pn, pval, batch.out_off, 3, times)
+    assert np.all((got >= 0) & (got <= 1))
+    d = np.abs(got - ref)
+    assert (d > 0).mean() < 0.02, "positions that differ: %.4f" % (d > 0).mean()
+    assert d.max() < 0.02, "largest difference %g" % d.max()
+    # a different cut of the batch moves the flat positions (first_index = out_off[k]): other draws, same law
+    a = int(batch.out_off[10])
+    part = ctx.detect_fdr(exp[a:], winp[a:], batch.out_off[10:] - a, 3, times, seed)
+    assert part.shape == (batch.total - a,)
+    assert abs(part.mean() - got[a:].mean()) < 0.05
+
+
+def test_detect_fdr_is_calibrated_under_the_null(ctx):
+    """Observed counts drawn from the model itself: the empirical FDR of a null position is ~uniform."""
+    rng = np.random.default_rng(8)
+    n_iv, ln, times = 60, 300, 50
+    off = np.arange(n_iv + 1, dtype=np.int64) * ln
+    exp = np.rint(rng.gamma(2.0, 8.0, n_iv * ln))
+    cnt, pv = ctx.null_sample(exp, 1, seed=777)
+    winp = np.empty(n_iv * ln)
+    ctx.window(pv[:, 0].copy(), None, n_iv * ln, off, n_iv, 3, _native.WIN_STOUFFER, winp, _native.MEM_HOST)
+    e = ctx.detect_fdr(exp, winp, off, 3, times, seed=778)
+    inner = np.ones(n_iv * ln, dtype=bool)
+    for k in range(n_iv):
+        inner[k * ln: k * ln + 3] = False
+        inner[(k + 1) * ln - 3: (k + 1) * ln] = False
+    v = e[inner]
+    assert abs(v.mean() - 0.5) < 0.03
+    hist = np.histogram(v, bins=10, range=(0, 1))[0] / v.size
+    assert np.all(np.abs(hist - 0.1) < 0.03), hist
+    assert (e[~inner] == 1.0).all()  # edge positions: observed window p = 1 -> every null value is <= it
