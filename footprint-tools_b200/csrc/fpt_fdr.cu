@@ -48,12 +48,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
-// uniform double in (0, 1) for (seed, flat position, sample index): 53 random bits, centred
+// uniform double in (0, 1) for (seed, flat position, sample index): 52 random bits, centred
 __device__ __forceinline__ double null_uniform(unsigned long long seed, long long flat, int j) {
     const uint4 x = philox4x32_10(make_uint4((unsigned)flat, (unsigned)((unsigned long long)flat >> 32), (unsigned)j, 0x46445231u),
                                   make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
-    const unsigned long long bits = ((unsigned long long)(x.x >> 5) << 26) | (unsigned long long)(x.y >> 6);
-    return ((double)bits + 0.5) * 1.1102230246251565e-16;  // 2^-53
+    const unsigned long long bits = ((unsigned long long)(x.x >> 6) << 26) | (unsigned long long)(x.y >> 6);
+    return ((double)bits + 0.5) * 2.220446049250313e-16;  // 52 bits: (bits + 0.5) * 2^-52 is exact and never 0 or 1
 }
 
 struct NullDraw {
@@ -82,17 +82,50 @@ __device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__re
         }
         lo = lut_o;
     }
-    // outside the table: the same search over direct evaluations
+    // outside the table: the same inverse transform over direct evaluations of nbinom.cdf. Each evaluation is a few
+    // thousand instructions, so the search is bracketed around the normal quantile mu + sigma * ndtri(u) with steps
+    // of sigma/8 that double (about nine evaluations) instead of bisecting [0, 2^30).
     const double rr = fit_r(dm + 9, ex), mu = fit_mu(dm, ex);
     const double pr = nb_prob(rr, mu);
-    long long hi = lo > 0 ? 2 * lo : (mu > 1.0 ? (long long)mu : 1);
-    while (hi < (1LL << 30) && !(nb_cdf((int)hi, pr, rr) >= u)) {
-        lo = hi + 1;
-        hi = 2 * hi + 1;
+    if (!(pr == pr)) {  // degenerate model at this expected count (r = 1/0): the reference's numpy raises here
+        d.k = 0; d.p = pr; d.z = pr;
+        return d;
     }
-    while (lo < hi) {
-        const long long m = (lo + hi) >> 1;
-        if (nb_cdf((int)m, pr, rr) >= u) hi = m; else lo = m + 1;
+    const long long kcap = 1LL << 30;
+    long long hi;
+    if (nb_cdf((int)lo, pr, rr) >= u) {
+        hi = lo;  // lo is 0, or the first count beyond the table (whose last entry is below u)
+    } else {
+        const double sigma = sqrt(mu + mu * mu / rr);
+        double c = mu + sigma * ndtri_fn(u);
+        if (!(c > (double)(lo + 1))) c = (double)(lo + 1);
+        if (!(c < (double)kcap)) c = (double)kcap;
+        long long k = (long long)c, step = (long long)(sigma * 0.125);
+        if (step < 1) step = 1;
+        if (step > kcap) step = kcap;
+        if (nb_cdf((int)k, pr, rr) >= u) {
+            hi = k;
+            for (;;) {  // walk down to a count whose cdf is below u (cdf(lo) is)
+                const long long t = hi - step;
+                if (t <= lo) { lo = lo + 1; break; }
+                if (!(nb_cdf((int)t, pr, rr) >= u)) { lo = t + 1; break; }
+                hi = t;
+                step *= 2;
+            }
+        } else {
+            lo = k + 1;
+            for (;;) {  // walk up to a count whose cdf reaches u
+                const long long t = lo - 1 + step;
+                if (t >= kcap) { hi = kcap; break; }
+                if (nb_cdf((int)t, pr, rr) >= u) { hi = t; break; }
+                lo = t + 1;
+                step *= 2;
+            }
+        }
+        while (lo < hi) {
+            const long long m = (lo + hi) >> 1;
+            if (nb_cdf((int)m, pr, rr) >= u) hi = m; else lo = m + 1;
+        }
     }
     d.k = hi;
     d.p = nb_cdf((int)hi, pr, rr);
