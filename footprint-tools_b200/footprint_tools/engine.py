@@ -115,6 +115,16 @@ class IntervalBatch(object):
         iv_start = block_off[:-1] + lead
         return IntervalBatch(seq2, nmask, cp, cm, n_track, iv_start, out_off, block_off, block_len=L + 6)
 
+    def select(self, idx):
+        """The intervals `idx` (ascending indices) over the SAME track: a rank's shard of the interval list
+        (SURVEY.md §8e). Outputs are laid out back to back in the order of idx."""
+        idx = np.asarray(idx, dtype=np.int64)
+        lens = np.diff(self.out_off)[idx]
+        out_off = np.zeros(len(idx) + 1, dtype=np.int64)
+        np.cumsum(lens, out=out_off[1:])
+        return IntervalBatch(self.seq2, self.nmask, self.cuts_plus, self.cuts_minus, self.n_track, self.iv_start[idx],
+                             out_off, self.block_off, block_len=self.block_len)
+
     def to_device(self, device):
         """Device-resident copy (torch tensors; uint32 payloads carried as int32)."""
         import torch
