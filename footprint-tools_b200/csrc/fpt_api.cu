@@ -75,6 +75,7 @@ struct fpt_ctx {
     double *d_dm = nullptr;
     int n_models = 0;
     double2 *d_lut = nullptr;
+    unsigned short *d_guide = nullptr;  // quantile guide of the table rows (null sampler)
     int lut_e = 0, lut_o = 0;
     int *d_status = nullptr;
     int64_t launches = 0;
@@ -230,6 +231,7 @@ int fpt_ctx_destroy(fpt_ctx *ctx) {
     cudaFree(ctx->d_bias);
     cudaFree(ctx->d_dm);
     cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_guide);
     cudaFree(ctx->d_status);
     ctx->plan.release();
     ctx->scratch.release();
@@ -344,6 +346,8 @@ int fpt_dm_upload(fpt_ctx *ctx, const double *mu_params, const double *r_params,
     ctx->d_dm = nullptr;
     cudaFree(ctx->d_lut);
     ctx->d_lut = nullptr;
+    cudaFree(ctx->d_guide);
+    ctx->d_guide = nullptr;
     ctx->lut_e = ctx->lut_o = 0;
     CU(cudaMalloc(&ctx->d_dm, host.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->d_dm, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -352,6 +356,11 @@ int fpt_dm_upload(fpt_ctx *ctx, const double *mu_params, const double *r_params,
         CU(cudaMalloc(&ctx->d_lut, (size_t)lut_exp * lut_obs * sizeof(double2)));
         CU(launch_lut_build(ctx->stream, ctx->d_dm, ctx->d_lut, lut_exp, lut_obs));
         ctx->launches++;
+        if (lut_obs <= 65536) {
+            CU(cudaMalloc(&ctx->d_guide, (size_t)lut_exp * (kGuide + 1) * sizeof(unsigned short)));
+            CU(launch_guide_build(ctx->stream, ctx->d_lut, lut_exp, lut_obs, ctx->d_guide));
+            ctx->launches++;
+        }
         ctx->lut_e = lut_exp;
         ctx->lut_o = lut_obs;
     }
@@ -947,7 +956,7 @@ int fpt_null_sample(fpt_ctx *ctx, const double *exp, int64_t n, int times, uint6
     DeviceGuard g(ctx->device);
     cudaStream_t st = ctx->stream;
     if (mem == FPT_MEM_DEVICE) {
-        CU(launch_null_sample(st, ctx->d_dm, ctx->d_lut, ctx->lut_e, ctx->lut_o, exp, n, times, seed, first_index,
+        CU(launch_null_sample(st, ctx->d_dm, ctx->d_lut, ctx->d_guide, ctx->lut_e, ctx->lut_o, exp, n, times, seed, first_index,
                               reinterpret_cast<long long *>(counts_out), pvals_out, ctx->sm_count));
         ctx->launches++;
         return FPT_OK;
@@ -957,7 +966,7 @@ int fpt_null_sample(fpt_ctx *ctx, const double *exp, int64_t n, int times, uint6
     CU(ctx->h_out[0].need(ob));
     CU(ctx->h_out[1].need(ob));
     CU(cudaMemcpyAsync(ctx->h_in[0].p, exp, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    CU(launch_null_sample(st, ctx->d_dm, ctx->d_lut, ctx->lut_e, ctx->lut_o, ctx->h_in[0].as<double>(), n, times, seed,
+    CU(launch_null_sample(st, ctx->d_dm, ctx->d_lut, ctx->d_guide, ctx->lut_e, ctx->lut_o, ctx->h_in[0].as<double>(), n, times, seed,
                           first_index, counts_out ? ctx->h_out[0].as<long long>() : nullptr,
                           pvals_out ? ctx->h_out[1].as<double>() : nullptr, ctx->sm_count));
     ctx->launches++;
@@ -972,7 +981,7 @@ static int efdr_common(fpt_ctx *ctx, const char *what, const double *d_exp, cons
                        double *d_out) {
     {
         ProfScope ps(ctx, FPT_KERNEL_FDR);
-        CU(launch_efdr(ctx->stream, ctx->d_dm, ctx->d_lut, ctx->lut_e, ctx->lut_o, d_exp, d_winp, d_off, n_iv, (int)max_len,
+        CU(launch_efdr(ctx->stream, ctx->d_dm, ctx->d_lut, ctx->d_guide, ctx->lut_e, ctx->lut_o, d_exp, d_winp, d_off, n_iv, (int)max_len,
                        hw, times, seed, d_nulls, m, d_out, ctx->d_status, ctx->sm_count));
     }
     ctx->launches++;

@@ -63,8 +63,8 @@ struct NullDraw {
 
 // One NB draw by inverse transform for expected count `ex`: the smallest k with cdf(k) >= u, its cdf and
 // z = ndtri(1 - cdf) (dispersion.pyx:318-355: the p-value of a sampled count is nbinom.cdf(k, p, r)).
-__device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__restrict__ lut, int lut_e, int lut_o, double ex,
-                                           double u) {
+__device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__restrict__ lut,
+                                           const unsigned short *__restrict__ guide, int lut_e, int lut_o, double ex, double u) {
     NullDraw d;
     long long lo = 0;
     const int e = (int)ex;
@@ -72,6 +72,12 @@ __device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__re
         const double2 *row = lut + (size_t)e * lut_o;
         if (__ldg(&row[lut_o - 1]).x >= u) {
             int a = 0, b = lut_o - 1;  // invariant: cdf(b) >= u
+            if (guide) {  // the row's quantile guide brackets the draw: a few entries are bisected, not the row
+                const int g = (int)(u * (double)kGuide);
+                const unsigned short *gr = guide + (size_t)e * (kGuide + 1) + g;
+                a = __ldg(gr);
+                b = __ldg(gr + 1);
+            }
             while (a < b) {
                 const int m = (a + b) >> 1;
                 if (__ldg(&row[m]).x >= u) b = m; else a = m + 1;
@@ -134,14 +140,15 @@ __device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__re
 }
 
 // dispersion_model.sample over a flat array (row-major (n, times) outputs like the reference's)
-__global__ void null_sample_kernel(const double *__restrict__ dm, const double2 *__restrict__ lut, int lut_e, int lut_o,
+__global__ void null_sample_kernel(const double *__restrict__ dm, const double2 *__restrict__ lut,
+                                   const unsigned short *__restrict__ guide, int lut_e, int lut_o,
                                    const double *__restrict__ ex, long long n, int times, unsigned long long seed,
                                    long long first_index, long long *__restrict__ counts_out, double *__restrict__ pvals_out) {
     const long long tot = n * (long long)times;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
         const long long i = q / times;
         const int j = (int)(q - i * times);
-        const NullDraw d = null_draw(dm, lut, lut_e, lut_o, ex[i], null_uniform(seed, first_index + i, j));
+        const NullDraw d = null_draw(dm, lut, guide, lut_e, lut_o, ex[i], null_uniform(seed, first_index + i, j));
         if (counts_out) counts_out[q] = d.k;
         if (pvals_out) pvals_out[q] = d.p;
     }
@@ -165,6 +172,7 @@ struct FdrParams {
     double *out;
     const double *dm;
     const double2 *lut;
+    const unsigned short *guide;
     int lut_e, lut_o;
     int np;    // power of two >= the longest interval
     int nmax;  // longest interval
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
                 __syncthreads();  // zcol free (and, first pass, the sort visible)
                 for (int q = tid; q < nj * n; q += kFdrThreads) {
                     const int jj = q / n, i = q - jj * n;
-                    const NullDraw d = null_draw(P.dm, P.lut, P.lut_e, P.lut_o, P.ex[o0 + i], null_uniform(P.seed, o0 + i, j0 + jj));
+                    const NullDraw d = null_draw(P.dm, P.lut, P.guide, P.lut_e, P.lut_o, P.ex[o0 + i], null_uniform(P.seed, o0 + i, j0 + jj));
                     zcol[jj * P.nmax + i] = d.z;
                 }
                 __syncthreads();
@@ -319,26 +327,28 @@ size_t efdr_smem_bytes(int np, int nmax, int jb) {
     return (size_t)np * 8 + (size_t)jb * nmax * 8 + (size_t)np * 4 + (size_t)nmax * 4 + (size_t)(np + 1) * 4 + 16;
 }
 
-cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 *lut, int lut_e, int lut_o, const double *ex,
+cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e,
+                               int lut_o, const double *ex,
                                long long n, int times, unsigned long long seed, long long first_index, long long *counts_out,
                                double *pvals_out, int sm_count) {
     const long long tot = n * (long long)times;
     if (tot <= 0) return cudaSuccess;
     long long blocks = (tot + 255) / 256;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    null_sample_kernel<<<(unsigned)blocks, 256, 0, st>>>(dm, lut, lut_e, lut_o, ex, n, times, seed, first_index, counts_out,
+    null_sample_kernel<<<(unsigned)blocks, 256, 0, st>>>(dm, lut, guide, lut_e, lut_o, ex, n, times, seed, first_index, counts_out,
                                                         pvals_out);
     return cudaGetLastError();
 }
 
-cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, int lut_e, int lut_o, const double *ex,
+cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e, int lut_o,
+                        const double *ex,
                         const double *winp, const long long *off, long long n_iv, int nmax, int hw, int times,
                         unsigned long long seed, const double *nulls, long long m, double *out, int *status, int sm_count) {
     if (n_iv <= 0 || nmax <= 0) return cudaSuccess;
     FdrParams P;
     P.ex = ex; P.winp = winp; P.off = off; P.n_iv = n_iv; P.hw = hw; P.times = times; P.seed = seed;
     P.inv_sqrt_k = 1.0 / sqrt((double)(2 * hw + 1));
-    P.out = out; P.dm = dm; P.lut = lut; P.lut_e = lut_e; P.lut_o = lut_o;
+    P.out = out; P.dm = dm; P.lut = lut; P.guide = guide; P.lut_e = lut_e; P.lut_o = lut_o;
     P.nmax = nmax;
     P.np = 1;
     while (P.np < nmax) P.np <<= 1;

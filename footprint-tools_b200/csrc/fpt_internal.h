@@ -7,7 +7,8 @@
 
 namespace fpt {
 
-constexpr int kModelDoubles = 24;  // 9 mu params + 15 r params (dispersion.pyx:117-125)
+constexpr int kModelDoubles = 24;
+constexpr int kGuide = 64;         // quantile guide entries per table row (fpt_ops.cu guide_build_kernel, fpt_fdr.cu)  // 9 mu params + 15 r params (dispersion.pyx:117-125)
 
 // Fused-kernel geometry. One CTA = kThreads threads works on sub-tiles of at
 // most kComputeMax scored positions staged into at most kStageCap shared-memory slots.
@@ -107,13 +108,16 @@ int score_fast_blocks_per_sm(size_t smem);
 cudaError_t launch_score_fast(cudaStream_t st, const ScoreParams &p, int grid);
 cudaError_t launch_window_fast(cudaStream_t st, const WindowParams &w, int sm_count);
 
-cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 *lut, int lut_e, int lut_o, const double *ex,
+cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e,
+                               int lut_o, const double *ex,
                                long long n, int times, unsigned long long seed, long long first_index, long long *counts_out,
                                double *pvals_out, int sm_count);
-cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, int lut_e, int lut_o, const double *ex,
+cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e, int lut_o,
+                        const double *ex,
                         const double *winp, const long long *off, long long n_iv, int nmax, int hw, int times,
                         unsigned long long seed, const double *nulls, long long m, double *out, int *status, int sm_count);
 
+cudaError_t launch_guide_build(cudaStream_t st, const double2 *lut, int lut_e, int lut_o, unsigned short *guide);
 cudaError_t launch_lut_build(cudaStream_t st, const double *dm, double2 *lut, int lut_e, int lut_o);
 cudaError_t launch_nb_values(cudaStream_t st, const double *dm, const double *e, const double *o, long long n,
                              int what, int model_index, long long row_len, int model_stride, double *out);

@@ -36,6 +36,27 @@ __global__ void lut_build_kernel(const double *__restrict__ dm, double2 *__restr
     }
 }
 
+// ---- quantile guide of the table rows, for the inverse-transform null sampler (fpt_fdr.cu) ----------
+// guide[e][g] = min{k : cdf_e(k) >= g / kGuide} (k capped at lut_o - 1), guide[e][kGuide] = lut_o - 1: a uniform u in
+// [g/kGuide, (g+1)/kGuide) has its draw in [guide[e][g], guide[e][g+1]], so the sampler bisects a few entries
+// instead of the whole row.
+__global__ void guide_build_kernel(const double2 *__restrict__ lut, int lut_e, int lut_o, unsigned short *__restrict__ guide) {
+    const int n = lut_e * (kGuide + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int e = i / (kGuide + 1), g = i - e * (kGuide + 1);
+        const double2 *row = lut + (size_t)e * lut_o;
+        int a = 0, b = lut_o - 1;
+        if (g < kGuide) {
+            const double u = (double)g / (double)kGuide;
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if (row[m].x >= u) b = m; else a = m + 1;
+            }
+        }
+        guide[i] = (unsigned short)b;
+    }
+}
+
 // ---- dispersion_model.p_values / pmf_values / log_pmf_values (dispersion.pyx:170-316) --------
 __global__ void nb_values_kernel(const double *__restrict__ dm, const double *__restrict__ ex,
                                  const double *__restrict__ ob, long long n, int what, int model_index,
@@ -313,6 +334,13 @@ cudaError_t launch_lut_build(cudaStream_t st, const double *dm, double2 *lut, in
     long long n = (long long)lut_e * lut_o;
     if (n <= 0) return cudaSuccess;
     lut_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(dm, lut, lut_e, lut_o);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_guide_build(cudaStream_t st, const double2 *lut, int lut_e, int lut_o, unsigned short *guide) {
+    const long long n = (long long)lut_e * (kGuide + 1);
+    if (n <= 0) return cudaSuccess;
+    guide_build_kernel<<<grid_for(n, 128), 128, 0, st>>>(lut, lut_e, lut_o, guide);
     return cudaGetLastError();
 }
 
