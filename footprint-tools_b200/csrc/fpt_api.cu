@@ -500,7 +500,7 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
             CU(score_fused_prepare());
             ctx->fused_prepared = true;
         }
-        const int per_sm = score_fused_blocks_per_sm(shw != 0, inwin);
+        const int per_sm = score_fused_blocks_per_sm(shw != 0, inwin, p.hist != nullptr);
         if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: fused kernel does not fit on an SM");
         long long grid = (long long)ctx->sm_count * per_sm;
         if (grid > p.n_tiles) grid = p.n_tiles;

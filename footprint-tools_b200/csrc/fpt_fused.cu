@@ -34,6 +34,7 @@ namespace fpt {
 namespace {
 
 constexpr int kGPad = 24;                      // readable entries after the group arrays
+constexpr int kHistSubE = 16, kHistSubO = 64;  // bins of the learn_dm histogram counted in shared memory first
 constexpr unsigned kPackedCutLimit = 0x3FFu;   // largest cut count the packed format carries
 
 __device__ __forceinline__ unsigned vmin2(unsigned a, unsigned b) { return __vminu2(a, b); }
@@ -309,6 +310,11 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
     // c-space positions beyond the tile (P.tile < kCCap) and therefore have the least scoring work
     const bool builder = warp == kFT / 32 - 1;
     __shared__ double q4tab[kNdTab];  // 2^(j/4) for ndtr4 (INWIN)
+    // learn_dm only: sub-histogram at the end of the dynamic allocation (launched with 4 KB more when P.hist is set,
+    // so that the detect pass keeps its L1 carve-out)
+    unsigned *hsub = reinterpret_cast<unsigned *>(zsT + (INWIN ? 4 * kZS : 0));
+    if (P.hist)
+        for (int i = tid; i < kHistSubE * kHistSubO; i += kFT) hsub[i] = 0;
     if (INWIN) ndtr4_table_init(q4tab, tid);
     const int WH = INWIN ? P.wh_max : 0;
     const bool want_win = INWIN && P.winp_out != nullptr && P.n_scales > 0;
@@ -742,10 +748,15 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
                     }
                 }
                 if (P.hist) {
+                    // learn_dm histogram (cli/learn_dm.py:276-287). Most positions fall into a few low bins: those are
+                    // counted in a shared-memory sub-histogram (flushed once when the CTA is done), the rest go to
+                    // global memory directly — contended 64-bit global atomics were 80 % of the learn_dm pass.
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (((omask >> e) & 1u) && exi[e] < P.hist_d0 && obi[e] < P.hist_d1)
-                            atomicAdd(P.hist + (size_t)exi[e] * P.hist_d1 + obi[e], 1ULL);
+                        if (((omask >> e) & 1u) && exi[e] < P.hist_d0 && obi[e] < P.hist_d1) {
+                            if (exi[e] < kHistSubE && obi[e] < kHistSubO) atomicAdd(&hsub[exi[e] * kHistSubO + obi[e]], 1u);
+                            else atomicAdd(P.hist + (size_t)exi[e] * P.hist_d1 + obi[e], 1ULL);
+                        }
                 }
                 if (!INWIN && direct) {
                     // hand the evaluation to direct_fix_kernel (z is only needed for outputs in this mode)
@@ -830,6 +841,12 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
         tile = ntile; hi = nhi; buf ^= 1;
         tb = tb == 2 ? 0 : tb + 1;
     }
+    if (P.hist) {  // flush the shared-memory part of the histogram (the loop's last barrier published it)
+        for (int i = tid; i < kHistSubE * kHistSubO; i += kFT) {
+            const unsigned v = hsub[i];
+            if (v) atomicAdd(P.hist + (size_t)(i / kHistSubO) * P.hist_d1 + (i % kHistSubO), (unsigned long long)v);
+        }
+    }
     // the last sub-tile's deferred work
     if (pend_omask) {
         if (INWIN) {
@@ -850,13 +867,14 @@ __global__ void __launch_bounds__(kFT, INWIN ? FPT_FUSED_CTAS : FPT_SPLIT_CTAS) 
 
 }  // namespace
 
-size_t score_fused_smem_bytes(bool inwin) {
+size_t score_fused_smem_bytes(bool inwin, bool hist) {
     size_t b = 4096 * sizeof(float);
     b += (size_t)(2 * kXCap + 4 * kXPad) * sizeof(uint32_t);  // [pad | cw | pad][pad | wcw | pad]
     b += (size_t)2 * (kNG + kGPad) * sizeof(uint4);
     b += sizeof(double) * kModelDoubles + 3 * sizeof(FastRegions) + sizeof(Ahead) + 16;
     b += (size_t)(2 * kXCap + kNG) * sizeof(uint32_t);  // rawP, rawM, lead
     if (inwin) b += (size_t)4 * kZS * sizeof(double);  // z of the tile, transposed
+    if (hist) b += (size_t)kHistSubE * kHistSubO * sizeof(unsigned);
     return b;
 }
 
@@ -865,21 +883,21 @@ cudaError_t score_fused_prepare() {
                         (const void *)score_fused_kernel<true, false>, (const void *)score_fused_kernel<false, false>};
     for (int i = 0; i < 4; ++i) {
         cudaError_t e = cudaFuncSetAttribute(k[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)score_fused_smem_bytes(i < 2));
+                                             (int)score_fused_smem_bytes(i < 2, true));
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-int score_fused_blocks_per_sm(bool smooth, bool inwin) {
+int score_fused_blocks_per_sm(bool smooth, bool inwin, bool hist) {
     int n = 0;
     const void *k = smooth ? (inwin ? (const void *)score_fused_kernel<true, true> : (const void *)score_fused_kernel<true, false>)
                            : (inwin ? (const void *)score_fused_kernel<false, true> : (const void *)score_fused_kernel<false, false>);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kFT, score_fused_smem_bytes(inwin)) == cudaSuccess ? n : 0;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kFT, score_fused_smem_bytes(inwin, hist)) == cudaSuccess ? n : 0;
 }
 
 cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth, bool inwin) {
-    const size_t smem = score_fused_smem_bytes(inwin);
+    const size_t smem = score_fused_smem_bytes(inwin, p.hist != nullptr);
     if (smooth && inwin) score_fused_kernel<true, true><<<grid, kFT, smem, st>>>(p);
     else if (smooth) score_fused_kernel<true, false><<<grid, kFT, smem, st>>>(p);
     else if (inwin) score_fused_kernel<false, true><<<grid, kFT, smem, st>>>(p);

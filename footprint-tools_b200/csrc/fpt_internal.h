@@ -95,9 +95,9 @@ cudaError_t launch_score(cudaStream_t st, const ScoreParams &p, int grid);
 cudaError_t score_kernel_prepare(size_t smem);
 int score_kernel_blocks_per_sm(size_t smem);
 
-size_t score_fused_smem_bytes(bool inwin);
+size_t score_fused_smem_bytes(bool inwin, bool hist);
 cudaError_t score_fused_prepare();
-int score_fused_blocks_per_sm(bool smooth, bool inwin);
+int score_fused_blocks_per_sm(bool smooth, bool inwin, bool hist);
 cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth, bool inwin);
 
 cudaError_t launch_direct_fix(cudaStream_t st, const ScoreParams &p, int sm_count);
