@@ -33,7 +33,9 @@ def _check(res, ref, scales, oracle=None, out_off=None):
 @pytest.mark.parametrize("lut", [(256, 512), (0, 0), (8, 16)])
 @pytest.mark.parametrize("hw,shw,clip,scales", [(5, 50, 0.01, (3, 5, 7)), (5, 50, 0.01, (3,)), (5, 0, 0.01, (3,)),
                                                 (3, 30, 0.02, (1, 4)), (5, 20, 0.01, (2,)), (4, 50, 0.025, (3,)),
-                                                (5, 50, 0.05, (3,)), (16, 100, 0.01, (3, 32))])
+                                                (5, 50, 0.05, (3,)), (16, 100, 0.01, (3, 32)),
+                                                (5, 50, 0.01, (5,)), (5, 50, 0.01, (7,)), (5, 50, 0.01, (3, 5)),
+                                                (5, 0, 0.01, (0, 8))])
 def test_score_matches_oracle(ctx, oracle, table, hw, shw, clip, scales, lut):
     if lut != (256, 512) and (hw, shw) not in ((5, 50), (5, 0)):
         pytest.skip("table variants are exercised on the default geometry")
