@@ -91,6 +91,11 @@ SIGNATURES = {
     "fpt_detect_fdr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                  C.c_int, C.c_uint64, C.c_void_p, C.c_int]),
     "fpt_empirical_fdr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "fpt_format_stats": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_char,
+                                     C.c_void_p, C.c_int64, C.c_void_p]),
+    "fpt_segment": (C.c_int64, [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "fpt_format_segments": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_int,
+                                        C.c_int, C.c_char_p, C.c_int, C.c_char, C.c_void_p, C.c_int64, C.c_void_p]),
     "fpt_special": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 

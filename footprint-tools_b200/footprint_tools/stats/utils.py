@@ -10,30 +10,21 @@ def segment(x, threshold, w=1, decreasing=False):
     start = first passing index - (w-1) and end = last passing index + w; a run whose widened start
     lies inside the previous segment extends that segment instead.
 
-    Two behaviours of the reference's single pass (utils.pyx:38-50) are kept: a run still open at
-    the end of the array is not reported, and a run near the array start only begins once
-    index - (w-1) >= 0 (so it starts at 0, and is dropped if it ends before index w-1)."""
+    The reference's single pass (utils.pyx:38-50) is run natively (fpt_segment, host code of libfpt_b200.so) with
+    all of its behaviours: a run still open at the end of the array is not reported, a run near the array start
+    only begins once index - (w-1) >= 0, and a NaN neither opens nor closes a run."""
+    from .. import _native
+
     x = np.ascontiguousarray(x, dtype=np.float64)
-    sign = -1.0 if decreasing else 1.0
-    passing = (sign * x) >= (sign * threshold)
-    out = []
-    if x.shape[0] == 0:
-        return out
-    edges = np.diff(passing.astype(np.int8))
-    starts = list(np.nonzero(edges == 1)[0] + 1)
-    ends = list(np.nonzero(edges == -1)[0] + 1)  # first failing index after each run
-    if passing[0]:
-        starts.insert(0, 0)
-    for s, e in zip(starts, ends):  # zip drops a trailing open run
-        first = max(int(s), w - 1)
-        if first >= e:
-            continue
-        lo, hi = first - w + 1, int(e) - 1 + w
-        if out and lo <= out[-1][1]:
-            out[-1][1] = hi
-        else:
-            out.append([lo, hi])
-    return out
+    n = x.shape[0]
+    if n == 0:
+        return []
+    pairs = np.empty((n // 2 + 1, 2), dtype=np.int64)
+    m = _native.lib().fpt_segment(x.ctypes.data, n, float(threshold), int(w), int(bool(decreasing)), pairs.ctypes.data,
+                                  pairs.shape[0])
+    if m < 0:
+        raise _native.FptError("fpt_segment: bad argument")
+    return pairs[:m].tolist()
 
 
 def bisect(a, b):

@@ -227,6 +227,28 @@ int fpt_detect_fdr(fpt_ctx *ctx, const double *exp, const double *winp, const in
 int fpt_empirical_fdr(fpt_ctx *ctx, const double *pvals_null, int64_t m, const double *pvals, int64_t n, double *out,
                       int mem);
 
+/* ---- text output (host code) ---------------------------------------------------- */
+
+/* write_stats_to_output (cli/utils.py:119-164) for a batch of intervals: one row per position,
+ * "chrom<d>start+i<d>start+i+1<d>v0<d>v1...\n" with every value as Python's format(v, ".{precision}f")
+ * (correctly rounded; "nan", "inf", "-inf"). cols[c] is a column of out_off[n_iv] doubles (HOST). Whole
+ * intervals are formatted until `buf` (cap bytes) cannot take another row; returns the bytes written and
+ * sets *n_done to the number of intervals consumed (call again from there with a flushed buffer). */
+int64_t fpt_format_stats(const char *const *chroms, const int64_t *starts, const int64_t *out_off, int64_t n_iv,
+                         const double *const *cols, int ncols, int precision, char delim, char *buf, int64_t cap,
+                         int64_t *n_done);
+
+/* utils.segment (stats/utils.pyx:15-50): runs of elements passing `threshold`, widened by w-1 / w and merged;
+ * pairs receives [start, end] per segment (up to cap_pairs); returns the number of segments. */
+int64_t fpt_segment(const double *x, int64_t n, double threshold, int w, int decreasing, int64_t *pairs, int64_t cap_pairs);
+
+/* write_segments_to_output (cli/utils.py:167-214) for a batch: per interval utils.segment(stats, threshold, w,
+ * decreasing) and one BED row "chrom<d>start+s<d>start+e<d>name<d>min(stats[s:e])\n" per segment. Same buffer
+ * protocol as fpt_format_stats. */
+int64_t fpt_format_segments(const char *const *chroms, const int64_t *starts, const int64_t *out_off, int64_t n_iv,
+                            const double *stats, double threshold, int w, int decreasing, const char *name, int precision,
+                            char delim, char *buf, int64_t cap, int64_t *n_done);
+
 /* Scalar probes of the device special functions (used by the parity tests; HOST arrays).
  * fn: 0 incbet(a,b,x) 1 gamma(a) 2 lgam(a) 3 ndtr(a) 4 ndtri(a) 5 igamc(a,b) 6 chdtrc(a,b) 7 log1p(a)
  *     8 nbinom.logpmf(k=a,p=b,r=x) 9 nbinom.pmf 10 nbinom.cdf (stats/distributions/nbinom.pyx:82-138) */
