@@ -70,19 +70,19 @@ __device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__re
     const int e = (int)ex;
     if (lut && ex == (double)e && e >= 0 && e < lut_e) {
         const double2 *row = lut + (size_t)e * lut_o;
-        if (__ldg(&row[lut_o - 1]).x >= u) {
-            int a = 0, b = lut_o - 1;  // invariant: cdf(b) >= u
-            if (guide) {  // the row's quantile guide brackets the draw: a few entries are bisected, not the row
-                const int g = (int)(u * (double)kGuide);
-                const unsigned short *gr = guide + (size_t)e * (kGuide + 1) + g;
-                a = __ldg(gr);
-                b = __ldg(gr + 1);
-            }
-            while (a < b) {
-                const int m = (a + b) >> 1;
-                if (__ldg(&row[m]).x >= u) b = m; else a = m + 1;
-            }
-            const double2 v = __ldg(&row[b]);
+        int a = 0, b = lut_o - 1;
+        if (guide) {  // the row's quantile guide brackets the draw: a few entries are bisected, not the row
+            const int g = (int)(u * (double)kGuide);
+            const unsigned short *gr = guide + (size_t)e * (kGuide + 1) + g;
+            a = __ldg(gr);
+            b = __ldg(gr + 1);
+        }
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if (__ldg(&row[m]).x >= u) b = m; else a = m + 1;
+        }
+        const double2 v = __ldg(&row[b]);
+        if (v.x >= u) {  // always, unless the draw lies beyond the last table entry (b == lut_o - 1 then)
             d.k = b; d.p = v.x; d.z = v.y;
             return d;
         }
@@ -137,6 +137,38 @@ __device__ __noinline__ NullDraw null_draw(const double *dm, const double2 *__re
     d.p = nb_cdf((int)hi, pr, rr);
     d.z = ndtri_fn(1.0 - d.p);
     return d;
+}
+
+// Two draws at once: the table searches run in lock-step so that both rows' gathers are in flight together (the
+// search is a chain of dependent L1/L2 accesses; one chain per thread leaves the memory pipe idle). Anything that
+// is not a plain in-table draw takes null_draw. Same results as two null_draw calls.
+__device__ __forceinline__ void null_draw2(const double *dm, const double2 *__restrict__ lut, const unsigned short *__restrict__ guide,
+                                           int lut_e, int lut_o, double ex0, double u0, double ex1, double u1, bool has1,
+                                           NullDraw &d0, NullDraw &d1) {
+    const int e0 = (int)ex0, e1 = (int)ex1;
+    const bool t0 = lut && guide && ex0 == (double)e0 && e0 >= 0 && e0 < lut_e;
+    const bool t1 = has1 && lut && guide && ex1 == (double)e1 && e1 >= 0 && e1 < lut_e;
+    const double2 *row0 = lut + (size_t)(t0 ? e0 : 0) * lut_o, *row1 = lut + (size_t)(t1 ? e1 : 0) * lut_o;
+    int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+    if (t0) {
+        const unsigned short *gr = guide + (size_t)e0 * (kGuide + 1) + (int)(u0 * (double)kGuide);
+        a0 = __ldg(gr); b0 = __ldg(gr + 1);
+    }
+    if (t1) {
+        const unsigned short *gr = guide + (size_t)e1 * (kGuide + 1) + (int)(u1 * (double)kGuide);
+        a1 = __ldg(gr); b1 = __ldg(gr + 1);
+    }
+    while (a0 < b0 || a1 < b1) {
+        const int m0 = (a0 + b0) >> 1, m1 = (a1 + b1) >> 1;
+        const double v0 = __ldg(&row0[m0]).x, v1 = __ldg(&row1[m1]).x;
+        if (a0 < b0) { if (v0 >= u0) b0 = m0; else a0 = m0 + 1; }
+        if (a1 < b1) { if (v1 >= u1) b1 = m1; else a1 = m1 + 1; }
+    }
+    const double2 r0 = __ldg(&row0[b0]), r1 = __ldg(&row1[b1]);
+    if (t0 && r0.x >= u0) { d0.k = b0; d0.p = r0.x; d0.z = r0.y; }
+    else d0 = null_draw(dm, lut, guide, lut_e, lut_o, ex0, u0);
+    if (t1 && r1.x >= u1) { d1.k = b1; d1.p = r1.x; d1.z = r1.y; }
+    else if (has1) d1 = null_draw(dm, lut, guide, lut_e, lut_o, ex1, u1);
 }
 
 // dispersion_model.sample over a flat array (row-major (n, times) outputs like the reference's)
@@ -256,10 +288,17 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
             for (int j0 = 0; j0 < P.times; j0 += P.jb) {
                 const int nj = min(P.jb, P.times - j0);
                 __syncthreads();  // zcol free (and, first pass, the sort visible)
-                for (int q = tid; q < nj * n; q += kFdrThreads) {
-                    const int jj = q / n, i = q - jj * n;
-                    const NullDraw d = null_draw(P.dm, P.lut, P.guide, P.lut_e, P.lut_o, P.ex[o0 + i], null_uniform(P.seed, o0 + i, j0 + jj));
-                    zcol[jj * P.nmax + i] = d.z;
+                for (int q = tid; q < nj * n; q += 2 * kFdrThreads) {  // two draws per thread and pass (null_draw2)
+                    const int q1 = q + kFdrThreads;
+                    const bool has1 = q1 < nj * n;
+                    const int jj0 = q / n, i0 = q - jj0 * n;
+                    const int jj1 = has1 ? q1 / n : jj0, i1 = has1 ? q1 - jj1 * n : i0;
+                    NullDraw d0, d1;
+                    d1.z = 0.0;
+                    null_draw2(P.dm, P.lut, P.guide, P.lut_e, P.lut_o, P.ex[o0 + i0], null_uniform(P.seed, o0 + i0, j0 + jj0),
+                               P.ex[o0 + i1], null_uniform(P.seed, o0 + i1, j0 + jj1), has1, d0, d1);
+                    zcol[jj0 * P.nmax + i0] = d0.z;
+                    if (has1) zcol[jj1 * P.nmax + i1] = d1.z;
                 }
                 __syncthreads();
                 for (int q = tid; q < nj * n; q += kFdrThreads) {

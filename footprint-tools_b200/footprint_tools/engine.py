@@ -213,6 +213,30 @@ def detect_fdr_host(ctx, exp, winp, out_off, hw=3, times=50, seed=0):
     return ctx.detect_fdr(exp, winp, out_off, hw, times, seed)
 
 
+def detect_host(ctx, batch, hw=5, shw=50, clip=0.01, win_hw=3, fdr_shuffle_n=50, seed=1):
+    """The per-interval body of `ftd detect` (cli/detect.py:120-144) for a whole batch: scoring, windowed p-values,
+    empirical FDR. Returns the five columns the reference stacks per interval — exp, obs, -log(pvals),
+    -log(win_pvals), efdr (natural logarithm, detect.py:142-144) — as float64[batch.total] arrays laid out by
+    batch.out_off. `seed` plays the role of np.random.seed(seed) (detect.py:349) for the counter-based draws."""
+    res = score_host(ctx, batch, hw, shw, clip, (win_hw,))
+    efdr = ctx.detect_fdr(res["exp"], res["winp"][0], batch.out_off, win_hw, fdr_shuffle_n, seed)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nlp, nlw = -np.log(res["pval"]), -np.log(res["winp"][0])
+    return {"exp": res["exp"], "obs": res["obs"], "neglog_pval": nlp, "neglog_winpval": nlw, "efdr": efdr}
+
+
+def write_detect_outputs(cols, chroms, starts, out_off, bedgraph_file, bed_files=None):
+    """What cli/detect.py:398-408 writes for every interval, for a whole batch: the five stats columns to the bedGraph
+    handle and, per FDR threshold, the footprint segments of the efdr column (decreasing, w = 3) to its BED handle."""
+    from .cli import utils as cli_utils
+
+    cli_utils.write_stats_batch(chroms, starts, out_off,
+                                [cols["exp"], cols["obs"], cols["neglog_pval"], cols["neglog_winpval"], cols["efdr"]],
+                                file=bedgraph_file)
+    for thresh, fh in (bed_files or {}).items():
+        cli_utils.write_segments_batch(chroms, starts, out_off, cols["efdr"], thresh, file=fh, decreasing=True)
+
+
 def shard_intervals(lengths, world_size):
     """Bases-balanced partition of an interval list over `world_size` GPUs:
     longest-processing-time-first greedy on the padded lengths; each rank's list keeps the

@@ -174,3 +174,31 @@ def test_detect_fdr_is_calibrated_under_the_null(ctx):
     hist = np.histogram(v, bins=10, range=(0, 1))[0] / v.size
     assert np.all(np.abs(hist - 0.1) < 0.03), hist
     assert (e[~inner] == 1.0).all()  # edge positions: observed window p = 1 -> every null value is <= it
+
+
+def test_detect_batch_columns_and_files(ctx, oracle):
+    """engine.detect_host + write_detect_outputs: the columns of cli/detect.py:142-144 and the files of :398-408."""
+    import io
+
+    table = synth.vierstra_table()
+    batch, info = synth.make_batch(30, 55, seed=9, table=table, depth_scale=5.0)
+    cols = engine.detect_host(ctx, batch, fdr_shuffle_n=25, seed=3)
+    seq, cp, cm, in_off = synth.oracle_inputs(batch, info)
+    ref = oracle.score_batch(seq, cp, cm, in_off, batch.out_off, table, mu=synth.MU_PARAMS, r=synth.R_PARAMS, scales=(3,), nthreads=4)
+    assert np.array_equal(cols["exp"], ref["exp"]) and np.array_equal(cols["obs"], ref["obs"])
+    assert_pvalues_close(np.exp(-cols["neglog_pval"]), ref["pval"], "pval column")
+    assert cols["efdr"].shape == (batch.total,) and np.all((cols["efdr"] >= 0) & (cols["efdr"] <= 1))
+    chroms = ["chr%d" % (k % 4 + 1) for k in range(batch.n_iv)]
+    starts = np.arange(batch.n_iv, dtype=np.int64) * 5000 + 100
+    bg, bed = io.StringIO(), {0.05: io.StringIO(), 0.5: io.StringIO()}
+    engine.write_detect_outputs(cols, chroms, starts, batch.out_off, bg, bed)
+    rows = bg.getvalue().splitlines()
+    assert len(rows) == batch.total
+    first = rows[0].split("\t")
+    assert first[0] == "chr1" and first[1] == "100" and first[2] == "101" and len(first) == 8
+    assert first[3] == "%0.4f" % cols["exp"][0] and first[7] == "%0.4f" % cols["efdr"][0]
+    n05, n5 = bed[0.05].getvalue().count("\n"), bed[0.5].getvalue().count("\n")
+    assert n5 >= n05 >= 0
+    for line in bed[0.5].getvalue().splitlines()[:20]:
+        f = line.split("\t")
+        assert len(f) == 5 and f[3] == "." and float(f[4]) <= 0.5
