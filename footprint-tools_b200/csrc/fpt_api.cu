@@ -76,6 +76,7 @@ struct fpt_ctx {
     int n_models = 0;
     double2 *d_lut = nullptr;
     unsigned short *d_guide = nullptr;  // quantile guide of the table rows (null sampler)
+    double *d_lgam = nullptr;           // [kLgamK] lgam(k + 1), then [n_models][kLgamE] lgam(r(e)) (posterior)
     int lut_e = 0, lut_o = 0;
     int *d_status = nullptr;
     int64_t launches = 0;
@@ -232,6 +233,7 @@ int fpt_ctx_destroy(fpt_ctx *ctx) {
     cudaFree(ctx->d_dm);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_guide);
+    cudaFree(ctx->d_lgam);
     cudaFree(ctx->d_status);
     ctx->plan.release();
     ctx->scratch.release();
@@ -348,10 +350,15 @@ int fpt_dm_upload(fpt_ctx *ctx, const double *mu_params, const double *r_params,
     ctx->d_lut = nullptr;
     cudaFree(ctx->d_guide);
     ctx->d_guide = nullptr;
+    cudaFree(ctx->d_lgam);
+    ctx->d_lgam = nullptr;
     ctx->lut_e = ctx->lut_o = 0;
     CU(cudaMalloc(&ctx->d_dm, host.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->d_dm, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_models = n_models;
+    CU(cudaMalloc(&ctx->d_lgam, ((size_t)kLgamK + (size_t)n_models * kLgamE) * sizeof(double)));
+    CU(launch_lgam_tables(ctx->stream, ctx->d_dm, n_models, ctx->d_lgam, kLgamK, ctx->d_lgam + kLgamK, kLgamE));
+    ctx->launches++;
     if (lut_exp > 0 && lut_obs > 0) {
         CU(cudaMalloc(&ctx->d_lut, (size_t)lut_exp * lut_obs * sizeof(double2)));
         CU(launch_lut_build(ctx->stream, ctx->d_dm, ctx->d_lut, lut_exp, lut_obs));
@@ -1124,12 +1131,13 @@ int fpt_posterior(fpt_ctx *ctx, const double *obs, const double *exp, const doub
     DeviceGuard g(ctx->device);
     cudaStream_t st = ctx->stream;
     size_t n = (size_t)n_samples * (size_t)m, bytes = n * sizeof(double);
-    CU(ctx->scratch.need((2 * (size_t)m + 2 * n) * sizeof(double)));
+    const bool fusedp = posterior_is_fused(win_hw);
+    if (!fusedp) CU(ctx->scratch.need((2 * (size_t)m + 2 * n) * sizeof(double)));
     if (mem == FPT_MEM_DEVICE) {
         CU(launch_posterior(st, ctx->d_dm, obs, exp, fdr, w, betas, n_samples, m,
                             reinterpret_cast<const long long *>(seg_off), n_seg, fdr_cutoff, win_hw,
-                            ctx->scratch.as<double>(), out));
-        ctx->launches += 4;
+                            ctx->scratch.as<double>(), ctx->d_lgam, kLgamK, ctx->d_lgam + kLgamK, kLgamE, out));
+        ctx->launches += fusedp ? 1 : 4;
         return FPT_OK;
     }
     const double *src[4] = {obs, exp, fdr, w};
@@ -1148,8 +1156,9 @@ int fpt_posterior(fpt_ctx *ctx, const double *obs, const double *exp, const doub
     CU(ctx->h_out[0].need(bytes));
     CU(launch_posterior(st, ctx->d_dm, ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(), ctx->h_in[2].as<double>(),
                         ctx->h_in[3].as<double>(), ctx->h_in[4].as<double>(), n_samples, m, dseg, n_seg, fdr_cutoff,
-                        win_hw, ctx->scratch.as<double>(), ctx->h_out[0].as<double>()));
-    ctx->launches += 4;
+                        win_hw, ctx->scratch.as<double>(), ctx->d_lgam, kLgamK, ctx->d_lgam + kLgamK, kLgamE,
+                        ctx->h_out[0].as<double>()));
+    ctx->launches += fusedp ? 1 : 4;
     CU(cudaMemcpyAsync(out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return FPT_OK;

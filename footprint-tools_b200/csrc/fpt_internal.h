@@ -126,10 +126,14 @@ cudaError_t launch_window(cudaStream_t st, const double *x, const double *w, lon
 cudaError_t launch_counts_to_u32(cudaStream_t st, const double *x, long long n, uint32_t *out, int sm_count);
 cudaError_t launch_hist2d(cudaStream_t st, const double *e, const double *o, long long n, unsigned long long *hist,
                           int d0, int d1);
+bool posterior_is_fused(int win_hw);  // one launch, no scratch (else four kernels over 2 (m + n) doubles of scratch)
 cudaError_t launch_posterior(cudaStream_t st, const double *dm, const double *obs, const double *exp,
                              const double *fdr, const double *w, const double *betas, int n_samples, long long m,
                              const long long *seg_off, long long n_seg, double cutoff, int win_hw, double *scratch,
-                             double *out);
+                             const double *lgk, int nk, const double *lgr, int ne, double *out);
+cudaError_t launch_lgam_tables(cudaStream_t st, const double *dm, int n_models, double *lgk, int nk, double *lgr, int ne);
+constexpr int kLgamK = 4096;  // lgam(k + 1) table entries
+constexpr int kLgamE = 512;   // lgam(r(e)) table entries per model
 cudaError_t launch_posterior_prior(cudaStream_t st, const double *fdr, const double *w, int ns, long long m,
                                    double cutoff, double pseudo, double *pr_scratch, double *out);
 cudaError_t launch_posterior_delta(cudaStream_t st, const double *obs, const double *exp, const double *fdr,

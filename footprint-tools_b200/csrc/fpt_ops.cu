@@ -285,6 +285,149 @@ __global__ void posterior_combine_kernel(const double *__restrict__ lp_on, const
     }
 }
 
+// ---- fused posterior (one launch; the four kernels above remain for half-widths beyond kPostMaxHw and as the
+// separately callable stages) ---------------------------------------------------------------------------
+// A CTA owns a tile of kPostThreads - 2*hw columns plus the hw halo on both sides — one column per thread.
+//  A. per column: prior (tile columns) and protection factor delta (tile + halo), the axis-0 reductions of
+//     posterior.py:32-36,69-88 in sample order;
+//  B. per sample: log-pmf with and without delta for every column of tile + halo into shared memory (double-buffered:
+//     one barrier per sample), windowed sums (windowing.sum, edges 1.0), posterior.py:142-149 and the post-processing
+//     of cli/post.py:121-126, collected in a [tile][16 samples] shared-memory block that is written out as whole
+//     128-byte row pieces of the transposed (m x n_samples) result — the four-kernel version wrote that array one
+//     8-byte element per 512-byte stride and went through 16 bytes of scratch per sample-base.
+// lgam(k + 1) for integer counts and lgam(r(e)) for integer expected counts per model, built with the device lgam
+// itself (same values as evaluating in place): three of the six log-gamma evaluations per sample-base become loads.
+__global__ void lgam_tables_kernel(const double *__restrict__ dm, int n_models, double *__restrict__ lgk, int nk,
+                                   double *__restrict__ lgr, int ne) {
+    const long long n = (long long)nk + (long long)n_models * ne;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        if (q < nk) {
+            lgk[q] = lgam_fn((double)(q + 1));
+        } else {
+            const long long r = q - nk;
+            const int mi = (int)(r / ne), e = (int)(r - (long long)mi * ne);
+            lgr[r] = lgam_fn(fit_r(dm + (size_t)mi * kModelDoubles + 9, (double)e));
+        }
+    }
+}
+
+constexpr int kPostThreads = 128;
+constexpr int kPostMaxHw = 16;
+constexpr int kPostSC = 16;  // samples per output block
+
+__global__ void __launch_bounds__(kPostThreads) posterior_fused_kernel(
+    const double *__restrict__ dm, const double *__restrict__ obs, const double *__restrict__ ex, const double *__restrict__ fdr,
+    const double *__restrict__ w, const double *__restrict__ betas, int ns, long long m, const long long *__restrict__ seg_off,
+    long long n_seg, double cutoff, int hw, const double *__restrict__ lgk, int nk, const double *__restrict__ lgr, int ne,
+    double *__restrict__ out) {
+    __shared__ double lpon[2][kPostThreads], lpoff[2][kPostThreads];
+    __shared__ double outT[kPostThreads * kPostSC];
+    const int tid = threadIdx.x;
+    const int tj = kPostThreads - 2 * hw;
+    const long long tiles = (m + tj - 1) / tj;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long j0 = tile * tj;
+        const long long j = j0 - hw + tid;            // this thread's column (tile + halo)
+        const bool col = j >= 0 && j < m;
+        const int t = tid - hw;                       // its index inside the tile
+        const bool own = col && t >= 0 && t < tj;     // a column whose outputs this CTA writes
+        // ---- A: column statistics ----
+        double delta = 1.0, pr = 1.0;
+        bool inner = false;
+        if (col) {
+            double num = 0.0, den = 0.0, kcnt = 0.0, nw = 0.0;
+            for (int i = 0; i < ns; ++i) {
+                const size_t ix = (size_t)i * m + j;
+                const double kk = obs[ix], e = ex[ix], f = fdr[ix];
+                double nn = e > kk ? e : kk;
+                if (e != e || kk != kk) nn = CUDART_NAN;
+                const double a = __dadd_rn(kk, betas[2 * i]), b = __dadd_rn(__dadd_rn(nn, -kk), betas[2 * i + 1]);
+                const double ab = __dadd_rn(a, b);
+                double mu = __ddiv_rn(a, ab);
+                double var = __ddiv_rn(__dmul_rn(a, b), __dmul_rn(__dmul_rn(ab, ab), __dadd_rn(ab, 1.0)));
+                if (!(a > 0.0) || !(b > 0.0)) { mu = CUDART_NAN; var = CUDART_NAN; }
+                double ws = __ddiv_rn(1.0, sqrt(var));
+                if (f > cutoff) ws = 0.0;
+                num = __dadd_rn(num, __dmul_rn(ws, mu));
+                den = __dadd_rn(den, ws);
+                if (own) {
+                    if (f <= cutoff) kcnt += 1.0;
+                    nw = __dadd_rn(nw, w[ix]);
+                }
+            }
+            const double d = __ddiv_rn(num, den);
+            delta = (d != d) ? 1.0 : d;
+            if (own) {
+                const double a = __dadd_rn(__dadd_rn(nw, -kcnt), 0.5), b = __dadd_rn(kcnt, 0.5);
+                pr = __ddiv_rn(a, __dadd_rn(a, b));
+                long long s0 = 0, s1 = m;
+                if (seg_off) {
+                    const long long sg = segment_of(seg_off, n_seg, j);
+                    s0 = __ldg(seg_off + sg);
+                    s1 = __ldg(seg_off + sg + 1);
+                }
+                inner = (j - s0 >= hw) && (j < s1 - hw);
+            }
+        }
+        // ---- B: samples ----
+        for (int i0 = 0; i0 < ns; i0 += kPostSC) {
+            const int sc = min(kPostSC, ns - i0);
+            for (int c = 0; c < sc; ++c) {
+                const int i = i0 + c, buf = c & 1;
+                double von = 0.0, voff = 0.0;
+                if (col) {
+                    const size_t ix = (size_t)i * m + j;
+                    const double *par = dm + (size_t)i * kModelDoubles;
+                    const int k = (int)obs[ix];
+                    const double e_off = ex[ix];
+                    const double e_on = __dmul_rn(e_off, delta);
+                    // nbinom.logpmf (nbinom.pyx:82-101) twice, term for term as nb_logpmf evaluates it; lgam(k + 1) is
+                    // shared and, like lgam(r(e_off)) for an integer e_off, read from the tables when in range
+                    const double lg_k1 = (lgk && k >= 0 && k < nk) ? __ldg(lgk + k) : lgam_fn((double)(k + 1));
+                    const double r1 = fit_r(par + 9, e_on), m1 = fit_mu(par, e_on);
+                    const double p1 = nb_prob(r1, m1);
+                    von = (lgam_fn((double)k + r1) - lg_k1 - lgam_fn(r1)) + r1 * log(p1) + (double)k * log1p_fn(-p1);
+                    const double r0 = fit_r(par + 9, e_off), m0 = fit_mu(par, e_off);
+                    const double p0 = nb_prob(r0, m0);
+                    const int ei = (int)e_off;
+                    const double lg_r0 = (lgr && e_off == (double)ei && ei >= 0 && ei < ne) ? __ldg(lgr + (size_t)i * ne + ei)
+                                                                                            : lgam_fn(r0);
+                    voff = (lgam_fn((double)k + r0) - lg_k1 - lg_r0) + r0 * log(p0) + (double)k * log1p_fn(-p0);
+                }
+                lpon[buf][tid] = von;
+                lpoff[buf][tid] = voff;
+                __syncthreads();
+                if (own) {
+                    double ll_on = 1.0, ll_off = 1.0;
+                    if (inner) {
+                        double a = 0.0, b = 0.0;
+                        for (int d = -hw; d <= hw; ++d) {
+                            a = __dadd_rn(a, lpon[buf][tid + d]);
+                            b = __dadd_rn(b, lpoff[buf][tid + d]);
+                        }
+                        ll_on = a;
+                        ll_off = b;
+                    }
+                    const double prior = (w[(size_t)i * m + j] == 0.0) ? 1.0 : pr;
+                    const double p_off = log(prior) + ll_off, p_on = log(1.0 - prior) + ll_on;
+                    double post = -(p_off - logaddexp_fn(p_on, p_off));
+                    if (post <= 0.0) post = 0.0;
+                    outT[t * kPostSC + c] = post;
+                }
+            }
+            __syncthreads();
+            // the block [tile columns][sc samples] -> out[(j0 + t) * ns + i0 + c], contiguous pieces of sc doubles
+            const long long nt = (j0 + tj <= m) ? tj : (m - j0);
+            for (int q = tid; q < (int)nt * sc; q += kPostThreads) {
+                const int tt = q / sc, c = q - tt * sc;
+                out[(size_t)(j0 + tt) * ns + i0 + c] = outT[tt * kPostSC + c];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+
 // ---- k-mer propensities of a packed sequence (modeling/bias.py:88-111) ------------------------
 __global__ void kmer_probs_kernel(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ nmask,
                                   long long n_bases, long long n_out, const double *__restrict__ bias_le, double dflt,
@@ -391,11 +534,37 @@ cudaError_t launch_hist2d(cudaStream_t st, const double *e, const double *o, lon
     return cudaGetLastError();
 }
 
+bool posterior_is_fused(int win_hw) { return win_hw <= kPostMaxHw; }
+
+cudaError_t launch_lgam_tables(cudaStream_t st, const double *dm, int n_models, double *lgk, int nk, double *lgr, int ne) {
+    const long long n = (long long)nk + (long long)n_models * ne;
+    if (n <= 0) return cudaSuccess;
+    lgam_tables_kernel<<<grid_for(n, 128), 128, 0, st>>>(dm, n_models, lgk, nk, lgr, ne);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_posterior(cudaStream_t st, const double *dm, const double *obs, const double *exp,
                              const double *fdr, const double *w, const double *betas, int n_samples, long long m,
                              const long long *seg_off, long long n_seg, double cutoff, int win_hw, double *scratch,
-                             double *out) {
+                             const double *lgk, int nk, const double *lgr, int ne, double *out) {
     if (m <= 0 || n_samples <= 0) return cudaSuccess;
+    if (win_hw <= kPostMaxHw) {  // fused single-launch path (no scratch)
+        const int tj = kPostThreads - 2 * win_hw;
+        const long long tiles = (m + tj - 1) / tj;
+        static int per_sm = 0, sms = 0;
+        if (!per_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, posterior_fused_kernel, kPostThreads, 0) != cudaSuccess || per_sm < 1)
+                per_sm = 1;
+        }
+        long long grid = (long long)sms * per_sm;
+        if (grid > tiles) grid = tiles;
+        posterior_fused_kernel<<<(unsigned)grid, kPostThreads, 0, st>>>(dm, obs, exp, fdr, w, betas, n_samples, m, seg_off, n_seg,
+                                                                       cutoff, win_hw, lgk, nk, lgr, ne, out);
+        return cudaGetLastError();
+    }
     long long n = (long long)n_samples * m;
     double *pr = scratch, *delta = scratch + m, *lp_on = scratch + 2 * m, *lp_off = lp_on + n;
     posterior_prior_kernel<<<grid_for(m, 128), 128, 0, st>>>(fdr, w, n_samples, m, cutoff, 0.5, pr);
