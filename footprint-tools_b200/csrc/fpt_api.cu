@@ -76,7 +76,7 @@ struct fpt_ctx {
     int n_models = 0;
     double2 *d_lut = nullptr;
     unsigned short *d_guide = nullptr;  // quantile guide of the table rows (null sampler)
-    double *d_lgam = nullptr;           // [kLgamK] lgam(k + 1), then [n_models][kLgamE] lgam(r(e)) (posterior)
+    double *d_lgam = nullptr;           // [kLgamK] lgam(k + 1), then [n_models][kLgamE]{lgam(r), r, log p, log1p(-p)} (posterior)
     int lut_e = 0, lut_o = 0;
     int *d_status = nullptr;
     int64_t launches = 0;
@@ -356,7 +356,7 @@ int fpt_dm_upload(fpt_ctx *ctx, const double *mu_params, const double *r_params,
     CU(cudaMalloc(&ctx->d_dm, host.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->d_dm, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_models = n_models;
-    CU(cudaMalloc(&ctx->d_lgam, ((size_t)kLgamK + (size_t)n_models * kLgamE) * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_lgam, ((size_t)kLgamK + (size_t)n_models * kLgamE * 4) * sizeof(double)));
     CU(launch_lgam_tables(ctx->stream, ctx->d_dm, n_models, ctx->d_lgam, kLgamK, ctx->d_lgam + kLgamK, kLgamE));
     ctx->launches++;
     if (lut_exp > 0 && lut_obs > 0) {

@@ -295,8 +295,9 @@ __global__ void posterior_combine_kernel(const double *__restrict__ lp_on, const
 //     of cli/post.py:121-126, collected in a [tile][16 samples] shared-memory block that is written out as whole
 //     128-byte row pieces of the transposed (m x n_samples) result — the four-kernel version wrote that array one
 //     8-byte element per 512-byte stride and went through 16 bytes of scratch per sample-base.
-// lgam(k + 1) for integer counts and lgam(r(e)) for integer expected counts per model, built with the device lgam
-// itself (same values as evaluating in place): three of the six log-gamma evaluations per sample-base become loads.
+// lgam(k + 1) for integer counts and {lgam(r), r, log p, log1p(-p)} at integer expected counts per model, built with
+// the device functions themselves (same values as evaluating in place): three of the six log-gamma evaluations and
+// the two logarithms of the unprotected log-pmf become loads.
 __global__ void lgam_tables_kernel(const double *__restrict__ dm, int n_models, double *__restrict__ lgk, int nk,
                                    double *__restrict__ lgr, int ne) {
     const long long n = (long long)nk + (long long)n_models * ne;
@@ -306,7 +307,13 @@ __global__ void lgam_tables_kernel(const double *__restrict__ dm, int n_models, 
         } else {
             const long long r = q - nk;
             const int mi = (int)(r / ne), e = (int)(r - (long long)mi * ne);
-            lgr[r] = lgam_fn(fit_r(dm + (size_t)mi * kModelDoubles + 9, (double)e));
+            const double *par = dm + (size_t)mi * kModelDoubles;
+            const double rr = fit_r(par + 9, (double)e), mu = fit_mu(par, (double)e);
+            const double pp = nb_prob(rr, mu);
+            lgr[4 * r] = lgam_fn(rr);
+            lgr[4 * r + 1] = rr;
+            lgr[4 * r + 2] = log(pp);
+            lgr[4 * r + 3] = log1p_fn(-pp);
         }
     }
 }
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kPostThreads) posterior_fused_kernel(
         const int t = tid - hw;                       // its index inside the tile
         const bool own = col && t >= 0 && t < tj;     // a column whose outputs this CTA writes
         // ---- A: column statistics ----
-        double delta = 1.0, pr = 1.0;
+        double delta = 1.0, pr = 1.0, lpr = 0.0, l1pr = 0.0;  // log(pr), log(1 - pr): once per column, not per sample
         bool inner = false;
         if (col) {
             double num = 0.0, den = 0.0, kcnt = 0.0, nw = 0.0;
@@ -360,6 +367,8 @@ __global__ void __launch_bounds__(kPostThreads) posterior_fused_kernel(
             if (own) {
                 const double a = __dadd_rn(__dadd_rn(nw, -kcnt), 0.5), b = __dadd_rn(kcnt, 0.5);
                 pr = __ddiv_rn(a, __dadd_rn(a, b));
+                lpr = log(pr);
+                l1pr = log(1.0 - pr);
                 long long s0 = 0, s1 = m;
                 if (seg_off) {
                     const long long sg = segment_of(seg_off, n_seg, j);
@@ -387,12 +396,16 @@ __global__ void __launch_bounds__(kPostThreads) posterior_fused_kernel(
                     const double r1 = fit_r(par + 9, e_on), m1 = fit_mu(par, e_on);
                     const double p1 = nb_prob(r1, m1);
                     von = (lgam_fn((double)k + r1) - lg_k1 - lgam_fn(r1)) + r1 * log(p1) + (double)k * log1p_fn(-p1);
-                    const double r0 = fit_r(par + 9, e_off), m0 = fit_mu(par, e_off);
-                    const double p0 = nb_prob(r0, m0);
                     const int ei = (int)e_off;
-                    const double lg_r0 = (lgr && e_off == (double)ei && ei >= 0 && ei < ne) ? __ldg(lgr + (size_t)i * ne + ei)
-                                                                                            : lgam_fn(r0);
-                    voff = (lgam_fn((double)k + r0) - lg_k1 - lg_r0) + r0 * log(p0) + (double)k * log1p_fn(-p0);
+                    if (lgr && e_off == (double)ei && ei >= 0 && ei < ne) {
+                        const double2 t0 = __ldg(reinterpret_cast<const double2 *>(lgr + 4 * ((size_t)i * ne + ei)));
+                        const double2 t1 = __ldg(reinterpret_cast<const double2 *>(lgr + 4 * ((size_t)i * ne + ei)) + 1);
+                        voff = (lgam_fn((double)k + t0.y) - lg_k1 - t0.x) + t0.y * t1.x + (double)k * t1.y;
+                    } else {
+                        const double r0 = fit_r(par + 9, e_off), m0 = fit_mu(par, e_off);
+                        const double p0 = nb_prob(r0, m0);
+                        voff = (lgam_fn((double)k + r0) - lg_k1 - lgam_fn(r0)) + r0 * log(p0) + (double)k * log1p_fn(-p0);
+                    }
                 }
                 lpon[buf][tid] = von;
                 lpoff[buf][tid] = voff;
@@ -408,8 +421,8 @@ __global__ void __launch_bounds__(kPostThreads) posterior_fused_kernel(
                         ll_on = a;
                         ll_off = b;
                     }
-                    const double prior = (w[(size_t)i * m + j] == 0.0) ? 1.0 : pr;
-                    const double p_off = log(prior) + ll_off, p_on = log(1.0 - prior) + ll_on;
+                    const bool unw = w[(size_t)i * m + j] == 0.0;  // prior 1 where the sample has no weight (posterior.py:38-40)
+                    const double p_off = (unw ? 0.0 : lpr) + ll_off, p_on = (unw ? -CUDART_INF : l1pr) + ll_on;
                     double post = -(p_off - logaddexp_fn(p_on, p_off));
                     if (post <= 0.0) post = 0.0;
                     outT[t * kPostSC + c] = post;
