@@ -30,6 +30,15 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+}  // namespace
+
+int fpt::set_error(int code, const char *msg) {
+    g_err = msg ? msg : "";
+    return code;
+}
+
+namespace {
+
 #define CU(call)                                                                               \
     do {                                                                                       \
         cudaError_t e__ = (call);                                                              \

@@ -145,4 +145,7 @@ cudaError_t launch_kmer_probs(cudaStream_t st, const uint32_t *seq2, const uint3
 cudaError_t launch_special(cudaStream_t st, int fn, const double *a, const double *b, const double *x, long long n,
                            double *out);
 
+// records the message fpt_last_error() returns (thread-local, fpt_api.cu) and hands `code` back
+int set_error(int code, const char *msg);
+
 }  // namespace fpt

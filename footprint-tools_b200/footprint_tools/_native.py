@@ -72,6 +72,9 @@ SIGNATURES = {
     "fpt_bias_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int]),
     "fpt_dm_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "fpt_pack_sequence": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "fpt_cuts_from_alignments": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "fpt_unpack_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "fpt_kmer_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]),
     "fpt_score": (C.c_int, [C.c_void_p, C.POINTER(ScoreArgs), C.c_int]),
     "fpt_nb_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64,

@@ -120,6 +120,23 @@ int fpt_pack_sequence(const char *seq, int64_t n, uint32_t *seq2, uint32_t *nmas
 int fpt_kmer_probs(fpt_ctx *ctx, const uint32_t *seq2, const uint32_t *nmask, int64_t n_bases, int64_t n_out,
                    double *out, int mem);
 
+/* bamfile.lookup / _add_read / validate_read (footprint_tools/cutcounts.py:118-146, 176-250, 276-313) over decoded
+ * alignment columns (HOST): for each of n alignments with SAM `flag`, MAPQ `mapq`, 0-based reference_start and
+ * exclusive reference_end, the reference's filters are applied (unmapped dropped; QC-fail 0x200 / duplicate 0x400
+ * per the switches; MAPQ < min_qual; paired reads must be proper pairs, primary and not supplementary) and the 5'
+ * cut — reference_start + offset_plus on the forward strand, reference_end + offset_minus on the reverse strand
+ * (reference default offsets (0, -1)) — is ADDED to cuts_plus / cuts_minus[cut - track_first] when it falls inside
+ * [track_first, track_first + track_len). Returns the number of cuts added (>= 0) or an FPT_ERR_* code. */
+int64_t fpt_cuts_from_alignments(const int64_t *ref_start, const int64_t *ref_end, const uint16_t *flag,
+                                 const uint8_t *mapq, int64_t n, int min_qual, int remove_dups, int remove_qcfail,
+                                 int offset_plus, int offset_minus, int64_t track_first, int64_t track_len,
+                                 uint32_t *cuts_plus, uint32_t *cuts_minus);
+
+/* Inverse of fpt_pack_sequence for track positions [first, first + n): 'A' 'C' 'G' 'T', or 'N' where the N bit is
+ * set (what pysam.FastaFile.fetch(...).upper() gives the bias model, modeling/predict.pyx:138-140, up to the
+ * spelling of non-ACGT characters, all of which score as the default propensity). HOST buffers. */
+int fpt_unpack_sequence(const uint32_t *seq2, const uint32_t *nmask, int64_t first, int64_t n, char *out);
+
 /* ---- the hot path ------------------------------------------------------------------------- */
 
 typedef struct fpt_score_args {

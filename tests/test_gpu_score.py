@@ -47,6 +47,19 @@ def test_score_matches_oracle(ctx, oracle, table, hw, shw, clip, scales, lut):
     _check(res, ref, scales, oracle, batch.out_off)
 
 
+@pytest.mark.parametrize("hw,shw,scales", [(5, 50, (3, 5, 7)), (5, 0, (3,)), (4, 30, (2,))])
+def test_score_unaligned_track_layout(ctx, oracle, table, hw, shw, scales):
+    """Blocks laid back to back without the mod-4 congruence between track and output offsets (what a
+    genome-wide track gives, footprint_tools/ingest.py): the per-element staging / store paths."""
+    batch, info = synth.make_batch(150, hw + shw, seed=311 + shw, table=table, aligned=False)
+    assert np.any((batch.iv_start - batch.out_off[:-1]) % 4 != 0)
+    ctx.set_bias(table, 1e-6)
+    ctx.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    res = engine.score_host(ctx, batch, hw, shw, 0.01, scales)
+    ref = _oracle_score(oracle, batch, info, table, hw, shw, 0.01, scales)
+    _check(res, ref, scales, oracle, batch.out_off)
+
+
 @pytest.mark.parametrize("depth", [0.02, 40.0, 400.0])
 def test_score_depth_regimes(ctx, oracle, table, depth):
     """sparse (mostly empty windows), deep and very deep (direct NB evaluation, log-space incbet)."""

@@ -1,0 +1,349 @@
+"""Packed at-rest inputs: GenomeTrack against restatements of the reference's per-interval
+readers — bamfile.lookup (footprint_tools/cutcounts.py:176-313) on fake alignment records and
+FastaFile.fetch(...).upper() — plus the file format; the GPU tests score a track batch against the
+per-interval packing path and the oracle."""
+from collections import defaultdict
+
+import numpy as np
+import pytest
+
+from footprint_tools import ingest, synth
+from footprint_tools.ingest import GenomeTrack
+
+
+class genomic_interval(object):
+    """Duck type of genome_tools.genomic_interval as predict.pyx:130-140 and cutcounts.py:291-294 use it."""
+
+    def __init__(self, chrom, start, end, strand="+"):
+        self.chrom, self.start, self.end, self.strand = chrom, start, end, strand
+
+    def __len__(self):
+        return self.end - self.start
+
+    def widen(self, w):
+        return genomic_interval(self.chrom, self.start - w, self.end + w, self.strand)
+
+
+@pytest.fixture(scope="module")
+def table():
+    return synth.vierstra_table()
+
+
+PAIRED, PROPER, UNMAPPED, REVERSE, READ1, READ2, SECONDARY, QCFAIL, DUP, SUPP = (
+    0x1, 0x2, 0x4, 0x10, 0x40, 0x80, 0x100, 0x200, 0x400, 0x800)
+
+
+class FakeRead(object):
+    def __init__(self, qname, start, end, flag, mapq):
+        self.query_name, self.reference_start, self.reference_end = qname, start, end
+        self.flag, self.mapping_quality = flag, mapq
+
+    is_paired = property(lambda s: bool(s.flag & PAIRED))
+    is_proper_pair = property(lambda s: bool(s.flag & PROPER))
+    is_reverse = property(lambda s: bool(s.flag & REVERSE))
+    is_read1 = property(lambda s: bool(s.flag & READ1))
+    is_secondary = property(lambda s: bool(s.flag & SECONDARY))
+    is_supplementary = property(lambda s: bool(s.flag & SUPP))
+    is_qcfail = property(lambda s: bool(s.flag & QCFAIL))
+    is_duplicate = property(lambda s: bool(s.flag & DUP))
+
+
+def reference_lookup(reads, start, end, min_qual=1, remove_dups=False, remove_qcfail=True, offset=(0, -1), flip=False):
+    """cutcounts.py:118-146, 176-313 restated on a list of FakeRead (the list plays samfile.fetch)."""
+    def fetch(lo, hi):
+        for r in reads:
+            if r.reference_start < hi and r.reference_end > lo:
+                yield r
+
+    def pairs():
+        read_dict = defaultdict(lambda: [None, None])
+        for read in fetch(max(start - 10, 0), end + 10):
+            if remove_qcfail and read.is_qcfail:
+                continue
+            if remove_dups and read.is_duplicate:
+                continue
+            if read.mapping_quality < min_qual:
+                continue
+            if not read.is_paired:
+                yield read, None
+            else:
+                if not read.is_proper_pair or read.is_secondary or read.is_supplementary:
+                    continue
+                q = read.query_name
+                if q not in read_dict:
+                    read_dict[q][0 if read.is_read1 else 1] = read
+                else:
+                    if read.is_read1:
+                        yield read, read_dict[q][1]
+                    else:
+                        yield read_dict[q][0], read
+                    del read_dict[q]
+        for k, rr in read_dict.items():
+            yield rr[0], rr[1]
+
+    fw, rev = {}, {}
+    for r1, r2 in pairs():
+        for r in (r1, r2):
+            if r is None:
+                continue
+            if r.is_reverse:
+                a = int(r.reference_end) + offset[1]
+                rev[a] = rev.get(a, 0.0) + 1.0
+            else:
+                a = int(r.reference_start) + offset[0]
+                fw[a] = fw.get(a, 0.0) + 1.0
+    f = np.array([fw.get(i, 0.0) for i in range(start, end)])
+    r = np.array([rev.get(i, 0.0) for i in range(start, end)])
+    return {"+": r[::-1] if flip else f, "-": f[::-1] if flip else r}
+
+
+def random_reads(rng, chrom_len, n_pairs, n_single):
+    reads = []
+    for q in range(n_pairs):
+        s = int(rng.integers(0, chrom_len - 300))
+        l1, l2 = int(rng.integers(20, 76)), int(rng.integers(20, 76))
+        ins = int(rng.integers(max(l1, l2), 250))
+        common = PAIRED | (PROPER if rng.random() < 0.9 else 0)
+        extra = lambda: ((QCFAIL if rng.random() < 0.05 else 0) | (DUP if rng.random() < 0.1 else 0) |
+                         (SECONDARY if rng.random() < 0.03 else 0) | (SUPP if rng.random() < 0.03 else 0))
+        mq = lambda: int(rng.choice([0, 0, 1, 20, 30, 42, 60]))
+        first_is_fw = rng.random() < 0.5
+        fa = FakeRead("p%d" % q, s, s + l1, common | extra() | (READ1 if first_is_fw else READ2), mq())
+        rb = FakeRead("p%d" % q, s + ins - l2, s + ins, common | REVERSE | extra() | (READ2 if first_is_fw else READ1), mq())
+        reads += [fa, rb]
+    for q in range(n_single):
+        s = int(rng.integers(0, chrom_len - 80))
+        l = int(rng.integers(20, 76))
+        fl = (REVERSE if rng.random() < 0.5 else 0) | (QCFAIL if rng.random() < 0.05 else 0) | \
+             (DUP if rng.random() < 0.1 else 0) | (SECONDARY if rng.random() < 0.05 else 0)
+        reads.append(FakeRead("s%d" % q, s, s + l, fl, int(rng.choice([0, 1, 30, 60]))))
+    reads.sort(key=lambda r: r.reference_start)
+    return reads
+
+
+def columns(reads):
+    return (np.array([r.reference_start for r in reads]), np.array([r.reference_end for r in reads]),
+            np.array([r.flag for r in reads]), np.array([r.mapping_quality for r in reads]))
+
+
+def random_sequence(rng, n, n_frac=0.01, lower_frac=0.2):
+    s = rng.choice(list("ACGT"), n)
+    s[rng.random(n) < n_frac] = "N"
+    s[rng.random(n) < 0.002] = "R"   # IUPAC codes read as N
+    s = "".join(s)
+    low = rng.random(n) < lower_frac
+    return "".join(c.lower() if l else c for c, l in zip(s, low))
+
+
+def expected_fetch(seq, start, end):
+    out = seq[max(start, 0):max(min(end, len(seq)), 0)].upper()
+    return "".join(c if c in "ACGT" else "N" for c in out)
+
+
+@pytest.fixture(scope="module")
+def small_track():
+    rng = np.random.default_rng(8)
+    seqs = [("chrA", random_sequence(rng, 5000)), ("chrB", random_sequence(rng, 3333)), ("chrE", ""),
+            ("chrC", random_sequence(rng, 97))]
+    track = GenomeTrack.from_sequences(seqs)
+    return rng, dict(seqs), track
+
+
+def test_layout_keeps_guards_and_word_boundaries(small_track):
+    _, seqs, track = small_track
+    assert track.names == ["chrA", "chrB", "chrE", "chrC"]
+    assert np.all(track.chrom_off % 32 == 0)
+    ends = track.chrom_off + np.array(track.lengths)
+    assert track.chrom_off[0] >= ingest.GUARD and track.n_track - ends[-1] >= ingest.GUARD
+    assert np.all(track.chrom_off[1:] - ends[:-1] >= ingest.GUARD)
+    assert track.seq2.shape[0] == (track.n_track + 15) // 16 and track.nmask.shape[0] == (track.n_track + 31) // 32
+    # every guard position reads as N
+    bits = np.unpackbits(track.nmask.view(np.uint8), bitorder="little")[:track.n_track]
+    inside = np.zeros(track.n_track, dtype=bool)
+    for o, n in zip(track.chrom_off, track.lengths):
+        inside[o:o + n] = True
+    assert np.all(bits[~inside] == 1)
+
+
+def test_fetch_equals_the_uppercased_fasta_slice(small_track):
+    rng, seqs, track = small_track
+    for name, seq in seqs.items():
+        n = len(seq)
+        assert track.fasta_func.fetch(name, 0, n) == expected_fetch(seq, 0, n)
+        for _ in range(60):
+            a = int(rng.integers(-20, n + 1))
+            b = int(rng.integers(a, n + 30))
+            assert track.fasta_func.fetch(name, a, b) == expected_fetch(seq, a, b)
+
+
+def test_alignment_cut_counts_equal_the_reference_lookup():
+    rng = np.random.default_rng(21)
+    n = 6000
+    track = GenomeTrack.from_sequences([("chr0", "A" * 500), ("chr1", "ACGT" * (n // 4))])
+    reads = random_reads(rng, n, 2500, 1200)
+    for kw in ({}, {"min_qual": 30}, {"remove_dups": True, "remove_qcfail": False}, {"offset": (4, -5)}):
+        track.cuts_plus[:] = 0
+        track.cuts_minus[:] = 0
+        # streamed in two chunks: counts accumulate
+        cols = columns(reads)
+        half = len(reads) // 2
+        added = track.add_alignments("chr1", *[c[:half] for c in cols], **kw)
+        added += track.add_alignments("chr1", *[c[half:] for c in cols], **kw)
+        assert added == int(track.cuts_plus.sum()) + int(track.cuts_minus.sum()) > 0
+        assert track.cuts_plus[:track.chrom_off[1]].sum() == 0   # nothing leaks into other chromosomes / guards
+        for _ in range(25):
+            s = int(rng.integers(0, n - 400))
+            e = s + int(rng.integers(1, 400))
+            strand = "-" if rng.random() < 0.3 else "+"
+            iv = genomic_interval("chr1", s, e, strand=strand)
+            ref = reference_lookup(reads, s, e, flip=(strand == "-"), **kw)
+            got = track.read_func[iv]
+            assert got["+"].dtype == np.float64
+            assert np.array_equal(got["+"], ref["+"]) and np.array_equal(got["-"], ref["-"])
+
+
+def test_alignment_argument_errors():
+    track = GenomeTrack.from_sequences([("c", "ACGT" * 10)])
+    with pytest.raises(ValueError):
+        track.add_alignments("c", [1, 2], [5], [0, 0], [60, 60])
+    with pytest.raises(KeyError):
+        track.add_alignments("nope", [1], [5], [0], [60])
+    assert track.add_alignments("c", [], [], [], []) == 0
+    # cuts falling off the chromosome (offsets) are dropped, not written into the guard
+    assert track.add_alignments("c", [0], [40], [REVERSE], [60], offset=(0, 3)) == 0
+    assert track.cuts_minus.sum() == 0
+
+
+def test_file_round_trip_and_in_place_accumulation(tmp_path, small_track):
+    rng, seqs, track = small_track
+    track.set_cuts("chrB", rng.integers(0, 9, 3333), rng.integers(0, 9, 3333))
+    path = str(tmp_path / "sample.fptrk")
+    track.save(path)
+    back = GenomeTrack.open(path)
+    assert back.names == track.names and back.lengths == track.lengths and back.n_track == track.n_track
+    assert np.array_equal(back.chrom_off, track.chrom_off)
+    for name in ("seq2", "nmask", "cuts_plus", "cuts_minus"):
+        a = getattr(back, name)
+        assert isinstance(a, np.memmap) and a.offset % ingest.ALIGN == 0
+        assert np.array_equal(a, getattr(track, name))
+    assert back.fasta_func.fetch("chrC", 0, 97) == expected_fetch(seqs["chrC"], 0, 97)
+    with pytest.raises(ValueError):
+        back.cuts_plus[0] = 1   # read-only mapping
+    rw = GenomeTrack.open(path, mode="r+")
+    before = int(rw.cuts_plus.sum())
+    assert rw.add_alignments("chrA", [10, 10, 20], [50, 60, 70], [0, 0, 0], [60, 60, 60]) == 3
+    rw.cuts_plus.flush()
+    del rw
+    again = GenomeTrack.open(path)
+    assert int(again.cuts_plus.sum()) == before + 3
+    assert again.read_func[genomic_interval("chrA", 8, 22)]["+"].tolist() == [0, 0, 2] + [0] * 9 + [1, 0]
+    with open(path, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(ValueError):
+        GenomeTrack.open(path)
+
+
+def test_batch_points_into_the_shared_track(small_track):
+    _, seqs, track = small_track
+    ivs = [genomic_interval("chrB", 200, 500), ("chrA", 1000, 1001), genomic_interval("chrA", 60, 460), ("chrC", 0, 97)]
+    b = track.batch(ivs, pad=55)
+    assert b.seq2 is track.seq2 and b.cuts_plus is track.cuts_plus   # zero-copy
+    assert b.out_off.tolist() == [0, 300, 301, 701, 798]
+    off = dict(zip(track.names, track.chrom_off))
+    assert b.iv_start.tolist() == [off["chrB"] + 200, off["chrA"] + 1000, off["chrA"] + 60, off["chrC"]]
+    ps = track.batch(ivs, pad=5, per_strand=True)
+    assert ps.out_off.tolist() == [0, 301, 303, 704, 802]
+    assert ps.iv_start.tolist() == [v - 1 for v in b.iv_start.tolist()]
+    with pytest.raises(IndexError):
+        track.batch([("chrC", 0, 98)], pad=5)
+    with pytest.raises(ValueError):
+        track.batch(ivs, pad=200)
+
+
+def _track_with_cuts(n_chrom=3, seed=4):
+    rng = np.random.default_rng(seed)
+    chroms = [("c%d" % i, random_sequence(rng, int(rng.integers(4000, 9000)), n_frac=0.002)) for i in range(n_chrom)]
+    track = GenomeTrack.from_sequences(chroms)
+    for name, s in chroms:
+        depth = rng.gamma(0.8, 4.0, len(s)) * (rng.random(len(s)) < 0.5)
+        track.set_cuts(name, rng.poisson(depth), rng.poisson(depth))
+    ivs = []
+    for name, s in chroms:
+        for _ in range(12):
+            a = int(rng.integers(70, len(s) - 900))
+            ivs.append(genomic_interval(name, a, a + int(rng.integers(1, 800))))
+    return track, ivs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geometry", [(5, 50, 0.01), (5, 0, 0.01), (7, 20, 0.05)])
+def test_gpu_track_batch_equals_per_interval_packing(table, geometry):
+    """Scoring the zero-copy track batch gives the bytes of the per-interval path (read_func / fasta_func ->
+    IntervalBatch.from_padded), i.e. of the reference's own call pattern."""
+    from footprint_tools import _native, engine
+    from footprint_tools.modeling import dispersion, predict
+
+    hw, shw, clip = geometry
+    track, ivs = _track_with_cuts()
+    ctx = _native.default_context(0)
+    ctx.set_bias(table, 1e-6)
+    ctx.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    got = engine.score_host(ctx, track.batch(ivs, hw + shw), hw, shw, clip, (3, 5, 7))
+
+    pred = predict.prediction(track.read_func, track.fasta_func, _TableModel(table), hw, shw, clip)
+    dm = dispersion.dispersion_model()
+    dm.mu_params, dm.r_params = synth.MU_PARAMS, synth.R_PARAMS
+    out_off, ref = pred.score_batch(ivs, dm=dm, scales=(3, 5, 7))
+    assert out_off.tolist() == track.batch(ivs, hw + shw).out_off.tolist()
+    for k in ("exp", "obs", "pval", "winp"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+    # per-strand outputs of prediction.compute
+    ps = engine.score_host(ctx, track.batch(ivs, hw + shw, per_strand=True), hw, shw, clip, scales=(),
+                           want=("exp", "win"), combine=False)
+    per_iv = pred.compute_batch(ivs)
+    pb = track.batch(ivs, hw + shw, per_strand=True)
+    for k, (obs, exp, win) in enumerate(per_iv):
+        a, b = pb.out_off[k], pb.out_off[k + 1]
+        for s, strand in enumerate("+-"):
+            assert np.array_equal(ps["exp"][s, a:b], exp[strand])
+            assert np.array_equal(ps["win"][s, a:b], win[strand], equal_nan=True)
+
+
+class _TableModel(object):
+    """A bias model over an explicit 4096-entry table (what kmer_model holds after reading its file)."""
+
+    def __init__(self, table):
+        self._table = np.asarray(table, dtype=np.float64)
+
+    def offset(self):
+        return 3
+
+    def upload(self, ctx):
+        ctx.set_bias(self._table, 1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_track_batch_matches_the_oracle(table, oracle):
+    from footprint_tools import _native, engine
+    from parity import assert_score_close
+
+    track, ivs = _track_with_cuts(seed=9)
+    pad = 55
+    ctx = _native.default_context(0)
+    ctx.set_bias(table, 1e-6)
+    ctx.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    batch = track.batch(ivs, pad)
+    res = engine.score_host(ctx, batch, 5, 50, 0.01, (3, 5, 7))
+    # oracle inputs exactly as the reference fetches them (predict.pyx:130-140)
+    seqs, cps, cms = [], [], []
+    for iv in ivs:
+        padded = genomic_interval(iv.chrom, iv.start - pad - 1, iv.end + pad)
+        c = track.read_func[padded]
+        seqs.append(track.fasta_func.fetch(iv.chrom, padded.start - 3, padded.end + 3))
+        cps.append(c["+"])
+        cms.append(c["-"])
+    in_off = np.concatenate([[0], np.cumsum([len(c) for c in cps])]).astype(np.int64)
+    ref = oracle.score_batch("".join(seqs), np.concatenate(cps), np.concatenate(cms), in_off, batch.out_off, table,
+                             mu=synth.MU_PARAMS, r=synth.R_PARAMS, scales=(3, 5, 7), nthreads=4)
+    assert_score_close(res, ref, (3, 5, 7), oracle, batch.out_off, "track batch")
