@@ -89,7 +89,6 @@ struct fpt_ctx {
     int lut_e = 0, lut_o = 0;
     int *d_status = nullptr;
     int64_t launches = 0;
-    size_t score_smem_prepared = 0;
     bool fast_prepared = false;
     int force_general = 0;  // FPT_B200_GENERAL=1 / FPT_B200_PATH=general: route everything through the general kernel
     int allow_fused = 1;    // FPT_B200_PATH=fast: skip the fused kernel (two-kernel throughput path instead)
@@ -532,10 +531,7 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
         q.tile_list = p.redo_list;
         q.n_list = p.redo_count;
         const size_t gsmem = score_smem_bytes(hw, q.uniform != 0);
-        if (gsmem > ctx->score_smem_prepared) {
-            CU(score_kernel_prepare(gsmem));
-            ctx->score_smem_prepared = gsmem;
-        }
+        CU(score_kernel_prepare(gsmem));  // raises the kernel's process-wide limit when needed
         long long rgrid = ctx->sm_count;
         if (rgrid > p.n_tiles) rgrid = p.n_tiles;
         {
@@ -612,10 +608,7 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
         return FPT_OK;
     }
     size_t smem = score_smem_bytes(hw, p.uniform != 0);
-    if (smem > ctx->score_smem_prepared) {
-        CU(score_kernel_prepare(smem));
-        ctx->score_smem_prepared = smem;
-    }
+    CU(score_kernel_prepare(smem));  // raises the kernel's process-wide limit when needed
     int per_sm = score_kernel_blocks_per_sm(smem);
     if (per_sm < 1) return fail(FPT_ERR_CUDA, "fpt_score: kernel does not fit on an SM (smem %zu)", smem);
     long long grid = (long long)ctx->sm_count * per_sm;

@@ -27,6 +27,7 @@
 // position whose pre-rounding value is within a guard band of a half-integer is recomputed with a
 // bit-faithful replica of the reference's quickselect-ordered summation (trimmed_mean_exact).
 // All operations that feed the integer result use explicitly rounded (non-FMA) intrinsics.
+#include <mutex>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -617,8 +618,19 @@ size_t score_smem_bytes(int hw, bool uniform) {
            sizeof(double) * kModelDoubles + sizeof(RegionTable) + 16;
 }
 
+// The attribute belongs to the kernel (per device, process-wide), not to a context: it is only ever raised, so
+// that a second context asking for less cannot take away what an earlier one relies on.
 cudaError_t score_kernel_prepare(size_t smem) {
-    return cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static std::mutex mu;
+    static size_t prepared[64] = {0};
+    int dev = 0;
+    cudaError_t rc = cudaGetDevice(&dev);
+    if (rc != cudaSuccess) return rc;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && smem <= prepared[dev]) return cudaSuccess;
+    rc = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc == cudaSuccess && dev >= 0 && dev < 64) prepared[dev] = smem;
+    return rc;
 }
 
 int score_kernel_blocks_per_sm(size_t smem) {

@@ -60,6 +60,26 @@ def test_score_unaligned_track_layout(ctx, oracle, table, hw, shw, scales):
     _check(res, ref, scales, oracle, batch.out_off)
 
 
+def test_general_kernel_shared_memory_limit_survives_a_second_context(ctx, table):
+    """The dynamic shared-memory limit is an attribute of the kernel, not of a context: a second context that
+    needs less must not lower it under a context that was given more (regression: 'kernel does not fit on an SM')."""
+    from footprint_tools import _native
+
+    big, _ = synth.make_batch(40, 116, seed=5, table=table)
+    small, _ = synth.make_batch(40, 33, seed=6, table=table)
+    ctx.set_bias(table, 1e-6)
+    ctx.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    first = engine.score_host(ctx, big, 16, 100, 0.01, (3,))
+    other = _native.Context(0)
+    other.set_bias(table, 1e-6)
+    other.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    engine.score_host(other, small, 3, 30, 0.02, (1,))
+    again = engine.score_host(ctx, big, 16, 100, 0.01, (3,))
+    other.close()
+    for k in first:
+        assert np.array_equal(first[k], again[k], equal_nan=True), k
+
+
 @pytest.mark.parametrize("depth", [0.02, 40.0, 400.0])
 def test_score_depth_regimes(ctx, oracle, table, depth):
     """sparse (mostly empty windows), deep and very deep (direct NB evaluation, log-space incbet)."""
