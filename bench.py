@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lut", action="store_true", help="evaluate every NB CDF directly (FP64-bound regime)")
+    ap.add_argument("--unaligned", action="store_true",
+                    help="lay the interval blocks back to back without the mod-4 track/output congruence "
+                         "(what a genome-wide track gives, footprint_tools/ingest.py); default is the aligned layout")
     return ap.parse_args()
 
 
@@ -187,7 +190,7 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
 
-    batch, info = synth.make_batch(args.intervals, HW + SHW, seed=20243 + rank, table=table)
+    batch, info = synth.make_batch(args.intervals, HW + SHW, seed=20243 + rank, table=table, aligned=not args.unaligned)
     total = batch.total
     ctx = _native.default_context(local_rank)
     ctx.set_bias(table, 1e-6)
@@ -309,6 +312,7 @@ def main():
         "config": {"workload": WORKLOAD % args.intervals, "bases_per_step_per_gpu": total,
                    "l2_policy": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % ((in_bytes + out_bytes) / 1e9),
                    "nb_cdf": "direct" if args.no_lut else "device-built (exp,obs) table %dx%d + deferred direct evaluation" % _native.DEFAULT_LUT + "",
+                   "track_layout": "unaligned (genome-wide track style)" if args.unaligned else "aligned blocks (IntervalBatch.from_padded)",
                    "parallelism": "intervals sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (TRAFFIC[dominant] * total / 79778894.0) if dominant in TRAFFIC else None, "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs, burst)" % peak_src,

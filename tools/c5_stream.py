@@ -36,6 +36,7 @@ def make_track(n, cuts_per_base, dev, seed):
     """Packed track of n positions (+ guards) generated on the device in 16 Mb pieces."""
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
+    torch.manual_seed(seed)   # torch.distributions samples from the global generator
     n_track = GUARD + n + GUARD
     seq2 = torch.randint(-2 ** 31, 2 ** 31, ((n_track + 15) // 16,), device=dev, dtype=torch.int64, generator=g).to(torch.int32)
     nmask = torch.zeros((n_track + 31) // 32, device=dev, dtype=torch.int32)
