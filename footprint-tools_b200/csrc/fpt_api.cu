@@ -1094,6 +1094,57 @@ int fpt_window(fpt_ctx *ctx, const double *x, const double *w, int64_t n, const 
     return FPT_OK;
 }
 
+int64_t fpt_segment_batch(fpt_ctx *ctx, const double *stats, const int64_t *out_off, int64_t n_iv, int64_t total,
+                          double threshold, int w, int decreasing, int64_t *seg_iv, int64_t *seg_start, int64_t *seg_end,
+                          double *seg_score, int64_t cap, int mem) {
+    if (!ctx) return fail(FPT_ERR_ARG, "fpt_segment_batch: ctx is NULL");
+    if (n_iv < 0 || total < 0 || cap < 0 || w < 1) return fail(FPT_ERR_ARG, "fpt_segment_batch: bad argument");
+    if (n_iv == 0) return 0;
+    if (!out_off || (total > 0 && !stats)) return fail(FPT_ERR_ARG, "fpt_segment_batch: NULL array");
+    if (cap > 0 && (!seg_iv || !seg_start || !seg_end || !seg_score))
+        return fail(FPT_ERR_ARG, "fpt_segment_batch: NULL output array");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const double *dx = stats;
+    const long long *doff = reinterpret_cast<const long long *>(out_off);
+    if (mem != FPT_MEM_DEVICE) {
+        CU(ctx->h_in[0].need((size_t)total * 8 + 8)); CU(ctx->h_in[1].need((size_t)(n_iv + 1) * 8));
+        CU(cudaMemcpyAsync(ctx->h_in[0].p, stats, (size_t)total * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->h_in[1].p, out_off, (size_t)(n_iv + 1) * 8, cudaMemcpyHostToDevice, st));
+        dx = ctx->h_in[0].as<double>();
+        doff = ctx->h_in[1].as<long long>();
+    }
+    // [counts(n_iv) | first(n_iv + 1)]
+    CU(ctx->plan.need((size_t)(2 * n_iv + 1) * sizeof(long long)));
+    long long *counts = ctx->plan.as<long long>(), *first = counts + n_iv;
+    CU(launch_segment_count(st, dx, doff, n_iv, threshold, w, decreasing, counts, first, ctx->sm_count));
+    ctx->launches += 2;
+    long long found = 0;
+    CU(cudaMemcpyAsync(&found, first + n_iv, sizeof found, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const long long nw = found < cap ? found : cap;
+    if (nw <= 0) return (int64_t)found;
+    if (mem == FPT_MEM_DEVICE) {
+        CU(launch_segment_write(st, dx, doff, n_iv, threshold, w, decreasing, first, nw,
+                                reinterpret_cast<long long *>(seg_iv), reinterpret_cast<long long *>(seg_start),
+                                reinterpret_cast<long long *>(seg_end), seg_score, ctx->sm_count));
+        ctx->launches++;
+        return (int64_t)found;
+    }
+    const size_t ob = (size_t)nw * 8;
+    for (int i = 0; i < 4; ++i) CU(ctx->h_out[i].need(ob));
+    CU(launch_segment_write(st, dx, doff, n_iv, threshold, w, decreasing, first, nw, ctx->h_out[0].as<long long>(),
+                            ctx->h_out[1].as<long long>(), ctx->h_out[2].as<long long>(), ctx->h_out[3].as<double>(),
+                            ctx->sm_count));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(seg_iv, ctx->h_out[0].p, ob, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(seg_start, ctx->h_out[1].p, ob, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(seg_end, ctx->h_out[2].p, ob, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(seg_score, ctx->h_out[3].p, ob, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return (int64_t)found;
+}
+
 int fpt_hist2d(fpt_ctx *ctx, const double *exp, const double *obs, int64_t n, int64_t *hist, int d0, int d1,
                int mem) {
     if (!ctx) return fail(FPT_ERR_ARG, "fpt_hist2d: ctx is NULL");

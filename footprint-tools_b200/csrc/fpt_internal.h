@@ -145,6 +145,15 @@ cudaError_t launch_kmer_probs(cudaStream_t st, const uint32_t *seq2, const uint3
 cudaError_t launch_special(cudaStream_t st, int fn, const double *a, const double *b, const double *x, long long n,
                            double *out);
 
+// fpt_segment.cu: utils.segment + np.min score for a batch (count pass + scan, then the write pass)
+cudaError_t launch_segment_count(cudaStream_t st, const double *x, const long long *out_off, long long n_iv,
+                                 double threshold, int w, int decreasing, long long *counts, long long *first,
+                                 int sm_count);
+cudaError_t launch_segment_write(cudaStream_t st, const double *x, const long long *out_off, long long n_iv,
+                                 double threshold, int w, int decreasing, const long long *first, long long cap,
+                                 long long *seg_iv, long long *seg_start, long long *seg_end, double *seg_score,
+                                 int sm_count);
+
 // records the message fpt_last_error() returns (thread-local, fpt_api.cu) and hands `code` back
 int set_error(int code, const char *msg);
 

@@ -99,6 +99,8 @@ SIGNATURES = {
     "fpt_segment": (C.c_int64, [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "fpt_format_segments": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_int,
                                         C.c_int, C.c_char_p, C.c_int, C.c_char, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fpt_segment_batch": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "fpt_special": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
@@ -274,6 +276,40 @@ class Context(object):
         _check(lib().fpt_detect_fdr(self._h, _ptr(exp), _ptr(winp), _ptr(out_off), int(n_iv), int(total), int(max_len),
                                     int(hw), int(times), int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out), mem))
         return out
+
+    def segment_batch(self, stats, out_off, threshold, w=3, decreasing=False, mem=MEM_HOST, n_iv=None, total=None,
+                      cap=None):
+        """utils.segment + np.min score for every interval of a batch on the device (fpt_segment_batch).
+        Returns (seg_iv, seg_start, seg_end, seg_score): numpy arrays for MEM_HOST, torch tensors on the stats'
+        device for MEM_DEVICE (stats / out_off device tensors; n_iv and total must be given)."""
+        if mem == MEM_HOST:
+            stats = np.ascontiguousarray(stats, dtype=np.float64)
+            out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+            n_iv, total = len(out_off) - 1, int(out_off[-1]) if len(out_off) else 0
+
+            def alloc(n):
+                return [np.empty(n, dtype=np.int64) for _ in range(3)] + [np.empty(n, dtype=np.float64)]
+        else:
+            import torch
+
+            def alloc(n):
+                return [torch.empty(n, dtype=torch.int64, device=stats.device) for _ in range(3)] + \
+                       [torch.empty(n, dtype=torch.float64, device=stats.device)]
+        if n_iv is None or n_iv <= 0:
+            return tuple(alloc(0))
+        cap = max(int(cap) if cap is not None else max(1024, total // 64), 1)
+        while True:
+            bufs = alloc(cap)
+            found = lib().fpt_segment_batch(self._h, _ptr(stats), _ptr(out_off), int(n_iv), int(total), float(threshold),
+                                            int(w), int(bool(decreasing)), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]),
+                                            _ptr(bufs[3]), cap, mem)
+            if found < 0:
+                _check(int(found))
+            if found <= cap:
+                if mem != MEM_HOST:
+                    self.sync()   # the write pass is queued on the context's stream; the caller may read on another
+                return tuple(b[:found] for b in bufs)
+            cap = int(found)
 
     def empirical_fdr(self, pvals_null, pvals):
         """fdr.emperical_fdr on the device (at most 4096 observed values)."""

@@ -225,6 +225,51 @@ def detect_host(ctx, batch, hw=5, shw=50, clip=0.01, win_hw=3, fdr_shuffle_n=50,
     return {"exp": res["exp"], "obs": res["obs"], "neglog_pval": nlp, "neglog_winpval": nlw, "efdr": efdr}
 
 
+def segments_host(ctx, stats, out_off, threshold, w=3, decreasing=True):
+    """utils.segment + np.min score of every interval of a batch (what write_segments_to_output computes per interval,
+    cli/utils.py:203-209) in one device pass; returns (seg_iv, seg_start, seg_end, seg_score) numpy arrays ordered by
+    (interval, start); start / end are relative to the interval like the reference's (s, e)."""
+    return ctx.segment_batch(stats, out_off, threshold, w, decreasing)
+
+
+def detect_footprints_device(ctx, dbatch, thresholds, hw=5, shw=50, clip=0.01, win_hw=3, fdr_shuffle_n=50, seed=1,
+                             max_len=None, bufs=None):
+    """`ftd detect` down to its footprints (cli/detect.py:120-135, 403-408) with every per-base column staying on the
+    device: scoring -> windowed p-values -> empirical FDR -> utils.segment per FDR threshold. Only the footprint
+    records cross PCIe (32 bytes per footprint instead of 40 bytes per base). Returns ({threshold: (seg_iv,
+    seg_start, seg_end, seg_score)} as numpy arrays, bufs) where bufs holds the device columns (exp, obs, pval,
+    winp, efdr) for callers that also want the bedGraph."""
+    import torch
+
+    dev = dbatch.out_off.device
+    tot = dbatch.total
+    if bufs is None:
+        bufs = {k: torch.empty(tot, dtype=torch.float64, device=dev) for k in ("exp", "obs", "pval", "efdr")}
+        bufs["winp"] = torch.empty((1, tot), dtype=torch.float64, device=dev)
+    torch.cuda.current_stream(dev).synchronize()   # the buffers are used on the context's stream from here on
+    score_device(ctx, dbatch, {k: bufs[k] for k in ("exp", "obs", "pval", "winp")}, hw, shw, clip, (win_hw,))
+    if max_len is None:
+        max_len = int((dbatch.out_off[1:] - dbatch.out_off[:-1]).max().item()) if dbatch.n_iv else 0
+    ctx.detect_fdr(bufs["exp"], bufs["winp"][0], dbatch.out_off, win_hw, fdr_shuffle_n, seed, out=bufs["efdr"],
+                   mem=MEM_DEVICE, max_len=max_len, n_iv=dbatch.n_iv, total=tot)
+    out = {}
+    for t in thresholds:
+        rec = ctx.segment_batch(bufs["efdr"], dbatch.out_off, t, 3, True, mem=MEM_DEVICE, n_iv=dbatch.n_iv, total=tot)
+        out[t] = tuple(r.cpu().numpy() for r in rec)
+    return out, bufs
+
+
+def write_footprint_records(chroms, starts, records, file, name=".", delim="\t", fmt_string="0.4f"):
+    """The BED rows write_segments_to_output prints (cli/utils.py:205-209) from segment records: chroms / starts are
+    per interval, records = (seg_iv, seg_start, seg_end, seg_score)."""
+    seg_iv, seg_start, seg_end, seg_score = records
+    fmt = "{0:" + fmt_string + "}"
+    rows = []
+    for k, s, e, v in zip(seg_iv.tolist(), seg_start.tolist(), seg_end.tolist(), seg_score.tolist()):
+        rows.append(f"{chroms[k]}{delim}{starts[k] + s}{delim}{starts[k] + e}{delim}{name}{delim}" + fmt.format(v) + "\n")
+    file.write("".join(rows))
+
+
 def write_detect_outputs(cols, chroms, starts, out_off, bedgraph_file, bed_files=None):
     """What cli/detect.py:398-408 writes for every interval, for a whole batch: the five stats columns to the bedGraph
     handle and, per FDR threshold, the footprint segments of the efdr column (decreasing, w = 3) to its BED handle."""

@@ -266,6 +266,17 @@ int64_t fpt_format_segments(const char *const *chroms, const int64_t *starts, co
                             const double *stats, double threshold, int w, int decreasing, const char *name, int precision,
                             char delim, char *buf, int64_t cap, int64_t *n_done);
 
+/* The footprint step of `ftd detect` (cli/detect.py:403-408) for a whole batch ON THE DEVICE: per interval k,
+ * utils.segment(stats[out_off[k]:out_off[k+1]], threshold, w, decreasing) (stats/utils.pyx:15-50) and, per segment,
+ * np.min(stats[s:e]) (write_segments_to_output, cli/utils.py:203-209). Record q: seg_iv[q] = k, seg_start[q] = s,
+ * seg_end[q] = e (relative to the interval, as the reference adds them to interval.start), seg_score[q]; records are
+ * ordered by (interval, start). Returns the number of segments FOUND (>= 0; the first min(found, cap) are written —
+ * call again with larger arrays when found > cap) or an FPT_ERR_* code. With FPT_MEM_DEVICE every array is a device
+ * array (the stats column never leaves the GPU); the call synchronises the context's stream to read the count. */
+int64_t fpt_segment_batch(fpt_ctx *ctx, const double *stats, const int64_t *out_off, int64_t n_iv, int64_t total,
+                          double threshold, int w, int decreasing, int64_t *seg_iv, int64_t *seg_start, int64_t *seg_end,
+                          double *seg_score, int64_t cap, int mem);
+
 /* Scalar probes of the device special functions (used by the parity tests; HOST arrays).
  * fn: 0 incbet(a,b,x) 1 gamma(a) 2 lgam(a) 3 ndtr(a) 4 ndtri(a) 5 igamc(a,b) 6 chdtrc(a,b) 7 log1p(a)
  *     8 nbinom.logpmf(k=a,p=b,r=x) 9 nbinom.pmf 10 nbinom.cdf (stats/distributions/nbinom.pyx:82-138) */
