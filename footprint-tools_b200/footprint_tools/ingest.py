@@ -27,7 +27,7 @@ import os
 import numpy as np
 
 from . import _native
-from .engine import IntervalBatch, counts_to_u32
+from .engine import DeviceBatch, IntervalBatch, counts_to_u32
 
 MAGIC = b"FPTTRK01"
 GUARD = 128   # N positions (and zero cuts) around every chromosome: >= max padding (116) + k-mer flank (3) + 1
@@ -192,6 +192,19 @@ class GenomeTrack(object):
         return IntervalBatch(self.seq2, self.nmask, self.cuts_plus, self.cuts_minus, self.n_track, iv_start, out_off,
                              np.array([0, self.n_track], dtype=np.int64), block_len=np.array([self.n_track]))
 
+    def to_device(self, device):
+        """Upload the four track arrays once (torch tensors; uint32 carried as int32). The returned DeviceTrack hands
+        out DeviceBatches that reference them: per batch only iv_start / out_off (16 bytes per interval) are copied."""
+        import torch
+
+        def dev(a):
+            a = np.ascontiguousarray(a)
+            if isinstance(a, np.memmap) or not a.flags.writeable:
+                a = np.array(a)          # torch.from_numpy wants a writable, in-memory array
+            return torch.from_numpy(a.view(np.int32)).to(device)
+
+        return DeviceTrack(self, dev(self.seq2), dev(self.nmask), dev(self.cuts_plus), dev(self.cuts_minus), device)
+
     # ---- at-rest format ------------------------------------------------------------------------------
     def save(self, path):
         arrays = [("seq2", self.seq2), ("nmask", self.nmask), ("cuts_plus", self.cuts_plus), ("cuts_minus", self.cuts_minus)]
@@ -240,3 +253,20 @@ class GenomeTrack(object):
             raise ValueError("%s: array sizes do not match the track length" % path)
         return cls(header["names"], header["lengths"], header["chrom_off"], n_track, arrs["seq2"], arrs["nmask"],
                    arrs["cuts_plus"], arrs["cuts_minus"])
+
+
+class DeviceTrack(object):
+    """A GenomeTrack resident in HBM (GenomeTrack.to_device)."""
+
+    def __init__(self, track, seq2, nmask, cuts_plus, cuts_minus, device):
+        self.track, self.device = track, device
+        self.seq2, self.nmask, self.cuts_plus, self.cuts_minus = seq2, nmask, cuts_plus, cuts_minus
+
+    def batch(self, intervals, pad, per_strand=False):
+        """DeviceBatch of `intervals` over the resident track (same geometry as GenomeTrack.batch)."""
+        import torch
+
+        hb = self.track.batch(intervals, pad, per_strand=per_strand)
+        return DeviceBatch(self.seq2, self.nmask, self.cuts_plus, self.cuts_minus, hb.n_track,
+                           torch.from_numpy(hb.iv_start).to(self.device), torch.from_numpy(hb.out_off).to(self.device),
+                           hb.n_iv, hb.total)

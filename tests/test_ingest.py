@@ -260,6 +260,29 @@ def test_batch_points_into_the_shared_track(small_track):
         track.batch(ivs, pad=200)
 
 
+def test_rank_shards_of_a_track_batch_share_the_track(small_track):
+    """SURVEY.md §8e on a genome-wide track: every rank scores its own interval list over the same resident track."""
+    from footprint_tools import engine
+
+    _, seqs, track = small_track
+    rng = np.random.default_rng(3)
+    ivs = []
+    for _ in range(40):
+        a = int(rng.integers(0, 4000))
+        ivs.append(("chrA", a, a + int(rng.integers(1, 900))))
+    full = track.batch(ivs, pad=55)
+    lens = np.diff(full.out_off)
+    shards = engine.shard_intervals(lens, 3)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(40))
+    loads = [int(lens[s].sum()) for s in shards]
+    assert max(loads) - min(loads) <= int(lens.max())
+    for s in shards:
+        b = full.select(s)
+        assert b.seq2 is track.seq2 and b.cuts_minus is track.cuts_minus and b.n_track == track.n_track
+        assert np.array_equal(b.iv_start, full.iv_start[s])
+        assert np.array_equal(np.diff(b.out_off), lens[s]) and b.out_off[0] == 0
+
+
 def _track_with_cuts(n_chrom=3, seed=4):
     rng = np.random.default_rng(seed)
     chroms = [("c%d" % i, random_sequence(rng, int(rng.integers(4000, 9000)), n_frac=0.002)) for i in range(n_chrom)]
@@ -308,6 +331,32 @@ def test_gpu_track_batch_equals_per_interval_packing(table, geometry):
         for s, strand in enumerate("+-"):
             assert np.array_equal(ps["exp"][s, a:b], exp[strand])
             assert np.array_equal(ps["win"][s, a:b], win[strand], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_gpu_resident_track_equals_host_batches(table, tmp_path):
+    """file -> memory map -> HBM once -> many device batches: the same bytes as the host-mode zero-copy batch."""
+    import torch
+
+    from footprint_tools import _native, engine
+
+    track, ivs = _track_with_cuts(seed=12)
+    path = str(tmp_path / "t.fptrk")
+    track.save(path)
+    dtrack = GenomeTrack.open(path).to_device("cuda:0")
+    ctx = _native.default_context(0)
+    ctx.set_bias(table, 1e-6)
+    ctx.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    for part in (ivs[:10], ivs[10:], ivs[::3]):
+        want = engine.score_host(ctx, track.batch(part, 55), 5, 50, 0.01, (3, 5, 7))
+        db = dtrack.batch(part, 55)
+        bufs = {k: torch.empty(db.total, dtype=torch.float64, device="cuda:0") for k in ("exp", "obs", "pval")}
+        bufs["winp"] = torch.empty((3, db.total), dtype=torch.float64, device="cuda:0")
+        torch.cuda.synchronize()
+        engine.score_device(ctx, db, bufs, 5, 50, 0.01, (3, 5, 7))
+        ctx.sync()
+        for k in want:
+            assert np.array_equal(bufs[k].cpu().numpy(), want[k], equal_nan=True), k
 
 
 class _TableModel(object):
