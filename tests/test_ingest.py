@@ -243,6 +243,31 @@ def test_file_round_trip_and_in_place_accumulation(tmp_path, small_track):
         GenomeTrack.open(path)
 
 
+def test_sparse_cut_encoding_round_trip(tmp_path, small_track):
+    rng, seqs, track = small_track
+    cp = rng.poisson(0.05, 5000)
+    cm = rng.poisson(0.05, 5000)
+    cm[4999] = 4000000000      # full uint32 range survives
+    track.cuts_plus[:] = 0
+    track.cuts_minus[:] = 0
+    track.set_cuts("chrA", cp, cm)
+    dense, sparse = str(tmp_path / "d.fptrk"), str(tmp_path / "s.fptrk")
+    track.save(dense)
+    track.save(sparse, sparse=True)
+    import os
+
+    assert os.path.getsize(sparse) < os.path.getsize(dense) / 2
+    back = GenomeTrack.open(sparse)
+    for name in ("seq2", "nmask", "cuts_plus", "cuts_minus"):
+        assert np.array_equal(getattr(back, name), getattr(track, name)), name
+    assert back.cuts_plus.dtype == np.uint32 and back.cuts_plus.flags.writeable
+    assert back.add_alignments("chrB", [5], [40], [0], [60]) == 1       # expanded arrays accept more alignments
+    empty = GenomeTrack.from_sequences([("z", "ACGT" * 20)])
+    empty.save(sparse, sparse=True)
+    assert GenomeTrack.open(sparse).cuts_plus.sum() == 0
+    track.set_cuts("chrA", np.zeros(5000), np.zeros(5000))
+
+
 def test_batch_points_into_the_shared_track(small_track):
     _, seqs, track = small_track
     ivs = [genomic_interval("chrB", 200, 500), ("chrA", 1000, 1001), genomic_interval("chrA", 60, 460), ("chrC", 0, 97)]
