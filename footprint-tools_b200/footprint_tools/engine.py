@@ -5,8 +5,6 @@ intervals are packed into one *track* (2-bit sequence + N mask + uint32 cut coun
 include/fpt_b200.h) and scored by one fused kernel launch. The same call works on host buffers
 (numpy; copies inside) or on device-resident buffers (torch tensors; no copies).
 """
-import ctypes as C
-
 import numpy as np
 
 from . import _native
@@ -124,6 +122,21 @@ class IntervalBatch(object):
         np.cumsum(lens, out=out_off[1:])
         return IntervalBatch(self.seq2, self.nmask, self.cuts_plus, self.cuts_minus, self.n_track, self.iv_start[idx],
                              out_off, self.block_off, block_len=self.block_len)
+
+    def compact(self, pad):
+        """The same intervals over only the part of the track they read: [min start - pad - 4, max end + pad + 4),
+        widened to 32-position boundaries (whole sequence / N-mask words). Views, no copies. With intervals sharded
+        contiguously in track order (`shard_contiguous`; a long range cut into pieces with read-only halos, SURVEY.md
+        §8e) every rank uploads its piece of the track instead of all of it."""
+        if self.n_iv == 0:
+            return self
+        lens = np.diff(self.out_off)
+        halo = int(pad) + 4   # padding + the minus strand's one-position shift + the 3-base k-mer flank
+        t0 = max(0, int((self.iv_start.min() - halo) // 32 * 32))
+        t1 = min(self.n_track, int(-(-(int((self.iv_start + lens).max()) + halo) // 32) * 32))
+        return IntervalBatch(self.seq2[t0 // 16:(t1 + 15) // 16], self.nmask[t0 // 32:(t1 + 31) // 32],
+                             self.cuts_plus[t0:t1], self.cuts_minus[t0:t1], t1 - t0, self.iv_start - t0, self.out_off,
+                             np.array([0, t1 - t0], dtype=np.int64), block_len=np.array([t1 - t0]))
 
     def to_device(self, device):
         """Device-resident copy (torch tensors; uint32 payloads carried as int32)."""
@@ -295,6 +308,24 @@ def shard_intervals(lengths, world_size):
         owner[i] = r
         load[r] += lengths[i]
     return [np.nonzero(owner == r)[0] for r in range(world_size)]
+
+
+def shard_contiguous(lengths, world_size):
+    """Contiguous partition of an interval list (kept in order) into `world_size` runs of nearly equal total length:
+    rank r gets indices [cut[r], cut[r+1]). For intervals in track order — a contiguous range tiled into intervals
+    (config C5), or a genome-wide track — each rank's intervals then touch one contiguous piece of the track, which
+    `IntervalBatch.select(idx).compact(pad)` cuts out with its read-only halo. Returns a list of index arrays."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(lengths)])
+    cuts = [0]
+    for r in range(1, world_size):
+        want = csum[-1] * r / world_size
+        k = int(np.searchsorted(csum, want, side="left"))
+        if k > 0 and abs(csum[k - 1] - want) <= abs(csum[min(k, len(csum) - 1)] - want):
+            k -= 1
+        cuts.append(min(max(k, cuts[-1]), len(lengths)))
+    cuts.append(len(lengths))
+    return [np.arange(cuts[r], cuts[r + 1], dtype=np.int64) for r in range(world_size)]
 
 
 def allreduce_histogram(hist, group=None):

@@ -421,3 +421,78 @@ def test_gpu_track_batch_matches_the_oracle(table, oracle):
     ref = oracle.score_batch("".join(seqs), np.concatenate(cps), np.concatenate(cms), in_off, batch.out_off, table,
                              mu=synth.MU_PARAMS, r=synth.R_PARAMS, scales=(3, 5, 7), nthreads=4)
     assert_score_close(res, ref, (3, 5, 7), oracle, batch.out_off, "track batch")
+
+
+def _window(track_like, t, lo, hi):
+    """Bases and cut counts of track positions [lo, hi) of an IntervalBatch-like object (host arrays)."""
+    from footprint_tools import _native
+
+    out = np.empty(hi - lo, dtype=np.uint8)
+    _native._check(_native.lib().fpt_unpack_sequence(_native._ptr(np.ascontiguousarray(track_like.seq2)),
+                                                     _native._ptr(np.ascontiguousarray(track_like.nmask)), lo, hi - lo,
+                                                     _native._ptr(out)))
+    return out.tobytes(), np.asarray(track_like.cuts_plus[lo:hi]), np.asarray(track_like.cuts_minus[lo:hi])
+
+
+def test_contiguous_shards_compact_to_track_pieces_with_halo():
+    """Config C5's multi-GPU layout (SURVEY.md §8e): a long range tiled into intervals, cut into contiguous pieces;
+    every piece carries exactly the halo its intervals read, so scoring a piece equals scoring the whole."""
+    from footprint_tools import engine
+
+    rng = np.random.default_rng(17)
+    n = 200000
+    track = GenomeTrack.from_sequences([("c", random_sequence(rng, n, n_frac=0.001, lower_frac=0.0))])
+    track.set_cuts("c", rng.poisson(0.3, n), rng.poisson(0.3, n))
+    step, pad = 5000, 55
+    ivs = [("c", a, min(n, a + step)) for a in range(0, n, step)]
+    full = track.batch(ivs, pad)
+    lens = np.diff(full.out_off)
+    for world in (2, 3, 8):
+        shards = engine.shard_contiguous(lens, world)
+        assert np.array_equal(np.concatenate(shards), np.arange(len(ivs)))
+        loads = [int(lens[s].sum()) for s in shards]
+        assert max(loads) - min(loads) <= step
+        for r, s in enumerate(shards):
+            piece = full.select(s).compact(pad)
+            assert piece.n_track <= loads[r] + 2 * (pad + 4) + 64   # a piece with its halo, not the track
+            assert piece.n_track % 32 == 0 or piece.n_track == full.n_track
+            assert piece.cuts_plus.base is not None            # a view of the shared arrays, no copy
+            halo = pad + 4
+            for k in (s[[0, len(s) // 2, -1]] if len(s) > 2 else s):
+                j = int(np.nonzero(s == k)[0][0])
+                a0, a1 = int(full.iv_start[k]) - halo, int(full.iv_start[k] + lens[k]) + halo
+                b0, b1 = int(piece.iv_start[j]) - halo, int(piece.iv_start[j] + lens[k]) + halo
+                assert b0 >= 0 and b1 <= piece.n_track
+                wa, wb = _window(full, None, a0, a1), _window(piece, None, b0, b1)
+                assert wa[0] == wb[0] and np.array_equal(wa[1], wb[1]) and np.array_equal(wa[2], wb[2])
+    # degenerate cases
+    assert [len(s) for s in engine.shard_contiguous(np.array([5, 5]), 4)].count(0) >= 2
+    assert sum(len(s) for s in engine.shard_contiguous(np.zeros(0, dtype=np.int64), 3)) == 0
+    empty = track.batch([], pad)
+    assert empty.compact(pad).n_iv == 0
+
+
+@pytest.mark.gpu
+def test_gpu_compacted_pieces_score_like_the_whole(table):
+    from footprint_tools import _native, engine
+
+    rng = np.random.default_rng(23)
+    n = 120000
+    track = GenomeTrack.from_sequences([("c", random_sequence(rng, n, n_frac=0.001, lower_frac=0.0))])
+    track.set_cuts("c", rng.poisson(0.8, n), rng.poisson(0.8, n))
+    ivs = [("c", a, min(n, a + 4000)) for a in range(0, n, 4000)]
+    full = track.batch(ivs, 55)
+    ctx = _native.default_context(0)
+    ctx.set_bias(table, 1e-6)
+    ctx.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+    want = engine.score_host(ctx, full, 5, 50, 0.01, (3, 5, 7))
+    for world in (2, 5):
+        got = {k: [] for k in want}
+        for s in engine.shard_contiguous(np.diff(full.out_off), world):
+            piece = full.select(s).compact(55)
+            assert piece.n_track < full.n_track
+            res = engine.score_host(ctx, piece, 5, 50, 0.01, (3, 5, 7))
+            for k in want:
+                got[k].append(res[k])
+        for k in want:
+            assert np.array_equal(np.concatenate(got[k], axis=-1), want[k], equal_nan=True), k
