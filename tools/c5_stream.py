@@ -7,6 +7,12 @@ device output sets; with --d2h every finished set is copied to pinned host memor
 tile is scored (double-buffered), which is the sustained end-to-end rate of a genome-scale run.
 
     python tools/c5_stream.py [--mb 256] [--tile-mb 64] [--interval-mb 1] [--cuts-per-base 0.25] [--steps 2] [--no-lut] [--d2h]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/c5_stream.py --mb 2000
+
+Under torchrun the range is cut into N contiguous pieces (strong scaling: --mb is the whole job), one per
+GPU, each resident with its own guard halo; no data-path collective — the ranks only meet at the barriers around the timed
+region, the reported time is the maximum over ranks. Each rank generates its own piece (synthetic data: the halos of
+neighbouring pieces are not the same bases, which changes nothing about the work done).
 
 The default is a 256 Mb range (the full configuration is --mb 2000: 17 GB of track + 6 GB of output sets). Checks that
 do not depend on the size (no oracle here): (1) the observed counts sum to the cut counts of the scored range exactly,
@@ -80,16 +86,24 @@ def main():
     ap.add_argument("--no-lut", action="store_true")
     ap.add_argument("--d2h", action="store_true")
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    n = int(args.mb * 1e6) // 32 * 32
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    n_job = int(args.mb * 1e6) // 32 * 32
+    n = n_job // world // 32 * 32          # this rank's contiguous piece
     tile = min(n, int(args.tile_mb * 1e6) // 32 * 32)
     interval = min(tile, int(args.interval_mb * 1e6))
-    track = make_track(n, args.cuts_per_base, dev, 20245)
+    track = make_track(n, args.cuts_per_base, dev, 20245 + rank)
     cp, cm = track[2], track[3]
     total_cuts = int(cp.sum(dtype=torch.int64) + cm.sum(dtype=torch.int64))
 
-    ctx = _native.default_context(0)
+    ctx = _native.default_context(local_rank)
     ctx.set_bias(synth.vierstra_table(), 1e-6)
     ctx.set_dm(synth.MU_PARAMS, synth.R_PARAMS, lut=(0, 0) if args.no_lut else _native.DEFAULT_LUT)
     stream = torch.cuda.Stream(device=dev)
@@ -181,6 +195,9 @@ def main():
     # timed passes
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
     n0 = ctx.launches
     e0.record(stream)
     for _ in range(args.steps):
@@ -192,14 +209,26 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / args.steps
+    ok = all(checks.values())
+    if dist is not None:
+        t = torch.tensor([ms, 0.0 if ok else 1.0, float(total_cuts)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, bad, total_cuts = float(tmax[0].item()), float(tmax[1].item()), int(t[2].item())
+        checks["all_ranks"] = bad == 0.0
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    n = n * world
     rate = n / (ms * 1e-3)
-    line = {"config": "C5 high-depth contiguous tiling", "range_mb": n / 1e6, "tile_mb": tile / 1e6,
+    line = {"config": "C5 high-depth contiguous tiling", "n_gpus": world, "scaling": "strong", "range_mb": n / 1e6, "tile_mb": tile / 1e6,
             "interval_mb": interval / 1e6, "cuts": total_cuts, "cuts_per_base": total_cuts / n,
             "nb_cdf": "direct" if args.no_lut else "table %dx%d + deferred direct" % _native.DEFAULT_LUT,
             "d2h_inside_timed_region": bool(args.d2h), "ms_per_pass": ms, "scored_bases_per_s": rate,
             "algorithmic_gbs": rate * BYTES_PER_BASE / 1e9, "gpu_launches_per_pass": (ctx.launches - n0) // args.steps,
-            "resident_track_gb": (cp.numel() * 8 + track[0].numel() * 4 + track[1].numel() * 4) / 1e9,
-            "output_sets_gb": 2 * tile * 8 * (3 + len(SCALES)) / 1e9, "checks": checks}
+            "resident_track_gb_per_gpu": (cp.numel() * 8 + track[0].numel() * 4 + track[1].numel() * 4) / 1e9,
+            "output_sets_gb_per_gpu": 2 * tile * 8 * (3 + len(SCALES)) / 1e9, "checks": checks}
     print(json.dumps(line))
     if not all(checks.values()):
         raise SystemExit("c5_stream: a property check failed")
