@@ -712,7 +712,15 @@ static int score_host_pipelined(fpt_ctx *ctx, const fpt_score_args *a, int n_chu
     std::atomic<int> enqueued{0};
     std::atomic<bool> aborted{false};
     std::vector<std::thread> workers;
-    const int n_workers = narrow ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 0;
+    // host threads that widen the uint32 counts: half the cores, shared among the ranks of this node (torchrun exports
+    // LOCAL_WORLD_SIZE), at most 8, at least 1 — eight ranks must not put 64 spinning threads on a small host
+    unsigned ranks_here = 1;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) {
+        const int v = atoi(lw);
+        if (v > 1) ranks_here = (unsigned)v;
+    }
+    const int n_workers =
+        narrow ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / (2 * ranks_here))) : 0;
     if (narrow) {
         double *hosts[2] = {a->exp_out, a->obs_out};
         uint32_t *pin = ctx->pin_counts;
