@@ -496,3 +496,37 @@ def test_gpu_compacted_pieces_score_like_the_whole(table):
                 got[k].append(res[k])
         for k in want:
             assert np.array_equal(np.concatenate(got[k], axis=-1), want[k], equal_nan=True), k
+
+
+def test_native_ingest_entry_points_report_errors():
+    """C-ABI behaviour of the host-side ingest functions: status codes and fpt_last_error messages, no GPU needed."""
+    import ctypes as C
+
+    from footprint_tools import _native
+
+    lib = _native.lib()
+    one = np.ones(4, dtype=np.uint32)
+    assert lib.fpt_unpack_sequence(None, None, 0, 4, None) == -1
+    assert b"fpt_unpack_sequence" in lib.fpt_last_error()
+    assert lib.fpt_unpack_sequence(_native._ptr(one), _native._ptr(one), -1, 4, _native._ptr(one)) == -1
+    assert lib.fpt_unpack_sequence(None, None, 0, 0, None) == 0
+    # a count that would wrap around uint32 is an error, not a silent overflow
+    cp = np.array([0xFFFFFFFF, 0], dtype=np.uint32)
+    cm = np.zeros(2, dtype=np.uint32)
+    rs, re_, fl, mq = (np.array([0], dtype=np.int64), np.array([30], dtype=np.int64), np.array([0], dtype=np.uint16),
+                       np.array([60], dtype=np.uint8))
+    rc = lib.fpt_cuts_from_alignments(_native._ptr(rs), _native._ptr(re_), _native._ptr(fl), _native._ptr(mq), 1, 1, 0, 1, 0, -1,
+                                      0, 2, _native._ptr(cp), _native._ptr(cm))
+    assert rc == -1 and b"overflows" in lib.fpt_last_error()
+    assert cp[0] == 0xFFFFFFFF
+    # unmapped reads and reads below the MAPQ floor are skipped; the reverse strand counts at reference_end + offset
+    rs = np.array([0, 0, 0], dtype=np.int64)
+    re_ = np.array([2, 2, 2], dtype=np.int64)
+    fl = np.array([0x4, 0x10, 0x10], dtype=np.uint16)
+    mq = np.array([60, 0, 60], dtype=np.uint8)
+    cp[:] = 0
+    rc = lib.fpt_cuts_from_alignments(_native._ptr(rs), _native._ptr(re_), _native._ptr(fl), _native._ptr(mq), 3, 1, 0, 1, 0, -1,
+                                      0, 2, _native._ptr(cp), _native._ptr(cm))
+    assert rc == 1 and cm.tolist() == [0, 1] and cp.tolist() == [0, 0]
+    assert lib.fpt_cuts_from_alignments(None, None, None, None, -1, 1, 0, 1, 0, -1, 0, 2, _native._ptr(cp), _native._ptr(cm)) == -1
+    assert isinstance(C.c_int64(rc).value, int)
