@@ -192,5 +192,31 @@ int64_t fpt_format_segments(const char *const *chroms, const int64_t *starts, co
     return (int64_t)(p - buf);
 }
 
+int64_t fpt_format_records(const char *const *chroms, const int64_t *starts, int64_t n_iv, const int64_t *seg_iv,
+                           const int64_t *seg_start, const int64_t *seg_end, const double *seg_score, int64_t n_seg,
+                           const char *name, int precision, char delim, char *buf, int64_t cap, int64_t *n_done) {
+    if (n_done) *n_done = 0;
+    if (n_seg < 0 || n_iv < 0 || precision < 0 || precision > 9 || cap < 0 || !name || (cap > 0 && !buf) ||
+        (n_seg > 0 && (!chroms || !starts || !seg_iv || !seg_start || !seg_end || !seg_score)))
+        return FPT_ERR_ARG;
+    const size_t nl = strlen(name);
+    char *p = buf, *const end = buf + cap;
+    int64_t q = 0;
+    for (; q < n_seg; ++q) {
+        const int64_t k = seg_iv[q];
+        if (k < 0 || k >= n_iv) return FPT_ERR_ARG;
+        const size_t cl = strlen(chroms[k]);
+        if ((size_t)(end - p) < cl + nl + 48 + 342) break;  // the caller flushes and calls again from record q
+        memcpy(p, chroms[k], cl); p += cl;
+        *p++ = delim; p = put_i64(p, starts[k] + seg_start[q]);
+        *p++ = delim; p = put_i64(p, starts[k] + seg_end[q]);
+        *p++ = delim; memcpy(p, name, nl); p += nl;
+        *p++ = delim; p = put_fixed(p, seg_score[q], precision);
+        *p++ = '\n';
+    }
+    if (n_done) *n_done = q;
+    return (int64_t)(p - buf);
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

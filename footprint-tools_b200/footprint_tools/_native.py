@@ -101,6 +101,8 @@ SIGNATURES = {
                                         C.c_int, C.c_char_p, C.c_int, C.c_char, C.c_void_p, C.c_int64, C.c_void_p]),
     "fpt_segment_batch": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "fpt_format_records": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_char_p, C.c_int, C.c_char, C.c_void_p, C.c_int64, C.c_void_p]),
     "fpt_special": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 }
 

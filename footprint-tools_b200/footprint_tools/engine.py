@@ -275,6 +275,14 @@ def detect_footprints_device(ctx, dbatch, thresholds, hw=5, shw=50, clip=0.01, w
 def write_footprint_records(chroms, starts, records, file, name=".", delim="\t", fmt_string="0.4f"):
     """The BED rows write_segments_to_output prints (cli/utils.py:205-209) from segment records: chroms / starts are
     per interval, records = (seg_iv, seg_start, seg_end, seg_score)."""
+    import re
+
+    from .cli import utils as cli_utils
+
+    m = re.match(r"^0?\.(\d)f$", fmt_string)
+    if m and len(delim) == 1:
+        cli_utils.write_segment_records(chroms, starts, records, name, file, delim, int(m.group(1)))
+        return
     seg_iv, seg_start, seg_end, seg_score = records
     fmt = "{0:" + fmt_string + "}"
     rows = []

@@ -266,6 +266,13 @@ int64_t fpt_format_segments(const char *const *chroms, const int64_t *starts, co
                             const double *stats, double threshold, int w, int decreasing, const char *name, int precision,
                             char delim, char *buf, int64_t cap, int64_t *n_done);
 
+/* The BED rows of write_segments_to_output (cli/utils.py:205-209) from footprint records (fpt_segment_batch's output,
+ * HOST arrays): "chrom<d>start+s<d>start+e<d>name<d>score\n" with the score as format(v, ".{precision}f"). Whole rows
+ * are written until `buf` cannot take another; returns the bytes written, *n_done = records consumed. */
+int64_t fpt_format_records(const char *const *chroms, const int64_t *starts, int64_t n_iv, const int64_t *seg_iv,
+                           const int64_t *seg_start, const int64_t *seg_end, const double *seg_score, int64_t n_seg,
+                           const char *name, int precision, char delim, char *buf, int64_t cap, int64_t *n_done);
+
 /* The footprint step of `ftd detect` (cli/detect.py:403-408) for a whole batch ON THE DEVICE: per interval k,
  * utils.segment(stats[out_off[k]:out_off[k+1]], threshold, w, decreasing) (stats/utils.pyx:15-50) and, per segment,
  * np.min(stats[s:e]) (write_segments_to_output, cli/utils.py:203-209). Record q: seg_iv[q] = k, seg_start[q] = s,

@@ -3,6 +3,7 @@ Python formatting (cli/utils.py:119-214 restated) and utils.segment (the loop of
 import io
 
 import numpy as np
+import pytest
 
 from footprint_tools.cli import utils as cli_utils
 from footprint_tools.stats import utils as st_utils
@@ -131,3 +132,52 @@ def test_header():
     lines = f.getvalue().split("\n")
     assert lines[0].startswith("# generated by footprint_tools version") and lines[1] == "# x"
     assert lines[2] == "# chrom\tstart\tend\tname\texp\tobs"
+
+
+def test_footprint_records_format_like_the_reference_rows():
+    """engine.write_footprint_records / cli.utils.write_segment_records (native) == the rows write_segments_to_output
+    prints (cli/utils.py:205-209) == write_segments_batch on the stats the records came from."""
+    import io
+
+    from footprint_tools import engine
+    from footprint_tools.cli import utils as cli_utils
+    from footprint_tools.stats.utils import segment
+
+    rng = np.random.default_rng(12)
+    lens = rng.integers(1, 400, 300)
+    out_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    stats = np.repeat(rng.choice([0.0, 0.0004, 0.00995, 0.01, 0.2, 1.0], len(lens) * 60), rng.integers(1, 9, len(lens) * 60))
+    stats = stats[:out_off[-1]].astype(np.float64)
+    stats[rng.random(stats.shape[0]) < 0.01] = np.nan
+    chroms = ["chr%s" % rng.choice(["1", "X", "12_random"]) for _ in lens]
+    starts = rng.integers(0, 2 ** 31, len(lens)).astype(np.int64)
+    iv, ss, ee, sc = [], [], [], []
+    for k in range(len(lens)):
+        x = stats[out_off[k]:out_off[k + 1]]
+        for s, e in segment(x, 0.01, 3, decreasing=True):
+            iv.append(k); ss.append(s); ee.append(e); sc.append(np.min(x[s:e]))
+    rec = (np.array(iv, dtype=np.int64), np.array(ss, dtype=np.int64), np.array(ee, dtype=np.int64), np.array(sc))
+    assert len(iv) > 200
+    a, b, c = io.StringIO(), io.StringIO(), io.StringIO()
+    engine.write_footprint_records(chroms, starts, rec, a)
+    cli_utils.write_segments_batch(chroms, starts, out_off, stats, 0.01, file=b, decreasing=True)
+    for k, s, e, v in zip(iv, ss, ee, sc):
+        c.write(f"{chroms[k]}\t{starts[k] + s}\t{starts[k] + e}\t.\t" + "{0:0.4f}".format(v) + "\n")
+    assert a.getvalue() == c.getvalue() == b.getvalue()
+    # other precisions natively, other format strings through the Python loop; empty record sets write nothing
+    d, e_ = io.StringIO(), io.StringIO()
+    engine.write_footprint_records(chroms, starts, rec, d, name="fp", delim=",", fmt_string=".2f")
+    for k, s, e, v in zip(iv, ss, ee, sc):
+        e_.write(f"{chroms[k]},{starts[k] + s},{starts[k] + e},fp," + "{0:.2f}".format(v) + "\n")
+    assert d.getvalue() == e_.getvalue()
+    g, h = io.StringIO(), io.StringIO()
+    engine.write_footprint_records(chroms, starts, rec, g, fmt_string="0.3e")
+    for k, s, e, v in zip(iv, ss, ee, sc):
+        h.write(f"{chroms[k]}\t{starts[k] + s}\t{starts[k] + e}\t.\t" + "{0:0.3e}".format(v) + "\n")
+    assert g.getvalue() == h.getvalue()
+    z = io.StringIO()
+    engine.write_footprint_records(chroms, starts, tuple(r[:0] for r in rec), z)
+    assert z.getvalue() == ""
+    bad = (np.array([len(lens)], dtype=np.int64), rec[1][:1], rec[2][:1], rec[3][:1])
+    with pytest.raises(Exception):
+        engine.write_footprint_records(chroms, starts, bad, io.StringIO())
