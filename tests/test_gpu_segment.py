@@ -121,3 +121,22 @@ def test_detect_footprints_device_equals_the_host_pipeline(ctx):
         cli_utils.write_segments_batch(chroms, starts, batch.out_off, cols["efdr"], t, file=b, decreasing=True)
         assert a.getvalue() == b.getvalue()
     assert n_total > 0
+
+
+def test_device_kernels_match_the_reference_golden_vectors(ctx):
+    """fpt_segment_batch and fpt_empirical_fdr against outputs of the reference's own compiled modules
+    (tests/golden/golden_misc.npz: utils.segment, fdr.emperical_fdr of the unmodified reference)."""
+    from conftest import golden
+
+    g = golden("golden_misc.npz")
+    cases = [("segment.x", "segment.a", 0.01, 3, True), ("segment.y2", "segment.f", 0.1, 4, True)]
+    for tag in "bcde":
+        thr, w, dec = g["segment.%s.args" % tag]
+        cases.append(("segment.y", "segment.%s" % tag, float(thr), int(w), bool(dec)))
+    for xk, wk, thr, w, dec in cases:
+        x = np.ascontiguousarray(g[xk], dtype=np.float64)
+        iv, s, e, sc = ctx.segment_batch(x, np.array([0, x.shape[0]], dtype=np.int64), thr, w, dec)
+        assert np.array_equal(np.stack([s, e], axis=1), g[wk]), wk
+        assert np.all(iv == 0)
+        assert np.array_equal(sc, np.array([np.min(x[a:b]) for a, b in g[wk]]))
+    assert np.array_equal(ctx.empirical_fdr(g["fdr.null"], g["fdr.p"]), g["fdr.efdr"])

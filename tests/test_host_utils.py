@@ -40,3 +40,21 @@ def test_emperical_fdr_known_answers():
     nulls = np.array([0.1, np.nan, 0.5, 0.9, np.nan, 0.3])
     pv = np.array([0.05, 0.3, np.nan, 0.95, 0.5, 1.0])
     assert np.allclose(fdr.emperical_fdr(nulls, pv), [0.0, 2 / 6, 1.0, 1.0, 3 / 6, 1.0])
+
+
+def test_host_mirrors_match_the_reference_golden_vectors():
+    """utils.segment / utils.bisect / fdr.emperical_fdr against outputs of the reference's own compiled modules
+    (tests/golden/golden_misc.npz, written by tests/golden/make_golden.py from the unmodified reference)."""
+    from conftest import golden
+    from footprint_tools.stats.utils import segment
+
+    g = golden("golden_misc.npz")
+    assert [list(p) for p in segment(g["segment.x"], 0.01, 3, decreasing=True)] == g["segment.a"].tolist() == [[0, 9]]
+    for tag in "bcde":
+        thr, w, dec = g["segment.%s.args" % tag]
+        got = np.array(segment(g["segment.y"], float(thr), int(w), decreasing=bool(dec)), dtype=np.int64).reshape(-1, 2)
+        assert np.array_equal(got, g["segment.%s" % tag]), tag
+    got = np.array(segment(g["segment.y2"], 0.1, 4, decreasing=True), dtype=np.int64).reshape(-1, 2)
+    assert np.array_equal(got, g["segment.f"])
+    assert np.array_equal(bisect(g["bisect.a"], g["bisect.b"]), g["bisect.out"])
+    assert np.array_equal(fdr.emperical_fdr(g["fdr.null"], g["fdr.p"]), g["fdr.efdr"])
