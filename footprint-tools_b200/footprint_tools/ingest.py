@@ -123,6 +123,35 @@ class GenomeTrack(object):
         return cls([n for n, _ in chroms], lengths, off, n_track, seq2, nmask,
                    np.zeros(n_track, dtype=np.uint32), np.zeros(n_track, dtype=np.uint32))
 
+    @classmethod
+    def from_fasta(cls, path, chroms=None):
+        """Pack a (optionally gzip-compressed) FASTA file — what pysam.FastaFile serves the reference one fetch at a
+        time (modeling/predict.pyx:138-140). Record names are the first word of the '>' line; `chroms` restricts and
+        orders the records kept. Case is dropped and every non-ACGT character reads as N, as after .upper() and the
+        bias model's default (bias.py:16-17)."""
+        import gzip
+
+        opener = gzip.open if str(path).endswith(".gz") else open
+        records, name, parts = [], None, []
+        with opener(path, "rb") as f:
+            for line in f:
+                if line.startswith(b">"):
+                    if name is not None:
+                        records.append((name, b"".join(parts)))
+                    fields = line[1:].split()
+                    name, parts = (fields[0].decode("ascii") if fields else ""), []
+                elif name is not None:
+                    parts.append(line.strip())
+        if name is not None:
+            records.append((name, b"".join(parts)))
+        if chroms is not None:
+            by_name = dict(records)
+            missing = [c for c in chroms if c not in by_name]
+            if missing:
+                raise KeyError("%s: no FASTA record named %s" % (path, ", ".join(missing)))
+            records = [(c, by_name[c]) for c in chroms]
+        return cls.from_sequences(records)
+
     def _span(self, chrom, start, end):
         i = self.index[chrom]
         start, end = int(start), int(end)

@@ -176,6 +176,32 @@ def test_fetch_equals_the_uppercased_fasta_slice(small_track):
             assert track.fasta_func.fetch(name, a, b) == expected_fetch(seq, a, b)
 
 
+def test_from_fasta_reads_plain_and_gzip_files(tmp_path):
+    import gzip
+
+    rng = np.random.default_rng(4)
+    seqs = {"chr1": random_sequence(rng, 1234), "chrM": random_sequence(rng, 61), "empty": "", "chr2": random_sequence(rng, 700)}
+    text = ""
+    for name, s in seqs.items():
+        text += ">%s some description\n" % name
+        width = 60 if name != "chr2" else 7
+        text += "".join(s[i:i + width] + "\n" for i in range(0, len(s), width))
+    plain, gz = tmp_path / "g.fa", tmp_path / "g.fa.gz"
+    plain.write_text(text + "\n")
+    with gzip.open(gz, "wt") as f:
+        f.write(text)
+    for path in (plain, gz):
+        t = GenomeTrack.from_fasta(str(path))
+        assert t.names == list(seqs) and t.lengths == [len(s) for s in seqs.values()]
+        for name, s in seqs.items():
+            assert t.fasta_func.fetch(name, 0, len(s)) == expected_fetch(s, 0, len(s))
+    t = GenomeTrack.from_fasta(str(plain), chroms=["chr2", "chr1"])
+    assert t.names == ["chr2", "chr1"]
+    assert t.fasta_func.fetch("chr1", 100, 130) == expected_fetch(seqs["chr1"], 100, 130)
+    with pytest.raises(KeyError):
+        GenomeTrack.from_fasta(str(plain), chroms=["chr9"])
+
+
 def test_alignment_cut_counts_equal_the_reference_lookup():
     rng = np.random.default_rng(21)
     n = 6000
