@@ -75,6 +75,8 @@ SIGNATURES = {
     "fpt_cuts_from_alignments": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "fpt_unpack_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "fpt_parse_stats_rows": (C.c_int64, [C.c_void_p, C.c_int64, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fpt_kmer_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]),
     "fpt_score": (C.c_int, [C.c_void_p, C.POINTER(ScoreArgs), C.c_int]),
     "fpt_nb_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64,

@@ -328,3 +328,51 @@ class DeviceTrack(object):
         return DeviceBatch(self.seq2, self.nmask, self.cuts_plus, self.cuts_minus, hb.n_track,
                            torch.from_numpy(hb.iv_start).to(self.device), torch.from_numpy(hb.out_off).to(self.device),
                            hb.n_iv, hb.total)
+
+
+def load_posterior_inputs(sample_files, intervals, delim="\t", chunk_bytes=64 << 20):
+    """The (n_samples x m) matrices `ftd posterior` builds per interval (posterior_stats._load_data,
+    cli/post.py:59-87), for a whole list of intervals at once and straight from the samples' `ftd detect` bedGraph
+    files (plain or .gz; the reference goes through one tabix fetch per interval and sample).
+
+    intervals: objects with .chrom/.start/.end or (chrom, start, end) tuples; their columns are laid back to back
+    (seg_off), which is the layout fpt_posterior / stats.posterior take. Returns (obs, exp, fdr, w, seg_off) with the
+    reference's defaults where a sample has no row: obs = exp = 0, fdr = 1, w = 0."""
+    import ctypes as C
+    import gzip
+
+    ivs = [(iv.chrom, iv.start, iv.end) if hasattr(iv, "chrom") else tuple(iv) for iv in intervals]
+    n_iv, n_s = len(ivs), len(sample_files)
+    starts = np.array([s for _, s, _ in ivs], dtype=np.int64)
+    ends = np.array([e for _, _, e in ivs], dtype=np.int64)
+    if np.any(ends < starts):
+        raise ValueError("interval with end < start")
+    seg_off = np.zeros(n_iv + 1, dtype=np.int64)
+    np.cumsum(ends - starts, out=seg_off[1:])
+    m = int(seg_off[-1])
+    obs, exp = np.zeros((n_s, m)), np.zeros((n_s, m))
+    fdr, w = np.ones((n_s, m)), np.zeros((n_s, m))
+    enc = [c.encode() for c, _, _ in ivs]
+    carr = (C.c_char_p * max(n_iv, 1))(*enc)
+    lib = _native.lib()
+    for i, path in enumerate(sample_files):
+        opener = gzip.open if str(path).endswith(".gz") else open
+        with opener(path, "rb") as f:
+            carry = b""
+            while True:
+                block = f.read(chunk_bytes)
+                data = carry + block
+                if not block:
+                    piece, carry = data, b""
+                else:
+                    cut = data.rfind(b"\n") + 1
+                    piece, carry = data[:cut], data[cut:]
+                if piece:
+                    rc = lib.fpt_parse_stats_rows(piece, len(piece), delim.encode(), C.cast(carr, C.c_void_p), starts.ctypes.data,
+                                                  ends.ctypes.data, seg_off.ctypes.data, n_iv, exp[i].ctypes.data,
+                                                  obs[i].ctypes.data, fdr[i].ctypes.data, w[i].ctypes.data)
+                    if rc < 0:
+                        _native._check(int(rc))
+                if not block:
+                    break
+    return obs, exp, fdr, w, seg_off

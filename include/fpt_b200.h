@@ -137,6 +137,16 @@ int64_t fpt_cuts_from_alignments(const int64_t *ref_start, const int64_t *ref_en
  * spelling of non-ACGT characters, all of which score as the default propensity). HOST buffers. */
 int fpt_unpack_sequence(const uint32_t *seq2, const uint32_t *nmask, int64_t first, int64_t n, char *out);
 
+/* posterior_stats._load_data (cli/post.py:59-87) for one sample: parses `n_bytes` of `ftd detect` bedGraph text
+ * (rows "chrom start end exp obs -logp -logwinp fdr", `delim`-separated) and writes exp (field 3), obs (field 4),
+ * fdr (field 7) and w = 1 at column seg_off[k] + (start - iv_starts[k]) of every interval k containing the row's
+ * start (intervals may overlap; seg_off lays the intervals out back to back as fpt_posterior reads them). The four
+ * rows (HOST, length seg_off[n_iv]) must be pre-set by the caller to the reference's defaults 0 / 0 / 1 / 0. Text may
+ * be passed in pieces cut at line ends. Returns the number of values placed (>= 0) or an FPT_ERR_* code. */
+int64_t fpt_parse_stats_rows(const char *text, int64_t n_bytes, char delim, const char *const *iv_chroms,
+                             const int64_t *iv_starts, const int64_t *iv_ends, const int64_t *seg_off, int64_t n_iv,
+                             double *exp_row, double *obs_row, double *fdr_row, double *w_row);
+
 /* ---- the hot path ------------------------------------------------------------------------- */
 
 typedef struct fpt_score_args {

@@ -556,3 +556,69 @@ def test_native_ingest_entry_points_report_errors():
     assert rc == 1 and cm.tolist() == [0, 1] and cp.tolist() == [0, 0]
     assert lib.fpt_cuts_from_alignments(None, None, None, None, -1, 1, 0, 1, 0, -1, 0, 2, _native._ptr(cp), _native._ptr(cm)) == -1
     assert isinstance(C.c_int64(rc).value, int)
+
+
+def reference_load_data(rows_by_sample, interval):
+    """posterior_stats._load_data (cli/post.py:59-87) restated: rows_by_sample[i] is the list of text rows of sample i
+    (the tabix fetch is the filter chrom == interval.chrom and start <= row start < end)."""
+    chrom, start, end = interval
+    n, m = len(rows_by_sample), end - start
+    obs, exp = np.zeros((n, m)), np.zeros((n, m))
+    fdr, w = np.ones((n, m)), np.zeros((n, m))
+    for i, rows in enumerate(rows_by_sample):
+        for line in rows:
+            row = line.split("\t")
+            if row[0] != chrom or not (start <= int(row[1]) < end):
+                continue
+            j = int(row[1]) - start
+            exp[i, j] = np.float64(row[3])
+            obs[i, j] = np.float64(row[4])
+            fdr[i, j] = np.float64(row[7])
+            w[i, j] = 1.0
+    return obs, exp, fdr, w
+
+
+def test_posterior_inputs_from_bedgraph_files(tmp_path):
+    import gzip
+
+    from footprint_tools.ingest import load_posterior_inputs
+
+    rng = np.random.default_rng(31)
+    intervals = [("chr1", 1000, 1300), ("chr2", 50, 51), ("chr1", 1250, 1500), ("chr1", 5000, 5200), ("chrX", 0, 40),
+                 ("chr1", 1290, 1295)]
+    files, rows_by_sample = [], []
+    for i in range(4):
+        rows = []
+        for chrom, lo, hi in (("chr1", 900, 1600), ("chr1", 4990, 5100), ("chr2", 40, 60), ("chrUn", 0, 30)):
+            for pos in range(lo, hi):
+                if rng.random() < 0.3:
+                    continue   # positions the sample did not report
+                vals = [rng.integers(0, 50), rng.integers(0, 60), rng.random() * 9, rng.random() * 9, rng.random() ** 3]
+                txt = ["%0.4f" % v for v in vals]
+                if rng.random() < 0.02:
+                    txt[4] = "nan"
+                if rng.random() < 0.02:
+                    txt[2] = "inf"
+                rows.append("\t".join([chrom, str(pos), str(pos + 1)] + txt))
+        rows_by_sample.append(rows)
+        body = "# generated by footprint_tools\n# chrom\tstart\tend\texp\tobs\n" + "\n".join(rows) + ("\n" if i % 2 else "")
+        path = tmp_path / ("s%d.bedgraph%s" % (i, ".gz" if i == 3 else ""))
+        if i == 3:
+            with gzip.open(path, "wt") as f:
+                f.write(body)
+        else:
+            path.write_text(body + ("short\tline\n" if i == 0 else ""))
+        files.append(str(path))
+    for chunk in (64 << 20, 997):      # whole files and many small pieces cut at line ends
+        obs, exp, fdr, w, seg_off = load_posterior_inputs(files, intervals, chunk_bytes=chunk)
+        assert seg_off.tolist() == np.concatenate([[0], np.cumsum([e - s for _, s, e in intervals])]).tolist()
+        for k, iv in enumerate(intervals):
+            ro, re_, rf, rw = reference_load_data(rows_by_sample, iv)
+            a, b = seg_off[k], seg_off[k + 1]
+            assert np.array_equal(obs[:, a:b], ro) and np.array_equal(exp[:, a:b], re_)
+            assert np.array_equal(fdr[:, a:b], rf, equal_nan=True) and np.array_equal(w[:, a:b], rw)
+        assert w.sum() > 1000 and w[:, seg_off[4]:seg_off[5]].sum() == 0     # chrX: no sample has rows
+    o2 = load_posterior_inputs([], intervals)
+    assert o2[0].shape == (0, int(seg_off[-1]))
+    o3 = load_posterior_inputs(files[:1], [])
+    assert o3[0].shape == (1, 0) and o3[4].tolist() == [0]
