@@ -622,3 +622,50 @@ def test_posterior_inputs_from_bedgraph_files(tmp_path):
     assert o2[0].shape == (0, int(seg_off[-1]))
     o3 = load_posterior_inputs(files[:1], [])
     assert o3[0].shape == (1, 0) and o3[4].tolist() == [0]
+
+
+@pytest.mark.gpu
+def test_gpu_ftd_posterior_from_bedgraph_files(tmp_path):
+    """`ftd posterior` (cli/post.py:98-127) over files: the loader's side-by-side matrices through one fused
+    posterior call == the reference's per-interval pattern (restated loader + one call per interval)."""
+    import io
+
+    from footprint_tools.cli import utils as cli_utils
+    from footprint_tools.ingest import load_posterior_inputs
+    from footprint_tools.modeling import dispersion
+    from footprint_tools.stats import posterior
+
+    rng = np.random.default_rng(77)
+    n_s = 5
+    regions = [("chr1", 2000, 2400), ("chr1", 9000, 9150), ("chr3", 100, 420)]
+    files, rows_by_sample = [], []
+    for i in range(n_s):
+        chroms, starts, lens = [r[0] for r in regions], [r[1] for r in regions], [r[2] - r[1] for r in regions]
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        tot = int(off[-1])
+        exp = rng.poisson(rng.gamma(0.8, 6.0, tot)).astype(np.float64)
+        obs = rng.poisson(exp * rng.uniform(0.3, 1.2, tot)).astype(np.float64)
+        cols = [exp, obs, rng.random(tot) * 5, rng.random(tot) * 5, rng.random(tot) ** 3]
+        buf = io.StringIO()
+        cli_utils.write_stats_batch(chroms, starts, off, cols, file=buf)
+        rows = [r for r in buf.getvalue().splitlines() if rng.random() > 0.1]   # samples miss some positions
+        rows_by_sample.append(rows)
+        path = tmp_path / ("sample%d.bedgraph" % i)
+        path.write_text("\n".join(rows) + "\n")
+        files.append(str(path))
+    intervals = [("chr1", 2050, 2350), ("chr3", 120, 400), ("chr1", 9000, 9150)]
+    obs, exp, fdr, w, seg_off = load_posterior_inputs(files, intervals)
+    dms = []
+    for i in range(n_s):
+        m = dispersion.dispersion_model()
+        m.mu_params, m.r_params = synth.MU_PARAMS, synth.R_PARAMS
+        dms.append(m)
+    betas = rng.uniform(2, 6, (n_s, 2))
+    got = posterior.posterior_batch(obs, exp, fdr, w, dms, betas, 0.05, 3, offsets=seg_off)
+    parts = []
+    for iv in intervals:
+        ro, re_, rf, rw = reference_load_data(rows_by_sample, iv)
+        parts.append(posterior.posterior_batch(ro, re_, rf, rw, dms, betas, 0.05, 3))
+    want = np.vstack(parts)
+    assert got.shape == want.shape == (int(seg_off[-1]), n_s)
+    assert np.array_equal(got, want, equal_nan=True)
