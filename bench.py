@@ -127,7 +127,7 @@ def cpu_reference_rate(batch, info, table, budget_s=15.0, threads=None):
     rate = bases / dt
     n_iv = int(min(batch.n_iv, max(n_probe, rate * budget_s / (bases / n_probe))))
     bases, dt = run(n_iv)
-    return {"value": bases / dt, "unit": "scored bases/sec", "cores": threads, "kind": kind,
+    return {"value": bases / dt, "unit": "bases/s", "cores": threads, "kind": kind,
             "sample": "%d intervals (%d bases) of the same C3 batch, %.1f s, compiled -O2 no-FMA" % (n_iv, bases, dt)}, (seq, cp, cm, in_off, orc, fn, threads)
 
 
