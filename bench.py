@@ -115,11 +115,11 @@ def cpu_reference_rate(batch, info, table, budget_s=15.0, threads=None):
     threads = threads or os.cpu_count() or 1
     seq, cp, cm, in_off = synth.oracle_inputs(batch, info)
 
-    def run(n_iv):
+    def run(n_iv, nthreads=None):
         oo = batch.out_off[:n_iv + 1]
         t0 = time.perf_counter()
         orc.score_batch(seq, cp, cm, in_off[:n_iv + 1], oo, table, mu=synth.MU_PARAMS, r=synth.R_PARAMS, hw=HW, shw=SHW,
-                        clip=CLIP, scales=SCALES, fn_table=fn, nthreads=threads)
+                        clip=CLIP, scales=SCALES, fn_table=fn, nthreads=nthreads or threads)
         return int(oo[-1]), time.perf_counter() - t0
 
     n_probe = min(batch.n_iv, 16 * threads)
@@ -127,8 +127,12 @@ def cpu_reference_rate(batch, info, table, budget_s=15.0, threads=None):
     rate = bases / dt
     n_iv = int(min(batch.n_iv, max(n_probe, rate * budget_s / (bases / n_probe))))
     bases, dt = run(n_iv)
+    # one core as well: about two seconds of the same work
+    n1 = int(min(batch.n_iv, max(16, n_iv * 2.0 / max(dt, 1e-3) / max(threads, 1))))
+    b1, dt1 = run(n1, nthreads=1)
     return {"value": bases / dt, "unit": "bases/s", "cores": threads, "kind": kind,
-            "sample": "%d intervals (%d bases) of the same C3 batch, %.1f s, compiled -O2 no-FMA" % (n_iv, bases, dt)}, (seq, cp, cm, in_off, orc, fn, threads)
+            "sample": "%d intervals (%d bases) of the same C3 batch, %.1f s, compiled -O2 no-FMA" % (n_iv, bases, dt),
+            "single_core_value": b1 / dt1, "single_core_sample": "%d intervals, %.1f s" % (n1, dt1)}, (seq, cp, cm, in_off, orc, fn, threads)
 
 
 def main():
