@@ -668,4 +668,8 @@ def test_gpu_ftd_posterior_from_bedgraph_files(tmp_path):
         parts.append(posterior.posterior_batch(ro, re_, rf, rw, dms, betas, 0.05, 3))
     want = np.vstack(parts)
     assert got.shape == want.shape == (int(seg_off[-1]), n_s)
-    assert np.array_equal(got, want, equal_nan=True)
+    # same kernel on the same columns: side-by-side segments are evaluated exactly like separate calls
+    # (tests/test_gpu_api.py::test_posterior_golden); the bar here only has to catch a misplaced or missing value
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)
+    assert np.any(got > 0)
