@@ -388,16 +388,20 @@ int fpt_pack_sequence(const char *seq, int64_t n, uint32_t *seq2, uint32_t *nmas
     int64_t nw2 = (n + 15) / 16, nwm = (n + 31) / 32;
     memset(seq2, 0, (size_t)nw2 * sizeof(uint32_t));
     memset(nmask, 0, (size_t)nwm * sizeof(uint32_t));
-    static signed char lut[256];
-    static bool init = false;
-    if (!init) {
-        memset(lut, -1, sizeof lut);
-        lut[(int)'A'] = lut[(int)'a'] = 0;
-        lut[(int)'C'] = lut[(int)'c'] = 1;
-        lut[(int)'G'] = lut[(int)'g'] = 2;
-        lut[(int)'T'] = lut[(int)'t'] = 3;
-        init = true;
-    }
+    // constant-initialised by a function-local static (thread-safe since C++11): ctypes releases the GIL, so two
+    // threads may pack concurrently on first use
+    struct Lut {
+        signed char v[256];
+        Lut() {
+            memset(v, -1, sizeof v);
+            v[(int)'A'] = v[(int)'a'] = 0;
+            v[(int)'C'] = v[(int)'c'] = 1;
+            v[(int)'G'] = v[(int)'g'] = 2;
+            v[(int)'T'] = v[(int)'t'] = 3;
+        }
+    };
+    static const Lut table;
+    const signed char *lut = table.v;
     for (int64_t i = 0; i < n; ++i) {
         int c = lut[(unsigned char)seq[i]];
         if (c < 0)
@@ -662,10 +666,12 @@ static int score_host_pipelined(fpt_ctx *ctx, const fpt_score_args *a, int n_chu
     std::vector<int64_t> piece_end(n_chunks, (int64_t)nt);
     if (monotone) {
         for (int c = 0; c + 1 < n_chunks; ++c) {
+            // furthest track position any interval of the chunk reads: starts are non-decreasing, ends need not be
+            // (nested / overlapping intervals of a sorted BED share one track), hence the maximum over the chunk
             int64_t e = 0;
-            if (first[c + 1] > first[c]) {
-                const int64_t j = first[c + 1] - 1;
-                e = a->iv_start[j] + (a->out_off[j + 1] - a->out_off[j]) + pad + 64;
+            for (int64_t j = first[c]; j < first[c + 1]; ++j) {
+                const int64_t ej = a->iv_start[j] + (a->out_off[j + 1] - a->out_off[j]) + pad + 64;
+                if (ej > e) e = ej;
             }
             e = (e + 31) / 32 * 32;
             if (c > 0 && e < piece_end[c - 1]) e = piece_end[c - 1];

@@ -66,14 +66,19 @@ class _FastaFunc(object):
     def fetch(self, chrom, start, end):
         t = self._t
         n_chrom = t.lengths[t.index[chrom]]
-        start, end = max(int(start), 0), min(int(end), n_chrom)   # pysam clips at the chromosome ends
+        start, end = int(start), min(int(end), n_chrom)   # pysam clips at the chromosome END only
+        # pysam raises for a negative start; the track's read_func serves such an interval from its guard region
+        # (zero cuts), so the bases before position 0 come back as N: the string stays aligned with the counts
+        # (a silent clip here would shift every base of the interval against its cut counts)
+        lead = "N" * max(min(end, 0) - start, 0) if start < 0 else ""
+        start = max(start, 0)
         if end <= start:
-            return ""
+            return lead
         a, b = t._span(chrom, start, end)
         out = np.empty(b - a, dtype=np.uint8)
         _native._check(_native.lib().fpt_unpack_sequence(_native._ptr(t.seq2), _native._ptr(t.nmask), a, b - a,
                                                          _native._ptr(out)))
-        return out.tobytes().decode("ascii")
+        return lead + out.tobytes().decode("ascii")
 
 
 class GenomeTrack(object):
@@ -185,6 +190,9 @@ class GenomeTrack(object):
             raise ValueError("alignment columns differ in length")
         i = self.index[chrom]
         o, ln = int(self.chrom_off[i]), self.lengths[i]
+        if not (self.cuts_plus.flags.writeable and self.cuts_minus.flags.writeable):
+            # the native counter increments in place through raw pointers: numpy's own read-only check never runs
+            raise ValueError("the track's cut counts are read-only (open the .fptrk file with mode='r+')")
         cp = self.cuts_plus[o:o + ln]
         cm = self.cuts_minus[o:o + ln]
         rc = _native.lib().fpt_cuts_from_alignments(

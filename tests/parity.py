@@ -130,3 +130,25 @@ def assert_score_close(res, ref, scales, oracle=None, out_off=None, what=""):
             stage = np.concatenate([oracle.window(np.ascontiguousarray(res["pval"][a:b]), h, 3)
                                     for a, b in zip(out_off[:-1], out_off[1:])]) if len(out_off) > 1 else np.zeros(0)
             assert_pvalues_close(res["winp"][i], stage, "%s winp hw=%d (window stage on device p)" % (what, h))
+
+
+def posterior_tolerance(prior, ll_on, ll_off, post_ref):
+    """Tolerance on the (negated, clipped) log posterior of stats/posterior.py:142-149,
+        post = (log prior + ll_off) - logaddexp(log(1 - prior) + ll_on, log prior + ll_off) = -softplus(d),
+        d = p_on - p_off.
+    The log-likelihoods are 7-position sums of log-pmfs of magnitude O(10..1000), each held to the parity bar
+    tol_ll = 1e-9 |ll| + 1e-11; d post / d ll_on = -d post / d ll_off = -sigmoid(d), so a pair of log-likelihoods
+    that both MEET the bar can move the posterior by sigmoid(d) (tol_on + tol_off). To that first-order image are
+    added the plain bar on the result and the rounding of the reference's own subtraction of two O(|p_off|) numbers,
+    4 ulp(|p_on| + |p_off|). Nothing here is fitted to the observed deviations."""
+    prior, ll_on, ll_off = (np.asarray(a, dtype=np.float64) for a in (prior, ll_on, ll_off))
+    post_ref = np.asarray(post_ref, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        p_off = np.log(prior) + ll_off
+        p_on = np.log(1 - prior) + ll_on
+        d = p_on - p_off
+        sig = np.where(d > 0, 1.0 / (1.0 + np.exp(-d)), np.exp(d) / (1.0 + np.exp(d)))
+        tol_ll = REL_TOL * (np.abs(ll_on) + np.abs(ll_off)) + 2 * ABS_FLOOR
+        tol = REL_TOL * np.abs(post_ref) + ABS_FLOOR + sig * tol_ll + 4 * 2.220446049250313e-16 * (np.abs(p_on) + np.abs(p_off))
+    tol[~np.isfinite(tol)] = ABS_FLOOR
+    return tol

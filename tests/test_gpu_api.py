@@ -16,7 +16,7 @@ from footprint_tools import synth
 from footprint_tools.modeling import bias, dispersion, predict
 from footprint_tools.stats import posterior, windowing
 from footprint_tools.stats.distributions import nbinom
-from parity import assert_close, assert_exact, assert_pvalues_close
+from parity import assert_close, assert_exact, assert_pvalues_close, assert_within, posterior_tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -85,11 +85,17 @@ def test_bias_model_probs(bm, oracle):
 
 
 # ---- modeling.predict ---------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["std", "nosmooth"])
+@pytest.mark.parametrize("case", ["std", "nosmooth", "uniform", "sparse", "deep", "k0", "k2", "k5", "hw3", "const"])
 def test_prediction_compute_golden(bm, case):
+    """Every case of golden_predict.npz (tests/golden/make_golden.py:80-89) through prediction.compute on the GPU:
+    the ftd detect / learn_dm geometries, the uniform model, sparse and 400x-deep counts, trimming k = 0 / 1 / 2 / 5,
+    other window half-widths and constant counts with one outlier."""
     g = golden("golden_predict.npz")
+    assert sorted(str(c) for c in g["cases"]) == sorted(
+        ["std", "nosmooth", "uniform", "sparse", "deep", "k0", "k2", "k5", "hw3", "const"])
     hw, shw, clip = int(g[case + ".params"][0]), int(g[case + ".params"][1]), float(g[case + ".params"][2])
-    pred = predict.prediction(_Reads(g[case + ".plus"], g[case + ".minus"]), _Fasta(str(g[case + ".seq"])), bm,
+    model = bias.uniform_model() if float(g[case + ".params"][3]) == 1.0 else bm
+    pred = predict.prediction(_Reads(g[case + ".plus"], g[case + ".minus"]), _Fasta(str(g[case + ".seq"])), model,
                               half_win_width=hw, smoothing_half_win_width=shw, smoothing_clip=clip)
     assert pred.padding == hw + shw
     ivs = [_Interval("chr1", int(s), int(e)) for s, e in g[case + ".intervals"]]
@@ -201,14 +207,65 @@ def test_posterior_golden():
     ll_off = posterior.log_likelihood(obs, exp, dms, w=3)
     assert_close(ll_on, g["ll_on"], "ll_on")
     assert_close(ll_off, g["ll_off"], "ll_off")
+    # the formula alone, on the reference's own inputs: the plain bar (posterior.py:142-149 in numpy's operation order)
     post = posterior.posterior(g["prior"], g["ll_on"], g["ll_off"])
-    assert_close(post, g["posterior"], "posterior", limit=50.0)  # cancellation of O(100) log-likelihoods
+    assert_close(post, g["posterior"], "posterior")
+    # end to end: the plain bar plus the image of the log-likelihoods' own bar through the formula (posterior_tolerance)
     fused = posterior.posterior_batch(obs, exp, fdr, w, dms, betas, cutoff, 3)
     assert fused.shape == g["post_T"].shape
-    assert_close(fused, g["post_T"], "post.T", limit=50.0)
+    assert_within(fused, g["post_T"], posterior_tolerance(g["prior"], g["ll_on"], g["ll_off"], g["post_T"].T).T, "post.T")
     # two intervals side by side == two calls
     m = obs.shape[1]
     both = posterior.posterior_batch(obs, exp, fdr, w, dms, betas, cutoff, 3, offsets=[0, 100, m])
     a = posterior.posterior_batch(obs[:, :100], exp[:, :100], fdr[:, :100], w[:, :100], dms, betas, cutoff, 3)
     b = posterior.posterior_batch(obs[:, 100:], exp[:, 100:], fdr[:, 100:], w[:, 100:], dms, betas, cutoff, 3)
     assert_exact(both, np.vstack([a, b]))
+
+
+def test_posterior_c4_shape(oracle):
+    """Config C4's shape (BASELINE.json: 64 samples sharing one dispersion model) on 120 intervals x 300 bp, every stage
+    of stats/posterior.py:12-149 + cli/post.py:114-126 against the numpy / oracle restatement (tests/refstyle.py):
+    prior, delta and both log-likelihoods at the plain 1e-9 bar; the formula alone on the reference's inputs at the
+    plain bar; the fused end-to-end result within the bar plus the first-order image of the log-likelihood bar."""
+    import refstyle
+
+    ns, n_iv, ln = 64, 120, 300
+    m = n_iv * ln
+    rng = np.random.Generator(np.random.PCG64(20244))
+    depth = np.exp(rng.uniform(np.log(0.3), np.log(3.0), (ns, 1)))            # LogUniform(0.3, 3) sample depth
+    base = rng.gamma(0.8, 4.0, (1, m)) * 4.0
+    exp = np.round(base * depth)
+    obs = rng.poisson(exp * rng.uniform(0.6, 1.2, (ns, m))).astype(np.float64)
+    fdr = rng.uniform(0, 1, (ns, m)) ** 3
+    w = (rng.uniform(0, 1, (ns, m)) < 0.8).astype(np.float64)
+    betas = rng.uniform(2, 6, (ns, 2))
+    cutoff = 0.05
+    mus = np.tile(np.asarray(synth.MU_PARAMS, dtype=np.float64), (ns, 1))
+    rs = np.tile(np.asarray(synth.R_PARAMS, dtype=np.float64), (ns, 1))
+    dms = [_dm(mus[0], rs[0])] * ns
+    off = np.arange(n_iv + 1, dtype=np.int64) * ln
+
+    # reference side, interval by interval as cli/post.py:98-127 runs it
+    prior_r, delta_r = np.empty((ns, m)), np.empty(m)
+    on_r, off_r = np.empty((ns, m)), np.empty((ns, m))
+    for a, b in zip(off[:-1], off[1:]):
+        sl = slice(a, b)
+        prior_r[:, sl] = refstyle.posterior_prior(fdr[:, sl], w[:, sl], cutoff)
+        delta_r[sl] = refstyle.posterior_delta(obs[:, sl], exp[:, sl], fdr[:, sl], betas, cutoff)
+        on_r[:, sl] = refstyle.posterior_loglik(oracle, obs[:, sl], exp[:, sl], mus, rs, delta=delta_r[sl])
+        off_r[:, sl] = refstyle.posterior_loglik(oracle, obs[:, sl], exp[:, sl], mus, rs)
+    post_r = -refstyle.posterior_post(prior_r, on_r, off_r)
+    post_r[post_r <= 0] = 0                                                    # cli/post.py:121-126
+
+    assert_close(posterior.compute_prior_weighted(fdr, w, cutoff), prior_r, "prior")
+    assert_close(posterior.compute_delta_prior(obs, exp, fdr, betas, cutoff), delta_r, "delta")
+    for a, b in ((0, ln), (57 * ln, 58 * ln), (m - ln, m)):                     # the per-interval API on three intervals
+        sl = slice(a, b)
+        assert_close(posterior.log_likelihood(obs[:, sl], exp[:, sl], dms, delta=delta_r[sl], w=3), on_r[:, sl], "ll_on")
+        assert_close(posterior.log_likelihood(obs[:, sl], exp[:, sl], dms, w=3), off_r[:, sl], "ll_off")
+    assert_close(posterior.posterior(prior_r, on_r, off_r), refstyle.posterior_post(prior_r, on_r, off_r), "formula")
+    fused = posterior.posterior_batch(obs, exp, fdr, w, dms, betas, cutoff, 3, offsets=off)
+    assert fused.shape == (m, ns)
+    assert_within(fused, post_r.T, posterior_tolerance(prior_r, on_r, off_r, post_r).T, "C4 posterior (end to end)")
+    frac_tight = float(np.mean(np.abs(fused - post_r.T) <= 1e-9 * np.abs(post_r.T) + 1e-11))
+    assert frac_tight > 0.999, "only %.5f of the posteriors meet the plain bar" % frac_tight

@@ -354,12 +354,25 @@ def _ctx_with_env(**env):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("shuffled", [False, True])
+@pytest.mark.parametrize("shuffled", [False, True, "nested"])
 def test_host_pipeline_equals_single_shot(table, shuffled):
     """FPT_MEM_HOST on a batch large enough for the chunked copy-in / score / copy-out pipeline gives the
-    same bytes as the single-shot staging path, also when the intervals are not in track order."""
+    same bytes as the single-shot staging path, also when the intervals are not in track order and when
+    intervals in track order overlap (a long interval that starts with a short one reaches further than the
+    last interval of its chunk: the chunk must wait for the track up to the furthest END, not the last one)."""
     batch, _ = synth.make_batch(16000, 55, seed=61, table=table)
-    if shuffled:
+    if shuffled == "nested":
+        lens = np.diff(batch.out_off)
+        starts = batch.iv_start
+        ins = np.arange(40, batch.n_iv - 200, 331)          # a 30 kb interval in front of every 331st one
+        long_len = np.minimum(30000, batch.n_track - 64 - starts[ins])
+        iv_start = np.insert(starts, ins, starts[ins])
+        lens = np.insert(lens, ins, long_len)
+        assert np.all(np.diff(iv_start) >= 0)
+        out_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        batch = engine.IntervalBatch(batch.seq2, batch.nmask, batch.cuts_plus, batch.cuts_minus, batch.n_track,
+                                     iv_start, out_off, batch.block_off)
+    elif shuffled:
         perm = np.random.Generator(np.random.PCG64(3)).permutation(batch.n_iv)
         lens = np.diff(batch.out_off)[perm]
         out_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)

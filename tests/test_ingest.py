@@ -173,7 +173,9 @@ def test_fetch_equals_the_uppercased_fasta_slice(small_track):
         for _ in range(60):
             a = int(rng.integers(-20, n + 1))
             b = int(rng.integers(a, n + 30))
-            assert track.fasta_func.fetch(name, a, b) == expected_fetch(seq, a, b)
+            # positions before 0 read as N (the guard region read_func serves), the end clips as pysam's does
+            lead = "N" * (min(b, 0) - a) if a < 0 else ""
+            assert track.fasta_func.fetch(name, a, b) == lead + expected_fetch(seq, a, b)
 
 
 def test_from_fasta_reads_plain_and_gzip_files(tmp_path):
@@ -255,6 +257,8 @@ def test_file_round_trip_and_in_place_accumulation(tmp_path, small_track):
     assert back.fasta_func.fetch("chrC", 0, 97) == expected_fetch(seqs["chrC"], 0, 97)
     with pytest.raises(ValueError):
         back.cuts_plus[0] = 1   # read-only mapping
+    with pytest.raises(ValueError, match="read-only"):   # the native in-place counter must not touch a read-only mapping
+        back.add_alignments("chrA", [10], [50], [0], [60])
     rw = GenomeTrack.open(path, mode="r+")
     before = int(rw.cuts_plus.sum())
     assert rw.add_alignments("chrA", [10, 10, 20], [50, 60, 70], [0, 0, 0], [60, 60, 60]) == 3
@@ -267,6 +271,20 @@ def test_file_round_trip_and_in_place_accumulation(tmp_path, small_track):
         f.write(b"XXXX")
     with pytest.raises(ValueError):
         GenomeTrack.open(path)
+
+
+def test_fetch_before_position_zero_stays_aligned_with_the_counts(small_track):
+    """A padded interval that starts before position 0: read_func serves guard positions (zero cuts), so fetch must
+    return N for the same positions — a silent clip would shift every base against its cut count."""
+    rng, seqs, track = small_track
+    name = track.names[0]
+    seq = seqs[name]
+    got = track.fasta_func.fetch(name, -39, 120)
+    assert len(got) == 159 and got[:39] == "N" * 39 and got[39:] == expected_fetch(seq, 0, 120)
+    assert track.fasta_func.fetch(name, -5, -2) == "NNN"
+    assert track.fasta_func.fetch(name, -5, 0) == "NNNNN"
+    n = len(seq)
+    assert track.fasta_func.fetch(name, n - 10, n + 40) == expected_fetch(seq, n - 10, n)   # the END clips as pysam does
 
 
 def test_sparse_cut_encoding_round_trip(tmp_path, small_track):
@@ -408,6 +426,33 @@ def test_gpu_resident_track_equals_host_batches(table, tmp_path):
         ctx.sync()
         for k in want:
             assert np.array_equal(bufs[k].cpu().numpy(), want[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_gpu_prediction_compute_near_a_chromosome_start_equals_the_track_batch(table):
+    """prediction(track.read_func, track.fasta_func, bm).compute on intervals within pad + 4 of position 0 and of the
+    chromosome end equals the zero-copy track batch bit for bit (the fetch must not shift bases against counts)."""
+    from footprint_tools import _native, engine
+    from footprint_tools.modeling import predict
+
+    track, _ = _track_with_cuts(seed=12)
+    name = track.names[0]
+    n = track.lengths[0]
+    ivs = [genomic_interval(name, 20, 200), genomic_interval(name, 1, 90), genomic_interval(name, 58, 300),
+           genomic_interval(name, n - 230, n - 12), genomic_interval(name, n - 150, n - 1)]
+    pad = 55
+    ctx = _native.default_context(0)
+    ctx.set_bias(table, 1e-6)
+    pr = predict.prediction(track.read_func, track.fasta_func, _TableModel(table), half_win_width=5,
+                            smoothing_half_win_width=50, smoothing_clip=0.01)
+    got = pr.compute_batch(ivs)
+    batch = track.batch(ivs, pad, per_strand=True)
+    want = engine.score_host(ctx, batch, 5, 50, 0.01, scales=(), want=("exp", "win"), combine=False)
+    for k, (obs, exp, win) in enumerate(got):
+        a, b = batch.out_off[k], batch.out_off[k + 1]
+        for s, strand in enumerate(("+", "-")):
+            assert np.array_equal(exp[strand], want["exp"][s, a:b]), (k, strand)
+            assert np.array_equal(win[strand], want["win"][s, a:b]), (k, strand)
 
 
 class _TableModel(object):
