@@ -297,7 +297,7 @@ def main():
     # kernel from its own event-timed launches, and for the whole path in `path`.
     split = bool(kern.get("window_fast", (0.0, 0))[1])  # windows evaluated by the streaming kernel, not in the scoring kernel
     alg = {"score_fused": 8.5 + 24.0 if split else BYTES_PER_BASE, "score_fast": 8.5 + 24.0, "window_fast": 8.0 * len(SCALES),
-           "score_general": BYTES_PER_BASE, "plan": 0.0, "redo": 0.0, "direct_fix": 0.0}
+           "score_general": BYTES_PER_BASE, "score_warp": BYTES_PER_BASE, "plan": 0.0, "redo": 0.0, "direct_fix": 0.0, "fdr": 0.0}
     per_kernel = {}
     for name, (tot_ms, n) in kern.items():
         if n:

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "fpt_internal.h"
+#include "fpt_warp_host.h"
 
 using namespace fpt;
 
@@ -92,6 +93,9 @@ struct fpt_ctx {
     bool fast_prepared = false;
     int force_general = 0;  // FPT_B200_GENERAL=1 / FPT_B200_PATH=general: route everything through the general kernel
     int allow_fused = 1;    // FPT_B200_PATH=fast: skip the fused kernel (two-kernel throughput path instead)
+    int allow_warp = 1;     // FPT_B200_PATH=fused / fast: skip the warp-autonomous kernel (the CTA-tiled kernels instead)
+    bool warp_prepared = false;
+    DevBuf items;           // [n_items | work counter | redo count | pad] ints, then the WItem records, then the redo ranges
     int fused_inwin = 0;    // FPT_B200_FUSED_WIN=1: Stouffer windows inside the fused kernel instead of the streaming kernel
     bool fused_prepared = false;
     DevBuf direct;          // [count | list] of positions whose NB p-value is evaluated by direct_fix_kernel
@@ -223,6 +227,7 @@ int fpt_ctx_create(int device, fpt_ctx **out) {
     const char *path = getenv("FPT_B200_PATH");
     if (path && !strcmp(path, "general")) c->force_general = 1;
     if (path && !strcmp(path, "fast")) c->allow_fused = 0;
+    if (path && (!strcmp(path, "fast") || !strcmp(path, "fused"))) c->allow_warp = 0;
     const char *pl = getenv("FPT_B200_PIPELINE");
     c->pipeline = (pl && pl[0] == '0') ? 0 : 1;
     const char *nr = getenv("FPT_B200_NARROW");
@@ -457,6 +462,53 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     // The fused kernel serves the two geometries the reference's programs use (cli/detect.py defaults:
     // smoothing half-width 50 with one value trimmed per side; cli/learn_dm.py: no smoothing).
     const bool fused = fast && ctx->allow_fused && ((shw == 50 && ktrim == 1) || shw == 0);
+    // The warp-autonomous kernel (fpt_warp.cu) serves the same two geometries in ONE launch: every warp takes an item
+    // (an interval or a piece of a long one) from the packed track to exp / obs / p / windowed p with no block barrier
+    // and nothing intermediate in HBM.
+    if (fused && ctx->allow_warp && wk::warp_geometry_ok(hw, shw, ktrim, wh_max, p.combine != 0, a->win_out != nullptr) &&
+        wk::warp_params_finish(p, a, wh_max)) {
+        const size_t cap = warp_items_capacity(a->n_iv, a->total);
+        const size_t head = 64, items_bytes = (cap * sizeof(WItem) + 63) & ~(size_t)63;
+        CU(ctx->items.need(head + items_bytes + cap * 3 * sizeof(long long)));
+        int *hd = ctx->items.as<int>();
+        WItem *items = reinterpret_cast<WItem *>(ctx->items.as<char>() + head);
+        p.items = items;
+        p.n_items = hd;
+        p.work_counter = hd + 1;
+        p.redo_count = hd + 2;
+        p.redo_ranges = reinterpret_cast<long long *>(ctx->items.as<char>() + head + items_bytes);
+        CU(cudaMemsetAsync(hd, 0, head, ctx->stream));
+        {
+            ProfScope ps(ctx, FPT_KERNEL_PLAN);
+            CU(launch_plan_items(ctx->stream, p.out_off, p.iv_start, p.n_iv, p.wh_max, items, hd));
+        }
+        ctx->launches++;
+        if (!ctx->warp_prepared) {
+            CU(score_warp_prepare());
+            ctx->warp_prepared = true;
+        }
+        {
+            ProfScope ps(ctx, FPT_KERNEL_SCORE_WARP);
+            CU(launch_score_warp(ctx->stream, p, ctx->sm_count, shw != 0));
+        }
+        ctx->launches++;
+        // items with cut counts beyond the packed 16-bit window format: rescored by the general kernel (range list;
+        // exits at once when the list is empty)
+        ScoreParams q = p;
+        q.wh_max = wh_max;
+        q.tile = kComputeMax - 2 * wh_max;
+        q.range_list = p.redo_ranges;
+        q.n_list = p.redo_count;
+        const size_t gsmem = score_smem_bytes(hw, q.uniform != 0);
+        CU(score_kernel_prepare(gsmem));
+        long long rgrid = ctx->sm_count;
+        {
+            ProfScope ps(ctx, FPT_KERNEL_REDO);
+            CU(launch_score(ctx->stream, q, (int)rgrid));
+        }
+        ctx->launches++;
+        return FPT_OK;
+    }
     if (fused) {
         auto al = [](const void *q, unsigned m) { return (reinterpret_cast<uintptr_t>(q) & m) == 0; };
         const bool windows = a->winp_out && a->n_scales > 0;

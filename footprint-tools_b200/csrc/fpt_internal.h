@@ -31,6 +31,15 @@ constexpr int kFastXCap = 8 * kFastThreads;       // staged slots per sub-tile
 constexpr int kFastHalfWin = 5;                   // half_win_width it is instantiated for
 constexpr int kFastMaxScaleHalfWin = 8;           // Stouffer half-width limit of the fast kernel
 
+// Work item of the warp-autonomous kernel (fpt_warp.cu): outputs [ta, tb) (interval-local) of interval iv.
+struct alignas(16) WItem {
+    long long o0;  // out_off[iv]
+    long long st;  // iv_start[iv]
+    int len;       // interval length
+    int ta, tb;
+    int iv;
+};
+
 struct ScoreParams {
     const uint32_t *seq2, *nmask, *cuts_p, *cuts_m;
     long long n_track;
@@ -74,6 +83,16 @@ struct ScoreParams {
     // general kernel in list mode: score tiles tile_list[0 .. *n_list) instead of 0 .. n_tiles
     const int *tile_list;
     const int *n_list;
+    // ... or, when range_list is set, the flat output ranges [range_list[3 w], range_list[3 w + 1]) of interval
+    // range_list[3 w + 2], w in 0 .. *n_list (items handed back by the warp-autonomous kernel)
+    const long long *range_list;
+    // warp-autonomous kernel (fpt_warp.cu)
+    int wmode;                 // windows: 0 none, 1 = {3}, 2 = {3, 5, 7}, 3 = win_h[0 .. n_win_h) (ascending, <= 3)
+    int win_h[3], n_win_h;
+    const WItem *items;        // built by plan_items_kernel
+    const int *n_items;
+    int *work_counter;         // next item to hand out
+    long long *redo_ranges;    // 3 per item whose cut counts exceed the packed range; count in redo_count
 };
 
 // window kernel of the fast path (fpt_fast.cu)
@@ -101,6 +120,13 @@ int score_fused_blocks_per_sm(bool smooth, bool inwin, bool hist);
 cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, bool smooth, bool inwin);
 
 cudaError_t launch_direct_fix(cudaStream_t st, const ScoreParams &p, int sm_count);
+
+// fpt_warp.cu: the warp-autonomous fused kernel (one launch: track -> exp / obs / p / windowed p)
+size_t warp_items_capacity(long long n_iv, long long total);
+cudaError_t launch_plan_items(cudaStream_t st, const long long *out_off, const long long *iv_start, long long n_iv, int wh,
+                              WItem *items, int *n_items);
+cudaError_t score_warp_prepare();
+cudaError_t launch_score_warp(cudaStream_t st, const ScoreParams &p, int sm_count, bool smooth);  // p.wmode selects the window variant
 
 size_t score_fast_smem_bytes();
 cudaError_t score_fast_prepare(size_t smem);

@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
     double *dmp = reinterpret_cast<double *>(W + kStageCap);                  // 24
     RegionTable *R = reinterpret_cast<RegionTable *>(dmp + kModelDoubles);
 
-    if (P.tile_list && (long long)blockIdx.x >= (long long)*P.n_list) return;  // list mode: nothing for this CTA
+    const bool list_mode = P.tile_list != nullptr || P.range_list != nullptr;
+    if (list_mode && (long long)blockIdx.x >= (long long)*P.n_list) return;  // list mode: nothing for this CTA
     const int tid = threadIdx.x;
     __shared__ double q4tab[kNdTab];  // 2^(j/4) for ndtr_fast1 (list mode; published by the kernel's first barrier)
     ndtr4_table_init(q4tab, tid);
@@ -247,13 +248,19 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
     while (pow2 * 2 <= wsm) pow2 *= 2;
 
     // list mode (redo of the tiles the fused kernel could not carry): tiles tile_list[0 .. *n_list)
-    const long long n_work = P.tile_list ? (long long)*P.n_list : P.n_tiles;
+    // ... or, with range_list, the flat output ranges the warp-autonomous kernel handed back (each inside one interval)
+    const long long n_work = list_mode ? (long long)*P.n_list : P.n_tiles;
     for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
-        const long long tile = P.tile_list ? (long long)P.tile_list[work] : work;
-        const long long lo = tile * (long long)P.tile;
-        const long long hi = (lo + P.tile < P.total) ? lo + P.tile : P.total;
+        long long lo, hi, k;
+        if (P.range_list) {
+            lo = P.range_list[3 * work]; hi = P.range_list[3 * work + 1]; k = P.range_list[3 * work + 2];
+        } else {
+            const long long tile = P.tile_list ? (long long)P.tile_list[work] : work;
+            lo = tile * (long long)P.tile;
+            hi = (lo + P.tile < P.total) ? lo + P.tile : P.total;
+            k = P.tile_first_iv[tile];
+        }
         long long cur = lo;
-        long long k = P.tile_first_iv[tile];
         while (cur < hi) {
             // ---- build the region table (warp 0) -------------------------------------------
             if (warp == 0) {
@@ -566,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 2) score_kernel(const ScoreParams P)
                 const long long f = R->flat0[r] + q;
                 if (f < sub_lo || f >= sub_hi) continue;
                 const long long t = R->t0[r] + q, len = R->ivlen[r];
-                if (P.tile_list) {
+                if (list_mode) {
                     // list mode = tiles handed back by the fused kernel: use that kernel's window arithmetic
                     // (sums grown outward from the centre, branch-free normal tail) so that a position
                     // carries the same bits whichever kernel scored its tile

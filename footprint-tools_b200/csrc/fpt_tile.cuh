@@ -289,6 +289,102 @@ __device__ __forceinline__ void ndtr4(const double (&a)[4], const double *s4, do
     }
 }
 
+// ndtr4 with the same operations in the same order (same bits), written for the instruction count of the warp-autonomous
+// kernel: |a| is taken by the FP64 instructions' own source modifier instead of an integer AND plus a register move,
+// and the double-precision constants that do not fit an instruction's 32-bit immediate come from constant memory as
+// direct operands (c[bank][offset]) instead of being rebuilt with two moves per use.
+__constant__ double kNdK[4] = {FPT_ND_SCALE, FPT_ND_LHI, FPT_ND_LLO, 0.0};
+__constant__ double kNdG[7] = {2.07949308206693863e-02, -6.91185624438261093e-02, 1.65020386126410318e-01, -3.13533160990166759e-01,
+                               4.95305615008850841e-01, -6.65382502818922417e-01, 7.69193049757243230e-01};
+#if !FPT_ND_EXP64 && !FPT_ND_G64
+__device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, double (&res)[4]) {
+    double u[4], q[4], r[4], G[4], pe[4];
+    int n[4];
+    bool slow = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        slow |= ((unsigned)__double2hiint(a[e]) & 0x7FFFFFFFu) >= 0x403A0000u;  // |a| >= 26, infinite or NaN
+        const double t = fabs(a[e]);
+        const double d = __dadd_rn(t, 5.0);
+        double rr;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(d));
+        const double er = fma(-d, rr, 1.0);
+        rr = fma(rr, er, rr);
+        r[e] = rr;
+        u[e] = fma(-10.0, rr, 1.0);
+        const double y = __dmul_rn(-0.5, __dmul_rn(t, t));
+        const double kf = fma(y, kNdK[0], 6755399441055744.0);
+        n[e] = __double2loint(kf);
+        const double nf = __dadd_rn(kf, -6755399441055744.0);
+        const double qq = fma(nf, kNdK[1], y);
+        q[e] = fma(nf, kNdK[2], qq);
+    }
+    {
+        float uf[4], Gf[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            uf[e] = __double2float_rn(u[e]);
+            Gf[e] = fmaf(6.153616596e-06f, uf[e], 1.409234847e-05f);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -5.337512994e-05f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -5.887623411e-05f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], 5.470084143e-04f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -7.975917542e-04f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Gf[e] = fmaf(Gf[e], uf[e], -2.993954578e-03f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) G[e] = fma((double)Gf[e], u[e], kNdG[0]);
+    }
+    {
+        float qf[4], Rf[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            qf[e] = __double2float_rn(q[e]);
+            Rf[e] = fmaf(1.0f / 720.0f, qf[e], 1.0f / 120.0f);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 24.0f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Rf[e] = fmaf(Rf[e], qf[e], 1.0f / 6.0f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pe[e] = fma((double)Rf[e], q[e], 0.5);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], kNdG[i + 1]);
+        if (i < 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pe[e] = fma(pe[e], q[e], 1.0);
+        }
+        if (i == 2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pe[e] = __dmul_rn(pe[e], s4[n[e] & FPT_ND_MASK]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double E = __hiloint2double(__double2hiint(pe[e]) + ((n[e] >> FPT_ND_SHIFT) << 20), __double2loint(pe[e]));
+        const double er = __dmul_rn(E, r[e]);
+        const int ah = __double2hiint(a[e]);
+        const double ers = __hiloint2double(__double2hiint(er) ^ (~ah & (int)0x80000000), __double2loint(er));
+        const double one0 = __hiloint2double(~(ah >> 31) & 0x3FF00000, 0);
+        res[e] = __fma_rn(ers, G[e], one0);  // tail for a < 0, 1 - tail otherwise (see ndtr_fast1)
+    }
+    if (slow) {  // |a| >= 26, infinite or NaN: the Cephes replica (rare)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (!(fabs(a[e]) < 26.0)) res[e] = ndtr_slow(a[e]);
+    }
+}
+#else
+__device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, double (&res)[4]) { ndtr4(a, s4, res); }
+#endif
+
 // ---- experimental (FPT_WIN_TABLE=1, off by default; DESIGN.md §9 item 3, tools/fit_ndtr_table.py) ---------------
 // Phi for |a| < 8 from a shared-memory table of the lower tail on a 1/64 grid and a Hermite-polynomial step:
 //   Phi(-t) = P0 + f0 d (1 + c1 d + c2 d^2 + c3 d^3 + c4 d^4),  d = t0 - t, entry i = {P0 = Phi(-t0), f0 = phi(t0), c1..c4}

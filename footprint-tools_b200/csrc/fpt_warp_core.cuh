@@ -1,0 +1,649 @@
+// fpt_warp_core.cuh — the warp-autonomous scoring kernel of the `ftd detect` / `ftd learn_dm` geometry, written as
+// per-lane steps that the device kernel (fpt_warp.cu) runs with __syncwarp between them and that tests/emu runs lane
+// by lane on the host against the CPU oracle (FPT_HOST_EMU; test infrastructure, never a product path).
+//
+// Reference behaviour reproduced (paths relative to /root/reference):
+//   6-mer bias lookup            footprint_tools/modeling/bias.py:88-111, predict.pyx:47-61,151-153
+//   window sums / expected       footprint_tools/modeling/predict.h:23-74
+//   trimmed-mean smoothing       footprint_tools/modeling/smoothing.h:11-132
+//   crop + strand combine        footprint_tools/modeling/predict.pyx:157-161, cli/detect.py:121-122
+//   NB lower-tail p-value        footprint_tools/modeling/dispersion.pyx:291-316 (table / direct)
+//   Stouffer windows             footprint_tools/stats/windowing.h:53-84, windowing.pyx:34-58
+//   learn_dm histogram           footprint_tools/cli/learn_dm.py:276-287
+//
+// Design: one WARP owns one work item — an interval, or a piece of at most kWC positions of a long
+// one — from the packed track to exp / obs / p and the windowed p-values. Nothing intermediate touches HBM, no
+// block barrier exists: the five steps of an item are separated by __syncwarp only, and the 16 warps of an SM
+// run desynchronised, so that the memory latency of one warp's staging is covered by the arithmetic of the others.
+//   A  stage    cut counts of the item's slots (halo of 56 on both sides), strand-PACKED: slot x = lo16 cuts+[x] |
+//               hi16 cuts-[x-1] (the pair cli/detect.py:121-122 adds); the item's sequence words
+//   B  sums     10-wide window sums of both strands at once (16x2 adds); per group of 4 slots {min, max, sum+, sum-}
+//   C  groups   aggregates over 2, 4, 8 and 24 consecutive groups (ping-pong between two arrays)
+//   D  score    per lane 4 positions: exact integer trimmed sums from two 24-group aggregates + bordering slots,
+//               13 k-mer look-ups per strand, fp32 estimate with a guard band (exact replica inside the band),
+//               strand combine, (exp, obs) table gather, stores of exp / obs / p, z into shared memory
+//   E  windows  multi-scale Stouffer windows from shared-memory z, sums grown outward, branch-free normal tail
+#pragma once
+#include "fpt_internal.h"
+#include "fpt_portable.cuh"
+#include "fpt_warp_host.h"
+
+namespace fpt {
+namespace wk {
+
+constexpr int kWC = 384;                      // c-space capacity of an item (computed positions, 3 rounds of 128)
+constexpr int kWPad = 56;                     // slots staged before and after the computed range (>= 5 + 50 + 1)
+constexpr int kWX = kWC + 2 * kWPad;          // 496 staged slots
+constexpr int kWXG = kWX / 4;                 // 124 groups of 4 slots
+constexpr int kWPre = 8;                      // readable slots before / after the packed-cut array
+constexpr int kWZS = kWC / 4 + 4;             // row stride of the transposed z array (2 pad entries each side)
+constexpr int kWSeqWords = 32, kWMaskWords = 16;
+constexpr unsigned kWPackedCutLimit = 0x3FFu;  // largest cut count the packed format carries
+constexpr int kWHistSubE = 16, kWHistSubO = 64;  // learn_dm bins counted in shared memory first
+
+// per-warp shared memory (11 456 bytes)
+struct alignas(16) WarpSmem {
+    uint32_t cw_[kWPre + kWX + kWPre];   // packed cuts, slot x at cw_[kWPre + x]
+    uint32_t wcw[kWX + 16];              // packed 10-wide sums
+    uint4 GA[kWXG];                      // group aggregates (ping)
+    uint4 GB[kWXG];                      //                  (pong)
+    uint32_t seq[kWSeqWords];            // 2-bit codes of the item's bases, word 0 = bases [B0, B0 + 16)
+    uint32_t msk[kWMaskWords];           // N bits, word 0 = bases [B0, B0 + 32)
+    double zsT[4 * kWZS];                // z of the item, transposed: zsT[e * kWZS + 2 + cg] = z[4 cg + e]
+};
+
+// geometry of one item, identical in every lane
+struct ItemGeo {
+    long long F0;      // flat output index of c = 0 (multiple of 4)
+    long long gbase;   // track coordinate of c = 0
+    long long G0;      // track coordinate of slot x = 0  (gbase - kWPad)
+    long long B0;      // track coordinate of bit 0 of seq[0] / msk[0] (multiple of 32)
+    int T0;            // interval-local index of c = 0 (may be -3 .. 0 for the first piece)
+    int len;           // interval length
+    int cb, cn;        // computed positions: c in [cb, cb + cn)
+    int oa, oz;        // outputs: c in [oa, oz)
+    int NCG, NXG;      // groups of 4 in c-space / x-space
+};
+
+FPT_HD int item_count(long long o0, long long len, int WH) {
+    if (len <= 0) return 0;
+    if (len <= kWC - 3) return 1;
+    const int OS = (kWC - 3 - 2 * WH) & ~3;
+    const long long base = o0 & ~3LL;
+    return (int)((o0 + len - base + OS - 1) / OS);
+}
+
+// piece j of n of an interval: outputs [ta, tb) in interval-local coordinates; pieces start on multiples of 4 of the
+// flat output index so that every lane's group of 4 outputs is one aligned 32-byte store
+FPT_HD void item_range(long long o0, long long len, int WH, int j, int n, int *ta, int *tb) {
+    if (n == 1) { *ta = 0; *tb = (int)len; return; }
+    const int OS = (kWC - 3 - 2 * WH) & ~3;
+    const long long base = o0 & ~3LL;
+    long long fa = base + (long long)j * OS, fb = fa + OS;
+    if (fa < o0) fa = o0;
+    if (fb > o0 + len) fb = o0 + len;
+    *ta = (int)(fa - o0);
+    *tb = (int)(fb - o0);
+}
+
+FPT_HD ItemGeo item_geometry(const WItem &it, int WH) {
+    ItemGeo G;
+    int ca = it.ta - WH, cz = it.tb + WH;
+    if (ca < 0) ca = 0;
+    if (cz > it.len) cz = it.len;
+    G.F0 = (it.o0 + ca) & ~3LL;
+    G.cb = (int)(it.o0 + ca - G.F0);
+    G.cn = cz - ca;
+    G.T0 = (int)(G.F0 - it.o0);
+    G.len = it.len;
+    G.gbase = it.st + G.T0;
+    G.G0 = G.gbase - kWPad;
+    G.B0 = ((G.gbase - 8) >> 5) << 5;  // arithmetic shift: floor for negative coordinates as well
+    G.oa = G.cb + (it.ta - ca);
+    G.oz = G.oa + (it.tb - it.ta);
+    G.NCG = (G.cb + G.cn + 3) >> 2;
+    G.NXG = G.NCG + 2 * kWPad / 4;
+    FPT_EMU_ASSERT(G.cb + G.cn <= kWC && G.NXG <= kWXG);
+    return G;
+}
+
+FPT_HD unsigned lo16(unsigned w) { return w & 0xFFFFu; }
+FPT_HD unsigned hi16(unsigned w) { return w >> 16; }
+FPT_HD uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+FPT_HD uint4 agg(const uint4 a, const uint4 b) {
+    return make_uint4(pt::vminu2(a.x, b.x), pt::vmaxu2(a.y, b.y), a.z + b.z, a.w + b.w);
+}
+
+// ---- step A: stage and pack the cut counts of group xg (slots 4 xg .. 4 xg + 3); returns the OR of the counts ----
+FPT_HD unsigned step_stage(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int xg, bool aligned) {
+    const int x = xg << 2;
+    const long long g = G.G0 + x;
+    uint4 a, b;
+    if (aligned && g >= 0 && g + 4 <= P.n_track) {
+        a = pt::ldg(reinterpret_cast<const uint4 *>(P.cuts_p + g));
+        b = pt::ldg(reinterpret_cast<const uint4 *>(P.cuts_m + g));
+    } else {
+        unsigned av[4], bv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long ge = g + e;
+            const bool ok = ge >= 0 && ge < P.n_track;
+            av[e] = ok ? pt::ldg(P.cuts_p + ge) : 0u;
+            bv[e] = ok ? pt::ldg(P.cuts_m + ge) : 0u;
+        }
+        a = make_uint4(av[0], av[1], av[2], av[3]);
+        b = make_uint4(bv[0], bv[1], bv[2], bv[3]);
+    }
+    const unsigned bm1 = (g >= 1 && g - 1 < P.n_track) ? pt::ldg(P.cuts_m + (g - 1)) : 0u;
+    uint4 w;
+    w.x = pt::pack_lo16(a.x, bm1);
+    w.y = pt::pack_lo16(a.y, b.x);
+    w.z = pt::pack_lo16(a.z, b.y);
+    w.w = pt::pack_lo16(a.w, b.z);
+    *reinterpret_cast<uint4 *>(S.cw_ + kWPre + x) = w;
+    return (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | bm1);
+}
+
+// sequence words of the item: lane l stages seq[l] (bases B0 + 16 l ..) and, for l < 16, msk[l] (bases B0 + 32 l ..);
+// bases outside the track read as N
+FPT_HD void step_stage_seq(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int lane) {
+    const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
+    const long long ws = (G.B0 >> 4) + lane;
+    S.seq[lane] = (ws >= 0 && ws < nw2) ? pt::ldg(P.seq2 + ws) : 0u;
+    if (lane < kWMaskWords) {
+        const long long wm = (G.B0 >> 5) + lane;
+        unsigned v = 0xFFFFFFFFu;
+        if (wm >= 0 && wm < nwm) {
+            v = pt::ldg(P.nmask + wm);
+            const long long left = P.n_track - (wm << 5);  // valid bits of this word
+            if (left < 32) v |= 0xFFFFFFFFu << (int)left;
+        }
+        S.msk[lane] = v;
+    }
+}
+
+// ---- step B: 10-wide window sums of both strands for group xg, level-0 group aggregate ----
+template <bool SMOOTH>
+FPT_HD void step_sums(WarpSmem &S, int xg) {
+    const int x0 = xg << 2;
+    const uint32_t *cw = S.cw_ + kWPre;
+    unsigned c[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 t4 = lds128(cw + x0 - 8 + 4 * q);
+        c[4 * q] = t4.x; c[4 * q + 1] = t4.y; c[4 * q + 2] = t4.z; c[4 * q + 3] = t4.w;
+    }
+    // element e sums slots x0+e-5 .. x0+e+4, i.e. c[3+e] .. c[12+e]
+    using pt::vadd2;
+    const unsigned core = vadd2(vadd2(vadd2(c[6], c[7]), vadd2(c[8], c[9])), vadd2(vadd2(c[10], c[11]), c[12]));
+    const unsigned p45 = vadd2(c[4], c[5]), p34 = vadd2(c[13], c[14]);
+    uint4 w;
+    w.x = vadd2(vadd2(core, c[3]), p45);
+    w.y = vadd2(vadd2(core, p45), c[13]);
+    w.z = vadd2(vadd2(core, c[5]), p34);
+    w.w = vadd2(vadd2(core, p34), c[15]);
+    *reinterpret_cast<uint4 *>(S.wcw + x0) = w;
+    if (SMOOTH) {
+        const unsigned sg = vadd2(vadd2(w.x, w.y), vadd2(w.z, w.w));  // <= 4 * 10230 per half
+        S.GA[xg] = make_uint4(pt::vminu2(pt::vminu2(w.x, w.y), pt::vminu2(w.z, w.w)),
+                              pt::vmaxu2(pt::vmaxu2(w.x, w.y), pt::vmaxu2(w.z, w.w)), lo16(sg), hi16(sg));
+    }
+}
+
+// ---- the reference's own operation order, for the guard band of step D (rare) -------------------------------------
+constexpr int kWSmoothMax = 101;
+
+// smoothing.h:11-53 on a lane-local buffer
+FPT_HD double nr_select(double *arr, unsigned n, unsigned k) {
+    unsigned lo = 0, hi = n - 1;
+    for (;;) {
+        if (hi <= lo + 1) {
+            if (hi == lo + 1 && arr[hi] < arr[lo]) { double t = arr[lo]; arr[lo] = arr[hi]; arr[hi] = t; }
+            return arr[k];
+        }
+        unsigned mid = (lo + hi) >> 1;
+        double t;
+        t = arr[mid]; arr[mid] = arr[lo + 1]; arr[lo + 1] = t;
+        if (arr[lo] > arr[hi]) { t = arr[lo]; arr[lo] = arr[hi]; arr[hi] = t; }
+        if (arr[lo + 1] > arr[hi]) { t = arr[lo + 1]; arr[lo + 1] = arr[hi]; arr[hi] = t; }
+        if (arr[lo] > arr[lo + 1]) { t = arr[lo]; arr[lo] = arr[lo + 1]; arr[lo + 1] = t; }
+        unsigned i = lo + 1, j = hi;
+        double piv = arr[lo + 1];
+        for (;;) {
+            do i++; while (arr[i] < piv);
+            do j--; while (arr[j] > piv);
+            if (j < i) break;
+            t = arr[i]; arr[i] = arr[j]; arr[j] = t;
+        }
+        arr[lo + 1] = arr[j];
+        arr[j] = piv;
+        if (j >= k) hi = j - 1;
+        if (j <= k) lo = i;
+    }
+}
+
+// Bit-faithful trimmed_mean (smoothing.h:59-104) of one strand's window sums wcw[i0 .. i0+w)
+static FPT_NOINLINE_HD double trimmed_mean_packed(const uint32_t *wcw, int strand, int i0, int w, int k) {
+    double buf[kWSmoothMax];
+    for (int j = 0; j < w; ++j) buf[j] = (double)(strand ? hi16(wcw[i0 + j]) : lo16(wcw[i0 + j]));
+    double os1 = nr_select(buf, w, k);
+    double os2 = nr_select(buf, w, w - k - 1);
+    double b = 0, d = 0, dm = 0, bm = 0;
+    for (int j = 0; j < w; ++j) {
+        double v = buf[j];
+        if (v < os1) bm += 1; else if (v == os1) b += 1;
+        if (v < os2) dm += 1; else if (v == os2) d += 1;
+    }
+    double w1 = pt::ddiv(b + bm - (double)k, b);
+    double w2 = pt::ddiv((double)(w - k) - dm, d);
+    double t = 0;
+    for (int j = 0; j < w; ++j) {
+        double v = buf[j], c;
+        if (v < os2 && v > os1) c = v;
+        else if (v < os1) c = 0;
+        else if (v > os2) c = 0;
+        else if (v == os1) c = pt::dmul(w1, v);
+        else c = pt::dmul(w2, v);
+        t = pt::dadd(t, c);
+    }
+    return pt::ddiv(t, (double)(w - 2 * k));
+}
+
+// predict.h:41-63 for one strand of one output position, from what the lane already holds: kw / rcw / nw = its
+// 18-base window (codes, reverse complement, N bits) whose k-mer m starts at base g0-8+m, e = element (0..3),
+// T = its exact trimmed window sum. The ten propensities of the window are k-mers e .. e+9, the position's own e+5.
+static FPT_NOINLINE_HD double expected_exact(const double *tab, double dflt, int uniform, unsigned long long kw, unsigned long long rcw,
+                      unsigned nw, int e, int strand, unsigned T, const uint32_t *wcw, int slot, int shw) {
+    double pd[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int m = e + i;
+        const unsigned km = strand ? (unsigned)(rcw >> (24 - 2 * m)) & 0xFFFu : (unsigned)(kw >> (2 * m)) & 0xFFFu;
+        pd[i] = uniform ? 1.0 : (((nw >> m) & 0x3Fu) ? dflt : pt::ldg(tab + km));
+    }
+    double wp = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) wp = pt::dadd(wp, pd[i]);
+    const double ratio = pt::ddiv(pd[5], wp);
+    double sm;
+    if (shw == 0) {
+        sm = (double)T;
+    } else {
+        // second tier: everything but the trimmed sum is in the reference's own order; the integer trimmed sum
+        // differs from the reference's float one by < 1e-14 relative (tie weights)
+        const int w = 2 * shw + 1;
+        const double v = pt::dmul(ratio, pt::ddiv((double)T, (double)(w - 2)));
+        const double rr = rint(v), av = fabs(v);
+        if ((av < 4.0e15) && (fabs(v - rr) < pt::dadd(pt::dmul(av, -4e-12), 0.5 - 4e-12))) return rr;
+        sm = trimmed_mean_packed(wcw, strand, slot - shw, w, 1);
+    }
+    return round(pt::dmul(ratio, sm));
+}
+
+// ---- step D: the 4 positions c0 .. c0+3 of group cg -------------------------------------------------------------
+// Env supplies what differs between the device and the host emulation: the direct NB evaluation, the 256-bit
+// store, the atomics.
+template <bool SMOOTH, class Env>
+FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, const float *tab, const double *dmp,
+                       unsigned *hsub, int cg, bool want_p, bool want_z, Env &env) {
+    constexpr int SHW = SMOOTH ? 50 : 0;
+    constexpr int WSM = 2 * SHW + 1;
+    const float dWf = SMOOTH ? (float)(WSM - 2) : 1.0f;
+    const int c0 = cg << 2;
+    // elements e with lo <= c0 + e < hi
+    auto range4 = [&](int lo, int hi) {
+        const int a = lo - c0 > 0 ? lo - c0 : 0, b = hi - c0 < 4 ? hi - c0 : 4;
+        return b > a ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+    };
+    const unsigned vmask = range4(G.cb, G.cb + G.cn);   // computed positions
+    const unsigned omask = vmask & range4(G.oa, G.oz);  // outputs of this item
+    const int x0 = c0 + kWPad;
+    const uint32_t *cw = S.cw_ + kWPre;
+    const uint32_t *wcw = S.wcw;
+
+    // -- the lane's 18-base window: bases g0-8 .. g0+9 (k-mer m starts at base g0-8+m)
+    unsigned long long kw = 0, rcw = 0;
+    unsigned nw = 0;
+    if (!P.uniform) {
+        const int q = (int)(G.gbase - 8 - G.B0) + c0;  // bit position of base g0-8 in the staged words
+        FPT_EMU_ASSERT(q >= 0 && (q >> 4) + 2 < kWSeqWords && (q >> 5) + 1 < kWMaskWords);
+        const int w = q >> 4, wm = q >> 5, sh = (q & 15) * 2;
+        const unsigned s0 = S.seq[w], s1 = S.seq[w + 1], s2 = S.seq[w + 2];
+        const unsigned lo32 = pt::funnel_r(s0, s1, sh), hi32 = pt::funnel_r(s1, s2, sh);
+        kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
+        nw = pt::funnel_r(S.msk[wm], S.msk[wm + 1], q & 31) & 0x3FFFFu;
+        unsigned long long t = pt::brevll(kw) >> 28;
+        t = ((t & 0xAAAAAAAAAull) >> 1) | ((t & 0x555555555ull) << 1);
+        rcw = t ^ 0xFFFFFFFFFull;
+    }
+
+    // -- trimmed window sums T[strand][e] (exact integers)
+    unsigned Tl[4], Th[4];
+    if (!SMOOTH) {
+        const uint4 w = lds128(wcw + x0);
+        Tl[0] = lo16(w.x); Tl[1] = lo16(w.y); Tl[2] = lo16(w.z); Tl[3] = lo16(w.w);
+        Th[0] = hi16(w.x); Th[1] = hi16(w.y); Th[2] = hi16(w.z); Th[3] = hi16(w.w);
+    } else {
+        // windows of elements 0..3 = slots [x0+e-50, x0+e+50]; with g = x0/4 and G(k) = group g+k:
+        //   e=0: G(-13)[2,3] + G(-12..+11) + G(+12)[0,1,2]      e=1: G(-13)[3] + G(-12..+12)
+        //   e=2: G(-12..+12) + G(+13)[0]                        e=3: G(-12)[1,2,3] + G(-11..+12) + G(+13)[0,1]
+        using pt::vmaxu2;
+        using pt::vminu2;
+        using pt::vadd2;
+        const int g = x0 >> 2;
+        FPT_EMU_ASSERT(g - 12 >= 0 && g - 11 + 24 <= G.NXG && x0 + 56 <= 4 * G.NXG);
+        const uint4 Ha = S.GA[g - 12], Hb = S.GA[g - 11];
+        const uint4 Lq = lds128(wcw + x0 - 52), Aq = lds128(wcw + x0 - 48);
+        const uint4 Bq = lds128(wcw + x0 + 48), Rq = lds128(wcw + x0 + 52);
+        unsigned mn[4], mx[4];
+        {
+            const unsigned tL = vminu2(Lq.z, Lq.w), tb = vminu2(vminu2(Bq.x, Bq.y), Bq.z);
+            const unsigned ta = vminu2(vminu2(Aq.y, Aq.z), Aq.w), tr = vminu2(Rq.x, Rq.y);
+            const unsigned hab = vminu2(Ha.x, vminu2(tb, Bq.w));
+            mn[0] = vminu2(vminu2(Ha.x, tL), tb);
+            mn[1] = vminu2(hab, Lq.w);
+            mn[2] = vminu2(hab, Rq.x);
+            mn[3] = vminu2(vminu2(Hb.x, ta), tr);
+        }
+        {
+            const unsigned tL = vmaxu2(Lq.z, Lq.w), tb = vmaxu2(vmaxu2(Bq.x, Bq.y), Bq.z);
+            const unsigned ta = vmaxu2(vmaxu2(Aq.y, Aq.z), Aq.w), tr = vmaxu2(Rq.x, Rq.y);
+            const unsigned hab = vmaxu2(Ha.y, vmaxu2(tb, Bq.w));
+            mx[0] = vmaxu2(vmaxu2(Ha.y, tL), tb);
+            mx[1] = vmaxu2(hab, Lq.w);
+            mx[2] = vmaxu2(hab, Rq.x);
+            mx[3] = vmaxu2(vmaxu2(Hb.y, ta), tr);
+        }
+        const unsigned p0 = vadd2(vadd2(vadd2(Bq.x, Bq.y), Bq.z), vadd2(Lq.z, Lq.w));  // <= 5 * 10230
+        unsigned Sl[4], Sh[4];
+        Sl[0] = Ha.z + lo16(p0);                 Sh[0] = Ha.w + hi16(p0);
+        Sl[1] = Sl[0] + lo16(Bq.w) - lo16(Lq.z); Sh[1] = Sh[0] + hi16(Bq.w) - hi16(Lq.z);
+        Sl[2] = Sl[1] + lo16(Rq.x) - lo16(Lq.w); Sh[2] = Sh[1] + hi16(Rq.x) - hi16(Lq.w);
+        Sl[3] = Sl[2] + lo16(Rq.y) - lo16(Aq.x); Sh[3] = Sh[2] + hi16(Rq.y) - hi16(Aq.x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            // sum - min - max, except that when all but one copy of the minimum equal the maximum the reference never
+            // reaches its second weight (smoothing.h:59-70): sum - min
+            const unsigned mnl = lo16(mn[e]), mxl = lo16(mx[e]), mnh = hi16(mn[e]), mxh = hi16(mx[e]);
+            unsigned tl = Sl[e] - mnl - mxl, th = Sh[e] - mnh - mxh;
+            if (tl == (unsigned)(WSM - 2) * mxl) tl += mxl;
+            if (th == (unsigned)(WSM - 2) * mxh) th += mxh;
+            Tl[e] = tl; Th[e] = th;
+        }
+    }
+
+    // -- the 13 k-mers starting at bases g0-8 .. g0+4 serve both strands: plus-strand position g0-5+m and
+    //    minus-strand position g0-6+m use k-mer m. Both strands ride in one f32x2 (plus low, minus high): the window
+    //    sums of propensities, the estimate and its rounding are FADD2 / FMUL2 / FFMA2, one instruction for both.
+    //    (uniform model: the table holds 1.0 everywhere and kw = rcw = nw = 0)
+    const float dflt_f = (float)P.dflt;
+    int exi[4] = {0, 0, 0, 0};  // plus[t+1] + minus[t] (cli/detect.py:121-122)
+    unsigned redo = 0;          // bit 4*s + e: strand s of element e needs the out-of-line evaluation
+    {
+        pt::f32x2 Pv[13];
+        const unsigned kwl = (unsigned)kw, kwh = (unsigned)(kw >> 32);       // bases 0..15, 16..17
+        const unsigned rcl = (unsigned)rcw, rch = (unsigned)(rcw >> 32);
+#pragma unroll
+        for (int m = 0; m < 13; ++m) {
+            // k-mer m of the window, and of its reverse complement (12 bits from bit 2m / 24 - 2m)
+            const unsigned kp = (m <= 10 ? (kwl >> (2 * m)) : pt::funnel_r(kwl, kwh, 2 * m)) & 0xFFFu;
+            const unsigned km = (24 - 2 * m <= 20 ? (rcl >> (24 - 2 * m)) : pt::funnel_r(rcl, rch, 24 - 2 * m)) & 0xFFFu;
+            Pv[m] = pt::pack2(tab[kp], tab[km]);
+        }
+        if (nw != 0) {
+            const pt::f32x2 d2 = pt::pack2(dflt_f, dflt_f);
+#pragma unroll
+            for (int m = 0; m < 13; ++m)
+                if ((nw >> m) & 0x3Fu) Pv[m] = d2;
+        }
+        pt::f32x2 wp[4];
+        {
+            pt::f32x2 s2[12], s4[8];
+#pragma unroll
+            for (int m = 0; m < 12; ++m) s2[m] = pt::add2(Pv[m], Pv[m + 1]);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) s4[m] = pt::add2(s2[m], s2[m + 2]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) wp[e] = pt::add2(pt::add2(s4[e], s4[e + 4]), s2[e + 8]);
+        }
+        // -- expected count estimate in single precision; magic-number rounding (v < 2^22)
+        const pt::f32x2 dW2 = pt::pack2(dWf, dWf), magic = pt::pack2(12582912.0f, 12582912.0f);
+        const pt::f32x2 nmagic = pt::pack2(-12582912.0f, -12582912.0f), neg1 = pt::pack2(-1.0f, -1.0f);
+        const pt::f32x2 slope = pt::pack2(-3e-6f, -3e-6f), half = pt::pack2(0.5f - 3e-6f, 0.5f - 3e-6f);
+        const pt::f32x2 n2p23 = pt::pack2(-8388608.0f, -8388608.0f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            // exact for T < 2^23
+            const pt::f32x2 Tf = pt::add2(pt::pack2(pt::uint_as_float(Tl[e] | 0x4B000000u), pt::uint_as_float(Th[e] | 0x4B000000u)), n2p23);
+            const pt::f32x2 den = pt::mul2(wp[e], dW2);
+            const pt::f32x2 rc = pt::pack2(pt::rcp_approx(pt::lo2(den)), pt::rcp_approx(pt::hi2(den)));
+            const pt::f32x2 v = pt::mul2(pt::mul2(Pv[e + 5], Tf), rc);
+            const pt::f32x2 vr = pt::add2(v, magic);
+            const pt::f32x2 rf = pt::add2(vr, nmagic);
+            const pt::f32x2 dv = pt::fma2(rf, neg1, v);          // v - rint(v)
+            const pt::f32x2 th = pt::fma2(v, slope, half);       // guard band: false for NaN and v > 1.6e5
+            if (fabsf(pt::lo2(dv)) < pt::lo2(th)) exi[e] += pt::float_as_int(pt::lo2(vr)) - 0x4B400000;
+            else redo |= 1u << e;
+            if (fabsf(pt::hi2(dv)) < pt::hi2(th)) exi[e] += pt::float_as_int(pt::hi2(vr)) - 0x4B400000;
+            else redo |= 1u << (4 + e);
+        }
+    }
+    redo &= vmask | (vmask << 4);
+    if (redo) {  // rare; kept out of the loops above so that nothing is live across the calls
+        for (unsigned m = redo; m; m &= m - 1) {
+            const int b = pt::ffs32(m) - 1, s = b >> 2, e = b & 3;
+            const unsigned Te = s ? (e == 0 ? Th[0] : e == 1 ? Th[1] : e == 2 ? Th[2] : Th[3])
+                                  : (e == 0 ? Tl[0] : e == 1 ? Tl[1] : e == 2 ? Tl[2] : Tl[3]);
+            const double res = expected_exact(P.bias, P.dflt, P.uniform, kw, rcw, nw, e, s, Te, wcw, x0 + e, SHW);
+            const int ri = (int)res;
+            if (e == 0) exi[0] += ri;
+            else if (e == 1) exi[1] += ri;
+            else if (e == 2) exi[2] += ri;
+            else exi[3] += ri;
+        }
+    }
+
+    // -- observed counts, p-value table look-ups (always from a valid entry; positions outside the table are
+    //    overwritten by the direct evaluation below)
+    const uint4 cq = lds128(cw + x0);
+    const unsigned cwv[4] = {cq.x, cq.y, cq.z, cq.w};
+    int obi[4];
+    double pvv[4], zv[4];
+    unsigned direct = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        obi[e] = (int)(lo16(cwv[e]) + hi16(cwv[e]));
+        pvv[e] = 1.0;
+        zv[e] = 0.0;
+    }
+    if (want_p) {
+        if (P.lut_e > 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool in = (unsigned)exi[e] < (unsigned)P.lut_e && (unsigned)obi[e] < (unsigned)P.lut_o;
+                const double2 e2 = pt::ldg(P.lut + (in ? (unsigned)(exi[e] * P.lut_o + obi[e]) : 0u));
+                pvv[e] = e2.x; zv[e] = e2.y;
+                if (!in) direct |= 1u << e;
+            }
+            direct &= vmask;
+        } else {
+            direct = vmask;
+        }
+    }
+    const long long f0 = G.F0 + c0;
+    {
+        const double exv[4] = {(double)exi[0], (double)exi[1], (double)exi[2], (double)exi[3]};
+        const double obv[4] = {(double)obi[0], (double)obi[1], (double)obi[2], (double)obi[3]};
+        if (omask == 0xFu && P.vec_ok) {
+            if (P.exp_out) env.st256(P.exp_out + f0, exv[0], exv[1], exv[2], exv[3]);
+            if (P.obs_out) env.st256(P.obs_out + f0, obv[0], obv[1], obv[2], obv[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((omask >> e) & 1u) {
+                    if (P.exp_out) P.exp_out[f0 + e] = exv[e];
+                    if (P.obs_out) P.obs_out[f0 + e] = obv[e];
+                }
+        }
+    }
+    if (P.hist) {
+        // learn_dm histogram (cli/learn_dm.py:276-287): the low bins in a shared-memory sub-histogram, flushed once per
+        // CTA; the rest straight to global memory
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (((omask >> e) & 1u) && exi[e] < P.hist_d0 && obi[e] < P.hist_d1) {
+                if (exi[e] < kWHistSubE && obi[e] < kWHistSubO) env.atomic_inc_shared(&hsub[exi[e] * kWHistSubO + obi[e]]);
+                else env.atomic_inc_u64(P.hist + (size_t)exi[e] * P.hist_d1 + obi[e]);
+            }
+    }
+    if (direct) {  // outside the table: evaluated in place — only this warp waits for it
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+            if (!((direct >> e) & 1u)) continue;
+            const double ex = (double)(e == 0 ? exi[0] : e == 1 ? exi[1] : e == 2 ? exi[2] : exi[3]);
+            const int kobs = e == 0 ? obi[0] : e == 1 ? obi[1] : e == 2 ? obi[2] : obi[3];
+            double pv, z;
+            env.direct_pz(dmp, ex, kobs, &pv, &z);
+            if (e == 0) { pvv[0] = pv; zv[0] = z; }
+            else if (e == 1) { pvv[1] = pv; zv[1] = z; }
+            else if (e == 2) { pvv[2] = pv; zv[2] = z; }
+            else { pvv[3] = pv; zv[3] = z; }
+        }
+    }
+    if (P.pval_out && omask) {
+        if (omask == 0xFu && P.vec_ok) env.st256(P.pval_out + f0, pvv[0], pvv[1], pvv[2], pvv[3]);
+        else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((omask >> e) & 1u) P.pval_out[f0 + e] = pvv[e];
+        }
+    }
+    if (want_z) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) S.zsT[e * kWZS + 2 + cg] = ((vmask >> e) & 1u) ? zv[e] : 0.0;
+    }
+}
+
+// ---- step E: multi-scale Stouffer windows (windowing.h:53-67) of the 4 outputs of group cg from shared-memory z ----
+// z is stored transposed (element index major) so that lane-consecutive groups read consecutive doubles. Sums grow
+// outward from the centre, S_h = S_{h-1} + (z[-h] + z[+h]); the edge rule of windowing.pyx:51-54 sets positions
+// closer than h to an interval end to 1.0. WM selects the half-widths: 1 = {3} (cli/detect.py:84), 2 = {3, 5, 7}
+// (BASELINE.json config C3), both unrolled at compile time; 3 = up to three ascending half-widths given at run time
+// (P.win_h). The normal tails of the up to three sums are evaluated in a ROLLED loop: one copy of the ~270
+// instructions of ndtr4 in the kernel instead of one per half-width (16 desynchronised warps share the SM's
+// instruction cache).
+template <int WM, class Env>
+FPT_HD void step_windows(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int cg, Env &env) {
+    constexpr int HTOP = WM == 1 ? 3 : (WM == 2 ? 7 : kFastMaxScaleHalfWin);
+    const int c0 = cg << 2;
+    const int a = G.oa - c0 > 0 ? G.oa - c0 : 0, b = G.oz - c0 < 4 ? G.oz - c0 : 4;
+    if (b <= a) return;
+    const unsigned omask = ((1u << b) - 1u) & ~((1u << a) - 1u);
+    const long long f0 = G.F0 + c0;
+    const int dl = G.T0 + c0, dr = G.len - 1 - dl;  // interval-local index of element 0 and its distance from the end
+    const double *zt = S.zsT + 2 + cg;
+    int h0 = WM == 3 ? P.win_h[0] : 3, h1 = WM == 3 ? P.win_h[1] : (WM == 2 ? 5 : -1), h2 = WM == 3 ? P.win_h[2] : (WM == 2 ? 7 : -1);
+    const int ns = WM == 3 ? P.n_win_h : (WM == 2 ? 3 : 1);
+    double A0[4] = {0.0, 0.0, 0.0, 0.0}, A1[4] = {0.0, 0.0, 0.0, 0.0}, A2[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+        double acc[4], Lw[4], Rw[4];  // Lw[e] = z[e - h], Rw[e] = z[e + h]
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = Lw[e] = Rw[e] = zt[e * kWZS];
+#pragma unroll
+        for (int h = 0; h <= HTOP; ++h) {
+            if (WM == 3 && h > P.wh_max) break;
+            if (h > 0) {
+                // element index j = -h on the left, 3 + h on the right: row j & 3, group offset j >> 2
+                const double zl = zt[((-h) & 3) * kWZS + ((-h) >> 2)];
+                const double zr = zt[((3 + h) & 3) * kWZS + ((3 + h) >> 2)];
+                Lw[3] = Lw[2]; Lw[2] = Lw[1]; Lw[1] = Lw[0]; Lw[0] = zl;
+                Rw[0] = Rw[1]; Rw[1] = Rw[2]; Rw[2] = Rw[3]; Rw[3] = zr;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] += Lw[e] + Rw[e];
+            }
+            const double cneg = -P.inv_sqrt_k[h];
+            if (h == h0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) A0[e] = acc[e] * cneg;
+            }
+            if (h == h1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) A1[e] = acc[e] * cneg;
+            }
+            if (h == h2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) A2[e] = acc[e] * cneg;
+            }
+        }
+    }
+#pragma unroll 1
+    for (int k = 0; k < ns; ++k) {
+        double res[4];
+        env.ndtr4(A0, res);
+        const int h = h0;
+        if (dl < h || dr < h + 3) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (dl + e < h || dr - e < h) res[e] = 1.0;
+        }
+        for (unsigned m = P.h_rows[h]; m; m &= m - 1) {
+            const int s = pt::ffs32(m) - 1;
+            double *dst = P.winp_out + (size_t)s * P.total + f0;
+            if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) {
+                env.st256(dst, res[0], res[1], res[2], res[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((omask >> e) & 1u) dst[e] = res[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { A0[e] = A1[e]; A1[e] = A2[e]; }
+        h0 = h1; h1 = h2;
+    }
+}
+
+// ---- one item, all five steps. W runs a per-lane body on every lane of the warp and synchronises the warp after
+// it (device: the calling lane + __syncwarp; host emulation: a loop over 32 lanes). Returns false when the item holds
+// a cut count the packed format cannot carry (nothing was written: the caller hands the item to the general kernel).
+template <bool SMOOTH, int WM, class W, class Env>
+FPT_HD bool process_item(const ScoreParams &P, const WItem &it, WarpSmem &S, const float *tab, const double *dmp,
+                         unsigned *hsub, W &warp, Env &env) {
+    constexpr bool want_win = WM != 0;
+    const bool want_p = (P.pval_out != nullptr) || want_win;
+    const ItemGeo G = item_geometry(it, want_win ? P.wh_max : 0);
+    const bool aligned = P.cuts_vec && ((G.G0 & 3) == 0);
+    const unsigned seen = warp.or_reduce([&](int lane) {
+        unsigned s = 0;
+        for (int xg = lane; xg < G.NXG; xg += 32) s |= step_stage(P, G, S, xg, aligned);
+        if (!P.uniform) step_stage_seq(P, G, S, lane);
+        if (want_win && lane < 16) {  // the 2 + 2 pad entries of each z row
+            const int e = lane >> 2, k = lane & 3;
+            S.zsT[e * kWZS + (k < 2 ? k : G.NCG + k)] = 0.0;
+        }
+        return s;
+    });
+    if (seen & ~kWPackedCutLimit) return false;
+    warp.each([&](int lane) {
+        for (int xg = lane; xg < G.NXG; xg += 32) step_sums<SMOOTH>(S, xg);
+    });
+    if (SMOOTH) {
+        const int n1 = G.NXG - 1, n2 = G.NXG - 3, n3 = G.NXG - 7, n4 = G.NXG - 23;
+        warp.each([&](int lane) { for (int g = lane; g < n1; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 1]); });
+        warp.each([&](int lane) { for (int g = lane; g < n2; g += 32) S.GA[g] = agg(S.GB[g], S.GB[g + 2]); });
+        warp.each([&](int lane) { for (int g = lane; g < n3; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 4]); });
+        warp.each([&](int lane) { for (int g = lane; g < n4; g += 32) S.GA[g] = agg(agg(S.GB[g], S.GB[g + 8]), S.GB[g + 16]); });
+    }
+    warp.each([&](int lane) {
+        for (int cg = lane; cg < G.NCG; cg += 32) step_score<SMOOTH>(P, G, S, tab, dmp, hsub, cg, want_p, want_win, env);
+    });
+    if (want_win) {
+        warp.each([&](int lane) {
+            for (int cg = lane; cg < G.NCG; cg += 32) step_windows<WM == 0 ? 1 : WM>(P, G, S, cg, env);
+        });
+    }
+    return true;
+}
+
+}  // namespace wk
+}  // namespace fpt

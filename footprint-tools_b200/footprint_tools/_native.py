@@ -208,7 +208,8 @@ class Context(object):
         _check(lib().fpt_ctx_last_transfer(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
-    KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo", "direct_fix", "fdr")
+    KERNELS = ("plan", "score_fast", "window_fast", "score_general", "score_fused", "redo", "direct_fix", "fdr",
+               "score_warp")
 
     def profile(self, enable=True):
         """Turn the per-kernel CUDA-event timers on or off (fpt_ctx_profile)."""

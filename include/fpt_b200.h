@@ -85,7 +85,8 @@ int64_t fpt_ctx_launch_count(const fpt_ctx *ctx);
 #define FPT_KERNEL_REDO 5          /* general kernel over the tiles the fused kernel handed back */
 #define FPT_KERNEL_DIRECT_FIX 6    /* NB p-values of the positions outside the (exp, obs) table */
 #define FPT_KERNEL_FDR 7           /* null sampling + windows + empirical FDR, one CTA per interval */
-#define FPT_KERNEL_COUNT 8
+#define FPT_KERNEL_SCORE_WARP 8    /* warp-autonomous fused kernel: track -> exp / obs / p / windowed p in one launch */
+#define FPT_KERNEL_COUNT 9
 int fpt_ctx_profile(fpt_ctx *ctx, int enable);
 /* Bytes the last FPT_MEM_HOST fpt_score call copied host->device and device->host (expected and
  * observed counts cross as uint32 and are widened to float64 on the host in the pipelined path). */

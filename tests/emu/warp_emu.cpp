@@ -1,0 +1,152 @@
+// TEST INFRASTRUCTURE ONLY. Host emulation of the warp-autonomous scoring kernel: the per-lane steps of
+// footprint-tools_b200/csrc/fpt_warp_core.cuh compiled by g++ (FPT_HOST_EMU) and run lane by lane, item by item, so
+// that the kernel's indexing, masks, packing, trimmed sums, guard band, piece planning and edge rules are checked
+// against the CPU oracle in the container that has no GPU (tests/test_warp_emu.py). The NB p-values outside the
+// table and the normal tail come from the oracle here; on the device they are the kernel's own functions.
+// Nothing under footprint-tools_b200/ builds, links or loads this file.
+#define FPT_HOST_EMU 1
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <vector_functions.h>
+
+#include "fpt_warp_core.cuh"
+
+extern "C" {
+double orc_nb_cdf(int k, double p, double r);
+double orc_fit_mu(const double *mu_params, double x);
+double orc_fit_r(const double *r_params, double x);
+double orc_ndtri(double y);
+double orc_ndtr(double a);
+}
+
+namespace {
+
+using namespace fpt;
+using namespace fpt::wk;
+
+struct HostWarp {
+    template <class F>
+    void each(F f) {
+        for (int lane = 0; lane < 32; ++lane) f(lane);
+    }
+    template <class F>
+    unsigned or_reduce(F f) {
+        unsigned v = 0;
+        for (int lane = 0; lane < 32; ++lane) v |= f(lane);
+        return v;
+    }
+};
+
+struct HostEnv {
+    long long n_direct = 0;
+    void st256(double *p, double a, double b, double c, double d) {
+        FPT_EMU_ASSERT((reinterpret_cast<uintptr_t>(p) & 31) == 0);
+        p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+    }
+    void atomic_inc_shared(unsigned *p) { *p += 1; }
+    void atomic_inc_u64(unsigned long long *p) { *p += 1; }
+    void direct_pz(const double *dmp, double ex, int kobs, double *pv, double *z) {
+        const double rr = orc_fit_r(dmp + 9, ex), mu = orc_fit_mu(dmp, ex);
+        const double p = orc_nb_cdf(kobs, rr / (rr + mu), rr);
+        *pv = p;
+        *z = orc_ndtri(1.0 - p);
+        ++n_direct;
+    }
+    void ndtr4(const double (&a)[4], double (&res)[4]) {
+        for (int e = 0; e < 4; ++e) res[e] = orc_ndtr(a[e]);
+    }
+};
+
+}  // namespace
+
+// Scores a batch exactly as score_device + score_warp_kernel would. bias_le: 4096 doubles, little-endian k-mer index;
+// dm: 24 doubles; lut: lut_e x lut_o (p, z) pairs or NULL. Returns the number of items handed to the general kernel
+// (their ranges are written to redo_ranges, 3 long long each, capacity redo_cap), or -1 on a geometry this kernel
+// does not serve. stats[0] = items, stats[1] = direct evaluations.
+extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double dflt, int uniform, const double *dm,
+                         const double *lut, int lut_e, int lut_o, long long *redo_ranges, int redo_cap, long long *stats) {
+    const int hw = a->half_win_width, shw = a->smoothing_half_win_width;
+    const int wsm = 2 * shw + 1;
+    const int ktrim = shw > 0 ? (int)((double)wsm * a->smoothing_clip) : 0;
+    int wh_max = 0;
+    ScoreParams p;
+    memset(&p, 0, sizeof p);
+    for (int s = 0; s < a->n_scales; ++s)
+        if (a->win_half_width[s] > wh_max) wh_max = a->win_half_width[s];
+    if (!a->winp_out) wh_max = 0;
+    if (!warp_geometry_ok(hw, shw, ktrim, wh_max, a->combine_strands != 0, a->win_out != nullptr)) return -1;
+    p.seq2 = a->seq2; p.nmask = a->nmask; p.cuts_p = a->cuts_plus; p.cuts_m = a->cuts_minus;
+    p.n_track = a->n_track;
+    p.iv_start = reinterpret_cast<const long long *>(a->iv_start);
+    p.out_off = reinterpret_cast<const long long *>(a->out_off);
+    p.n_iv = a->n_iv; p.total = a->total;
+    p.hw = hw; p.shw = shw; p.ktrim = ktrim; p.combine = 1;
+    p.n_scales = a->winp_out ? a->n_scales : 0;
+    p.bias = bias_le; p.dflt = dflt; p.uniform = uniform;
+    p.dm = dm; p.lut = reinterpret_cast<const double2 *>(lut); p.lut_e = lut ? lut_e : 0; p.lut_o = lut ? lut_o : 0;
+    p.exp_out = a->exp_out; p.obs_out = a->obs_out; p.pval_out = a->pval_out; p.winp_out = a->winp_out;
+    p.hist = reinterpret_cast<unsigned long long *>(a->hist);
+    p.hist_d0 = a->hist_d0; p.hist_d1 = a->hist_d1;
+    if (!warp_params_finish(p, a, wh_max)) return -1;
+
+    // planner (plan_items_kernel)
+    std::vector<WItem> items;
+    for (long long k = 0; k < p.n_iv; ++k) {
+        const long long o0 = p.out_off[k], len = p.out_off[k + 1] - o0;
+        const int cnt = item_count(o0, len, p.wh_max);
+        for (int j = 0; j < cnt; ++j) {
+            WItem it;
+            it.o0 = o0; it.st = p.iv_start[k]; it.len = (int)len; it.iv = (int)k;
+            item_range(o0, len, p.wh_max, j, cnt, &it.ta, &it.tb);
+            items.push_back(it);
+        }
+    }
+    // one "SM": the fp32 table, the model, a sub-histogram and one warp's shared memory, poisoned before every item
+    std::vector<float> tab(4096, 0.f);  // 1.0 everywhere for the uniform model
+    for (int i = 0; i < 4096; ++i) tab[i] = uniform ? 1.0f : (float)bias_le[i];
+    double dmp[kModelDoubles];
+    for (int i = 0; i < kModelDoubles; ++i) dmp[i] = dm ? dm[i] : 0.0;
+    std::vector<unsigned> hsub(kWHistSubE * kWHistSubO, 0u);
+    WarpSmem *S = static_cast<WarpSmem *>(aligned_alloc(64, sizeof(WarpSmem)));
+    HostWarp W;
+    HostEnv env;
+    int n_redo = 0;
+    for (const WItem &it : items) {
+        memset(S, 0xEE, sizeof(WarpSmem));  // anything read before it is written is loud
+        bool ok;
+#define EMU_RUN(SM, WMODE) ok = process_item<SM, WMODE>(p, it, *S, tab.data(), dmp, hsub.data(), W, env)
+        if (shw != 0) {
+            switch (p.wmode) {
+                case 0: EMU_RUN(true, 0); break;
+                case 1: EMU_RUN(true, 1); break;
+                case 2: EMU_RUN(true, 2); break;
+                default: EMU_RUN(true, 3); break;
+            }
+        } else {
+            switch (p.wmode) {
+                case 0: EMU_RUN(false, 0); break;
+                case 1: EMU_RUN(false, 1); break;
+                case 2: EMU_RUN(false, 2); break;
+                default: EMU_RUN(false, 3); break;
+            }
+        }
+#undef EMU_RUN
+        if (!ok) {
+            if (n_redo < redo_cap) {
+                redo_ranges[3 * n_redo] = it.o0 + it.ta;
+                redo_ranges[3 * n_redo + 1] = it.o0 + it.tb;
+                redo_ranges[3 * n_redo + 2] = it.iv;
+            }
+            ++n_redo;
+        }
+    }
+    if (p.hist)
+        for (int i = 0; i < kWHistSubE * kWHistSubO; ++i)
+            p.hist[(size_t)(i / kWHistSubO) * p.hist_d1 + (i % kWHistSubO)] += hsub[i];
+    free(S);
+    if (stats) { stats[0] = (long long)items.size(); stats[1] = env.n_direct; }
+    return n_redo;
+}

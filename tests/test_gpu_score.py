@@ -394,16 +394,17 @@ def test_host_pipeline_equals_single_shot(table, shuffled):
 
 
 def test_scoring_paths_agree(table, oracle):
-    """The general kernel, the two-kernel throughput path and the fused kernel (windows streamed or in
-    the kernel) give identical exp / obs / p / histogram and windowed p-values within the parity bar; a
+    """The general kernel, the two-kernel throughput path, the CTA-tiled fused kernel (windows streamed or in
+    the kernel) and the warp-autonomous kernel (the default) give identical exp / obs / p / histogram and windowed p-values within the parity bar; a
     batch with cut counts beyond the fused kernel's packed range exercises its hand-back to the general
     kernel."""
     for depth in (1.0, 30.0):
         batch, info = synth.make_batch(1500, 55, seed=71, table=table, depth_scale=depth)
         outs = {}
         for name, env in (("general", {"FPT_B200_PATH": "general"}), ("fast", {"FPT_B200_PATH": "fast"}),
-                          ("fused", {"FPT_B200_PATH": "auto", "FPT_B200_FUSED_WIN": 0}),
-                          ("fused_inwin", {"FPT_B200_PATH": "auto", "FPT_B200_FUSED_WIN": 1})):
+                          ("fused", {"FPT_B200_PATH": "fused", "FPT_B200_FUSED_WIN": 0}),
+                          ("fused_inwin", {"FPT_B200_PATH": "fused", "FPT_B200_FUSED_WIN": 1}),
+                          ("warp", {"FPT_B200_PATH": "auto"})):
             c = _ctx_with_env(**env)
             c.set_bias(table, 1e-6)
             c.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
@@ -413,10 +414,11 @@ def test_scoring_paths_agree(table, oracle):
             outs[name] = o
             c.close()
         ref = outs["general"]
-        for name in ("fast", "fused", "fused_inwin"):
+        for name in ("fast", "fused", "fused_inwin", "warp"):
             for k in ("exp", "obs", "pval", "hist"):
                 assert np.array_equal(outs[name][k], ref[k], equal_nan=True), (name, k, depth)
             assert_pvalues_close(outs[name]["winp"], ref["winp"], "%s winp depth %g" % (name, depth))
         # the streamed and the in-kernel windows use the same arithmetic: same bits
         assert np.array_equal(outs["fused"]["winp"], outs["fused_inwin"]["winp"], equal_nan=True)
         assert np.array_equal(outs["fused"]["winp"], outs["fast"]["winp"], equal_nan=True)
+        assert np.array_equal(outs["fused"]["winp"], outs["warp"]["winp"], equal_nan=True)

@@ -3,7 +3,7 @@
 name=$1; shift
 cd /root/repo/footprint-tools_b200
 mkdir -p lib_alt/$name
-for f in fpt_score fpt_fast fpt_fused fpt_ops fpt_fdr fpt_text fpt_ingest fpt_segment fpt_api; do
+for f in fpt_score fpt_fast fpt_fused fpt_warp fpt_ops fpt_fdr fpt_text fpt_ingest fpt_segment fpt_api; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr "$@" -c csrc/$f.cu -o lib_alt/$name/$f.o &
 done
 wait
