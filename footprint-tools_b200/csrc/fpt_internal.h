@@ -89,6 +89,7 @@ struct ScoreParams {
     // warp-autonomous kernel (fpt_warp.cu)
     int wmode;                 // windows: 0 none, 1 = {3}, 2 = {3, 5, 7}, 3 = win_h[0 .. n_win_h) (ascending, <= 3)
     int win_h[3], n_win_h;
+    long long win_row_off[FPT_MAX_SCALES];  // s * total: offset of output row s in winp_out
     const WItem *items;        // built by plan_items_kernel
     const int *n_items;
     int *work_counter;         // next item to hand out

@@ -185,6 +185,16 @@ FPT_HD float hi2(f32x2 a) {
     return a.hi_;
 #endif
 }
+// the pair stored at p (8-byte aligned): low half first
+FPT_HD f32x2 ld_pair(const float *p) {
+    f32x2 r;
+#if defined(__CUDA_ARCH__)
+    r.v = *reinterpret_cast<const unsigned long long *>(p);
+#else
+    r.lo_ = p[0]; r.hi_ = p[1];
+#endif
+    return r;
+}
 FPT_HD f32x2 add2(f32x2 a, f32x2 b) {
     f32x2 r;
 #if defined(__CUDA_ARCH__)

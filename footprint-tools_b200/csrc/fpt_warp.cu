@@ -71,6 +71,17 @@ struct DeviceWarp {
 
 struct DeviceEnv {
     const double *s4;  // 2^(j/4) table of ndtr4 (shared memory)
+    // asynchronous global -> shared copies (LDGSTS); src_bytes 0 zero-fills the destination
+    __device__ __forceinline__ void cp16(uint32_t *dst, const uint32_t *src) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    }
+    __device__ __forceinline__ void cp4(uint32_t *dst, const uint32_t *src, bool ok) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
+                     "r"(ok ? 4 : 0) : "memory");
+    }
+    __device__ __forceinline__ void stage(const StageSrc T, const StageGeo g, WarpSmem &S, int lane) { stage_issue(T, g, S, lane, *this); }
+    __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
     __device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) { fpt::st256(p, a, b, c, d); }
     __device__ __forceinline__ void atomic_inc_shared(unsigned *p) { atomicAdd(p, 1u); }
     __device__ __forceinline__ void atomic_inc_u64(unsigned long long *p) { atomicAdd(p, 1ULL); }
@@ -87,13 +98,13 @@ struct DeviceEnv {
 template <bool SMOOTH, int WM>
 __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScoreParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *tab = reinterpret_cast<float *>(smem_raw);                                    // 4096 f32
-    double *dmp = reinterpret_cast<double *>(tab + 4096);                                // 24
+    float *tab = reinterpret_cast<float *>(smem_raw);                                    // 4096 x {P[k], P[revcomp k]} f32
+    double *dmp = reinterpret_cast<double *>(tab + 2 * 4096);                            // 24
     double *s4 = dmp + kModelDoubles;                                                    // kNdTab
     WarpSmem *WS = reinterpret_cast<WarpSmem *>(s4 + kNdTab);                            // one per warp
     unsigned *hsub = reinterpret_cast<unsigned *>(WS + kWWarps);                         // learn_dm only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 4096; i += kWThreads) tab[i] = P.uniform ? 1.0f : (float)P.bias[i];
+    for (int i = tid; i < 4096; i += kWThreads) fill_pair_table(tab, P.bias, P.uniform, i);
     if (tid < kModelDoubles) dmp[tid] = P.dm ? P.dm[tid] : 0.0;
     ndtr4_table_init(s4, tid);
     if (P.hist)
@@ -109,11 +120,21 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
         if (lane == 0) v = atomicAdd(P.work_counter, 1);
         return __shfl_sync(0xffffffffu, v, 0);
     };
-    int cur = fetch();
-    while (cur < n_items) {
-        const int nxt = fetch();  // consumed at the end of this item: the round trip hides behind its arithmetic
-        const WItem it = P.items[cur];
-        const bool ok = process_item<SMOOTH, WM>(P, it, S, tab, dmp, hsub, W, env);
+    // Software pipeline over the items of this warp: while item i is processed, the raw cut counts of item i+1 are
+    // copied into shared memory asynchronously (issued inside process_item, before the window step) and the index of
+    // item i+2 is on its way back from the global counter — no step of an item waits for a global round trip.
+    int cur = -1;          // no current item in the first pass: it only issues the copies of the warp's first item
+    int nxt = fetch();
+    WItem it = {};
+    while (cur >= 0 || nxt < n_items) {
+        const int nn = nxt < n_items ? fetch() : nxt;
+        if (cur >= 0) it = S.next;   // parked by the previous pass
+        __syncwarp();
+        const bool have_next = nxt < n_items;
+        if (have_next && lane == 0) S.next = P.items[nxt];   // the load is waited for only at this store
+        __syncwarp();
+        const bool ok = process_item<SMOOTH, WM>(P, cur >= 0 ? &it : nullptr, have_next ? &S.next : nullptr, S, tab, dmp,
+                                                  hsub, W, env);
         if (!ok && lane == 0) {
             const int slot = atomicAdd(P.redo_count, 1);
             P.redo_ranges[3 * slot] = it.o0 + it.ta;
@@ -121,7 +142,8 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
             P.redo_ranges[3 * slot + 2] = it.iv;
         }
         __syncwarp();
-        cur = nxt;
+        cur = have_next ? nxt : -1;
+        nxt = nn;
     }
     if (P.hist) {  // flush the shared-memory part of the histogram
         __syncthreads();
@@ -133,7 +155,7 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
 }
 
 size_t score_warp_smem_bytes(bool hist) {
-    return 4096 * sizeof(float) + (kModelDoubles + kNdTab) * sizeof(double) + (size_t)kWWarps * sizeof(WarpSmem) +
+    return 2 * 4096 * sizeof(float) + (kModelDoubles + kNdTab) * sizeof(double) + (size_t)kWWarps * sizeof(WarpSmem) +
            (hist ? (size_t)kWHistSubE * kWHistSubO * sizeof(unsigned) : 0);
 }
 

@@ -41,7 +41,7 @@ constexpr int kWSeqWords = 32, kWMaskWords = 16;
 constexpr unsigned kWPackedCutLimit = 0x3FFu;  // largest cut count the packed format carries
 constexpr int kWHistSubE = 16, kWHistSubO = 64;  // learn_dm bins counted in shared memory first
 
-// per-warp shared memory (11 456 bytes)
+// per-warp shared memory (11 488 bytes)
 struct alignas(16) WarpSmem {
     uint32_t cw_[kWPre + kWX + kWPre];   // packed cuts, slot x at cw_[kWPre + x]
     uint32_t wcw[kWX + 16];              // packed 10-wide sums
@@ -50,6 +50,7 @@ struct alignas(16) WarpSmem {
     uint32_t seq[kWSeqWords];            // 2-bit codes of the item's bases, word 0 = bases [B0, B0 + 16)
     uint32_t msk[kWMaskWords];           // N bits, word 0 = bases [B0, B0 + 32)
     double zsT[4 * kWZS];                // z of the item, transposed: zsT[e * kWZS + 2 + cg] = z[4 cg + e]
+    WItem next;                          // record of the warp's next item (device: parked here by the kernel loop)
 };
 
 // geometry of one item, identical in every lane
@@ -107,6 +108,23 @@ FPT_HD ItemGeo item_geometry(const WItem &it, int WH) {
     return G;
 }
 
+// reverse complement of a little-endian 6-mer index (first base in the two low bits; A0 C1 G2 T3)
+FPT_HD unsigned revcomp12(unsigned x) {
+    unsigned r = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) r |= (3u - ((x >> (2 * j)) & 3u)) << (2 * (5 - j));
+    return r;
+}
+
+// The shared-memory bias table of the kernel: entry k = {propensity of k-mer k, propensity of its reverse complement}
+// as two floats. Output position g takes its plus-strand propensity from the 6 bases [g-3, g+3) and its minus-strand
+// one from the reverse complement of the SAME 6 bases (bias.py:88-111, predict.pyx:47-61,151-153), so one 64-bit
+// load delivers both — already in the (plus low, minus high) layout of the packed single-precision arithmetic.
+FPT_HD void fill_pair_table(float *tab2, const double *bias_le, int uniform, int i) {
+    tab2[2 * i] = uniform ? 1.0f : (float)bias_le[i];
+    tab2[2 * i + 1] = uniform ? 1.0f : (float)bias_le[revcomp12((unsigned)i)];
+}
+
 FPT_HD unsigned lo16(unsigned w) { return w & 0xFFFFu; }
 FPT_HD unsigned hi16(unsigned w) { return w >> 16; }
 FPT_HD uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
@@ -114,51 +132,97 @@ FPT_HD uint4 agg(const uint4 a, const uint4 b) {
     return make_uint4(pt::vminu2(a.x, b.x), pt::vmaxu2(a.y, b.y), a.z + b.z, a.w + b.w);
 }
 
-// ---- step A: stage and pack the cut counts of group xg (slots 4 xg .. 4 xg + 3); returns the OR of the counts ----
-FPT_HD unsigned step_stage(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int xg, bool aligned) {
-    const int x = xg << 2;
-    const long long g = G.G0 + x;
-    uint4 a, b;
-    if (aligned && g >= 0 && g + 4 <= P.n_track) {
-        a = pt::ldg(reinterpret_cast<const uint4 *>(P.cuts_p + g));
-        b = pt::ldg(reinterpret_cast<const uint4 *>(P.cuts_m + g));
-    } else {
-        unsigned av[4], bv[4];
+// ---- step A: staging. The raw cut counts of an item are copied global -> shared ASYNCHRONOUSLY (cp.async: the data
+// never passes through registers) while the PREVIOUS item of the warp evaluates its windows — the arrays they land
+// in (packed cuts, window sums) are dead by then:
+//     rawP[x] = S.cw_[kWPre + x] = cuts+[G0 + x], x in [0, NX)       rawM[x] = S.wcw[4 + x] = cuts-[G0 + x], x in [-1, NX)
+// and the item's sequence / N-mask words into S.seq / S.msk. When the warp comes to the item it waits for its own
+// copies (long since complete) and packs shared -> shared. Positions outside the track are zero-filled by the copy.
+// Env::cp16 / cp4(dst, src, ok): 16- / 4-byte asynchronous copy (zeros when !ok); the host emulation copies at once.
+// (the track pointers travel by value: the device calls this out of line, once per item, so that the kernel holds one
+// copy of it)
+struct StageSrc {
+    const uint32_t *cuts_p, *cuts_m, *seq2, *nmask;
+    long long n_track;
+    int cuts_vec, uniform;
+};
+FPT_HD StageSrc stage_src(const ScoreParams &P) {
+    StageSrc T;
+    T.cuts_p = P.cuts_p; T.cuts_m = P.cuts_m; T.seq2 = P.seq2; T.nmask = P.nmask;
+    T.n_track = P.n_track; T.cuts_vec = P.cuts_vec; T.uniform = P.uniform;
+    return T;
+}
+struct StageGeo {
+    long long G0, B0;
+    int NXG;
+};
+template <class Env>
+FPT_HD void stage_issue(const StageSrc P, const StageGeo G, WarpSmem &S, int lane, Env &env) {
+    const bool aligned = P.cuts_vec && ((G.G0 & 3) == 0);
+    uint32_t *rawP = S.cw_ + kWPre, *rawM = S.wcw + 4;
+    for (int xg = lane; xg < G.NXG; xg += 32) {
+        const int x = xg << 2;
+        const long long g = G.G0 + x;
+        if (aligned && g >= 0 && g + 4 <= P.n_track) {
+            env.cp16(rawP + x, P.cuts_p + g);
+            env.cp16(rawM + x, P.cuts_m + g);
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const long long ge = g + e;
-            const bool ok = ge >= 0 && ge < P.n_track;
-            av[e] = ok ? pt::ldg(P.cuts_p + ge) : 0u;
-            bv[e] = ok ? pt::ldg(P.cuts_m + ge) : 0u;
+            for (int e = 0; e < 4; ++e) {
+                const long long ge = g + e;
+                const bool ok = ge >= 0 && ge < P.n_track;
+                env.cp4(rawP + x + e, P.cuts_p + (ok ? ge : 0), ok);
+                env.cp4(rawM + x + e, P.cuts_m + (ok ? ge : 0), ok);
+            }
         }
-        a = make_uint4(av[0], av[1], av[2], av[3]);
-        b = make_uint4(bv[0], bv[1], bv[2], bv[3]);
     }
-    const unsigned bm1 = (g >= 1 && g - 1 < P.n_track) ? pt::ldg(P.cuts_m + (g - 1)) : 0u;
+    if (lane == 0) {  // the minus-strand partner of slot 0
+        const long long g = G.G0 - 1;
+        const bool ok = g >= 0 && g < P.n_track;
+        env.cp4(rawM - 1, P.cuts_m + (ok ? g : 0), ok);
+    }
+    if (!P.uniform) {
+        // lane l: seq[l] = bases B0 + 16 l .., msk[l] = bases B0 + 32 l .. (l < 16); stage_pack turns what lies outside
+        // the track into N
+        const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
+        const long long ws = (G.B0 >> 4) + lane;
+        const bool oks = ws >= 0 && ws < nw2;
+        env.cp4(S.seq + lane, P.seq2 + (oks ? ws : 0), oks);
+        if (lane < kWMaskWords) {
+            const long long wm = (G.B0 >> 5) + lane;
+            const bool okm = wm >= 0 && wm < nwm;
+            env.cp4(S.msk + lane, P.nmask + (okm ? wm : 0), okm);
+        }
+    }
+    env.cp_commit();
+}
+
+// packs group xg in place: slot x = lo16 cuts+[x] | hi16 cuts-[x-1]; returns the OR of the raw counts
+FPT_HD unsigned stage_pack(WarpSmem &S, int xg) {
+    const int x = xg << 2;
+    uint32_t *rawP = S.cw_ + kWPre;
+    const uint32_t *rawM = S.wcw + 4;
+    const uint4 a = lds128(rawP + x), b = lds128(rawM + x);
+    const unsigned bm1 = rawM[x - 1];
     uint4 w;
     w.x = pt::pack_lo16(a.x, bm1);
     w.y = pt::pack_lo16(a.y, b.x);
     w.z = pt::pack_lo16(a.z, b.y);
     w.w = pt::pack_lo16(a.w, b.z);
-    *reinterpret_cast<uint4 *>(S.cw_ + kWPre + x) = w;
+    *reinterpret_cast<uint4 *>(rawP + x) = w;  // only this lane ever reads rawP of its own group
     return (a.x | a.y) | (a.z | a.w) | (b.x | b.y) | (b.z | bm1);
 }
 
-// sequence words of the item: lane l stages seq[l] (bases B0 + 16 l ..) and, for l < 16, msk[l] (bases B0 + 32 l ..);
-// bases outside the track read as N
-FPT_HD void step_stage_seq(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int lane) {
-    const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
-    const long long ws = (G.B0 >> 4) + lane;
-    S.seq[lane] = (ws >= 0 && ws < nw2) ? pt::ldg(P.seq2 + ws) : 0u;
-    if (lane < kWMaskWords) {
-        const long long wm = (G.B0 >> 5) + lane;
-        unsigned v = 0xFFFFFFFFu;
-        if (wm >= 0 && wm < nwm) {
-            v = pt::ldg(P.nmask + wm);
-            const long long left = P.n_track - (wm << 5);  // valid bits of this word
-            if (left < 32) v |= 0xFFFFFFFFu << (int)left;
-        }
-        S.msk[lane] = v;
+// N bits of the staged mask words that lie outside the track (the copy zero-filled them)
+FPT_HD void stage_fix_mask(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int lane) {
+    if (lane >= kWMaskWords) return;
+    const long long nwm = (P.n_track + 31) >> 5;
+    const long long wm = (G.B0 >> 5) + lane;
+    if (wm < 0 || wm >= nwm) {
+        S.msk[lane] = 0xFFFFFFFFu;
+    } else {
+        const long long left = P.n_track - (wm << 5);  // valid bits of this word
+        if (left < 32) S.msk[lane] |= 0xFFFFFFFFu << (int)left;
     }
 }
 
@@ -280,6 +344,16 @@ static FPT_NOINLINE_HD double expected_exact(const double *tab, double dflt, int
     return round(pt::dmul(ratio, sm));
 }
 
+// per-element stores of a partial group (an interval's first / last group, or unaligned output arrays). Inline on
+// purpose: some lane of most rounds takes it, and a call to a far-away function costs the sixteen desynchronised
+// warps of an SM an instruction-cache miss each time (measured: 2.18 -> 2.53 ms per C3 pass when it was out of line).
+FPT_HD void store_partial(double *dst, unsigned omask, double v0, double v1, double v2, double v3) {
+    if (omask & 1u) dst[0] = v0;
+    if (omask & 2u) dst[1] = v1;
+    if (omask & 4u) dst[2] = v2;
+    if (omask & 8u) dst[3] = v3;
+}
+
 // ---- step D: the 4 positions c0 .. c0+3 of group cg -------------------------------------------------------------
 // Env supplies what differs between the device and the host emulation: the direct NB evaluation, the 256-bit
 // store, the atomics.
@@ -302,7 +376,7 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
     const uint32_t *wcw = S.wcw;
 
     // -- the lane's 18-base window: bases g0-8 .. g0+9 (k-mer m starts at base g0-8+m)
-    unsigned long long kw = 0, rcw = 0;
+    unsigned long long kw = 0;
     unsigned nw = 0;
     if (!P.uniform) {
         const int q = (int)(G.gbase - 8 - G.B0) + c0;  // bit position of base g0-8 in the staged words
@@ -312,9 +386,6 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
         const unsigned lo32 = pt::funnel_r(s0, s1, sh), hi32 = pt::funnel_r(s1, s2, sh);
         kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
         nw = pt::funnel_r(S.msk[wm], S.msk[wm + 1], q & 31) & 0x3FFFFu;
-        unsigned long long t = pt::brevll(kw) >> 28;
-        t = ((t & 0xAAAAAAAAAull) >> 1) | ((t & 0x555555555ull) << 1);
-        rcw = t ^ 0xFFFFFFFFFull;
     }
 
     // -- trimmed window sums T[strand][e] (exact integers)
@@ -375,20 +446,18 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
     // -- the 13 k-mers starting at bases g0-8 .. g0+4 serve both strands: plus-strand position g0-5+m and
     //    minus-strand position g0-6+m use k-mer m. Both strands ride in one f32x2 (plus low, minus high): the window
     //    sums of propensities, the estimate and its rounding are FADD2 / FMUL2 / FFMA2, one instruction for both.
-    //    (uniform model: the table holds 1.0 everywhere and kw = rcw = nw = 0)
+    //    (uniform model: the table holds 1.0 everywhere and kw = nw = 0)
     const float dflt_f = (float)P.dflt;
     int exi[4] = {0, 0, 0, 0};  // plus[t+1] + minus[t] (cli/detect.py:121-122)
     unsigned redo = 0;          // bit 4*s + e: strand s of element e needs the out-of-line evaluation
     {
         pt::f32x2 Pv[13];
         const unsigned kwl = (unsigned)kw, kwh = (unsigned)(kw >> 32);       // bases 0..15, 16..17
-        const unsigned rcl = (unsigned)rcw, rch = (unsigned)(rcw >> 32);
 #pragma unroll
         for (int m = 0; m < 13; ++m) {
-            // k-mer m of the window, and of its reverse complement (12 bits from bit 2m / 24 - 2m)
+            // k-mer m of the window (12 bits from bit 2m): {plus, minus} propensities in one 64-bit load
             const unsigned kp = (m <= 10 ? (kwl >> (2 * m)) : pt::funnel_r(kwl, kwh, 2 * m)) & 0xFFFu;
-            const unsigned km = (24 - 2 * m <= 20 ? (rcl >> (24 - 2 * m)) : pt::funnel_r(rcl, rch, 24 - 2 * m)) & 0xFFFu;
-            Pv[m] = pt::pack2(tab[kp], tab[km]);
+            Pv[m] = pt::ld_pair(tab + 2 * kp);
         }
         if (nw != 0) {
             const pt::f32x2 d2 = pt::pack2(dflt_f, dflt_f);
@@ -430,6 +499,9 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
     }
     redo &= vmask | (vmask << 4);
     if (redo) {  // rare; kept out of the loops above so that nothing is live across the calls
+        unsigned long long rcw = pt::brevll(kw) >> 28;  // reverse complement of the 18-base window
+        rcw = ((rcw & 0xAAAAAAAAAull) >> 1) | ((rcw & 0x555555555ull) << 1);
+        rcw ^= 0xFFFFFFFFFull;
         for (unsigned m = redo; m; m &= m - 1) {
             const int b = pt::ffs32(m) - 1, s = b >> 2, e = b & 3;
             const unsigned Te = s ? (e == 0 ? Th[0] : e == 1 ? Th[1] : e == 2 ? Th[2] : Th[3])
@@ -477,13 +549,9 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
         if (omask == 0xFu && P.vec_ok) {
             if (P.exp_out) env.st256(P.exp_out + f0, exv[0], exv[1], exv[2], exv[3]);
             if (P.obs_out) env.st256(P.obs_out + f0, obv[0], obv[1], obv[2], obv[3]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((omask >> e) & 1u) {
-                    if (P.exp_out) P.exp_out[f0 + e] = exv[e];
-                    if (P.obs_out) P.obs_out[f0 + e] = obv[e];
-                }
+        } else if (omask) {
+            if (P.exp_out) store_partial(P.exp_out + f0, omask, exv[0], exv[1], exv[2], exv[3]);
+            if (P.obs_out) store_partial(P.obs_out + f0, omask, obv[0], obv[1], obv[2], obv[3]);
         }
     }
     if (P.hist) {
@@ -512,11 +580,7 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
     }
     if (P.pval_out && omask) {
         if (omask == 0xFu && P.vec_ok) env.st256(P.pval_out + f0, pvv[0], pvv[1], pvv[2], pvv[3]);
-        else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((omask >> e) & 1u) P.pval_out[f0 + e] = pvv[e];
-        }
+        else store_partial(P.pval_out + f0, omask, pvv[0], pvv[1], pvv[2], pvv[3]);
     }
     if (want_z) {
 #pragma unroll
@@ -540,7 +604,7 @@ FPT_HD void step_windows(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, in
     if (b <= a) return;
     const unsigned omask = ((1u << b) - 1u) & ~((1u << a) - 1u);
     const long long f0 = G.F0 + c0;
-    const int dl = G.T0 + c0, dr = G.len - 1 - dl;  // interval-local index of element 0 and its distance from the end
+    const int dl = G.T0 + c0;  // interval-local index of element 0
     const double *zt = S.zsT + 2 + cg;
     int h0 = WM == 3 ? P.win_h[0] : 3, h1 = WM == 3 ? P.win_h[1] : (WM == 2 ? 5 : -1), h2 = WM == 3 ? P.win_h[2] : (WM == 2 ? 7 : -1);
     const int ns = WM == 3 ? P.n_win_h : (WM == 2 ? 3 : 1);
@@ -581,21 +645,19 @@ FPT_HD void step_windows(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, in
         double res[4];
         env.ndtr4(A0, res);
         const int h = h0;
-        if (dl < h || dr < h + 3) {
+        {
+            // edge rule: valid iff 0 <= t - h and t + h <= len - 1, i.e. (unsigned)(t - h) < len - 2h (none when len <= 2h)
+            const int lim = G.len - 2 * h;
+            const unsigned ulim = lim > 0 ? (unsigned)lim : 0u;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (dl + e < h || dr - e < h) res[e] = 1.0;
+                if ((unsigned)(dl + e - h) >= ulim) res[e] = 1.0;
         }
         for (unsigned m = P.h_rows[h]; m; m &= m - 1) {
             const int s = pt::ffs32(m) - 1;
-            double *dst = P.winp_out + (size_t)s * P.total + f0;
-            if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) {
-                env.st256(dst, res[0], res[1], res[2], res[3]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if ((omask >> e) & 1u) dst[e] = res[e];
-            }
+            double *dst = P.winp_out + (P.win_row_off[s] + f0);
+            if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) env.st256(dst, res[0], res[1], res[2], res[3]);
+            else store_partial(dst, omask, res[0], res[1], res[2], res[3]);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) { A0[e] = A1[e]; A1[e] = A2[e]; }
@@ -604,45 +666,63 @@ FPT_HD void step_windows(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, in
 }
 
 // ---- one item, all five steps. W runs a per-lane body on every lane of the warp and synchronises the warp after
-// it (device: the calling lane + __syncwarp; host emulation: a loop over 32 lanes). Returns false when the item holds
-// a cut count the packed format cannot carry (nothing was written: the caller hands the item to the general kernel).
+// it (device: the calling lane + __syncwarp; host emulation: a loop over 32 lanes). On entry the item's raw cut
+// counts are on their way into shared memory (stage_issue was called for it); before the window step — or before
+// returning — the copies of `next` (the warp's next item, or NULL) are issued. Returns false when the item holds a
+// cut count the packed format cannot carry (nothing was written: the caller hands the item to the general kernel).
+// `cur` may be NULL (the warp's first pass: nothing to score yet, only the copies of `next` are issued — the kernel
+// thus holds ONE copy of the staging code).
 template <bool SMOOTH, int WM, class W, class Env>
-FPT_HD bool process_item(const ScoreParams &P, const WItem &it, WarpSmem &S, const float *tab, const double *dmp,
-                         unsigned *hsub, W &warp, Env &env) {
+FPT_HD bool process_item(const ScoreParams &P, const WItem *cur, const WItem *next, WarpSmem &S, const float *tab,
+                         const double *dmp, unsigned *hsub, W &warp, Env &env) {
     constexpr bool want_win = WM != 0;
     const bool want_p = (P.pval_out != nullptr) || want_win;
-    const ItemGeo G = item_geometry(it, want_win ? P.wh_max : 0);
-    const bool aligned = P.cuts_vec && ((G.G0 & 3) == 0);
-    const unsigned seen = warp.or_reduce([&](int lane) {
-        unsigned s = 0;
-        for (int xg = lane; xg < G.NXG; xg += 32) s |= step_stage(P, G, S, xg, aligned);
-        if (!P.uniform) step_stage_seq(P, G, S, lane);
-        if (want_win && lane < 16) {  // the 2 + 2 pad entries of each z row
-            const int e = lane >> 2, k = lane & 3;
-            S.zsT[e * kWZS + (k < 2 ? k : G.NCG + k)] = 0.0;
-        }
-        return s;
-    });
-    if (seen & ~kWPackedCutLimit) return false;
-    warp.each([&](int lane) {
-        for (int xg = lane; xg < G.NXG; xg += 32) step_sums<SMOOTH>(S, xg);
-    });
-    if (SMOOTH) {
-        const int n1 = G.NXG - 1, n2 = G.NXG - 3, n3 = G.NXG - 7, n4 = G.NXG - 23;
-        warp.each([&](int lane) { for (int g = lane; g < n1; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 1]); });
-        warp.each([&](int lane) { for (int g = lane; g < n2; g += 32) S.GA[g] = agg(S.GB[g], S.GB[g + 2]); });
-        warp.each([&](int lane) { for (int g = lane; g < n3; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 4]); });
-        warp.each([&](int lane) { for (int g = lane; g < n4; g += 32) S.GA[g] = agg(agg(S.GB[g], S.GB[g + 8]), S.GB[g + 16]); });
+    const int wh = want_win ? P.wh_max : 0;
+    ItemGeo G;
+    bool good = false;
+    if (cur) {
+        G = item_geometry(*cur, wh);
+        warp.each([&](int) { env.cp_wait(); });  // this lane's copies have landed; the warp barrier publishes all of them
+        const unsigned seen = warp.or_reduce([&](int lane) {
+            unsigned s = 0;
+            for (int xg = lane; xg < G.NXG; xg += 32) s |= stage_pack(S, xg);
+            if (!P.uniform) stage_fix_mask(P, G, S, lane);
+            if (want_win && lane < 16) {  // the 2 + 2 pad entries of each z row
+                const int e = lane >> 2, k = lane & 3;
+                S.zsT[e * kWZS + (k < 2 ? k : G.NCG + k)] = 0.0;
+            }
+            return s;
+        });
+        good = !(seen & ~kWPackedCutLimit);
     }
-    warp.each([&](int lane) {
-        for (int cg = lane; cg < G.NCG; cg += 32) step_score<SMOOTH>(P, G, S, tab, dmp, hsub, cg, want_p, want_win, env);
-    });
-    if (want_win) {
+    if (good) {
+        warp.each([&](int lane) {
+            for (int xg = lane; xg < G.NXG; xg += 32) step_sums<SMOOTH>(S, xg);
+        });
+        if (SMOOTH) {
+            const int n1 = G.NXG - 1, n2 = G.NXG - 3, n3 = G.NXG - 7, n4 = G.NXG - 23;
+            warp.each([&](int lane) { for (int g = lane; g < n1; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 1]); });
+            warp.each([&](int lane) { for (int g = lane; g < n2; g += 32) S.GA[g] = agg(S.GB[g], S.GB[g + 2]); });
+            warp.each([&](int lane) { for (int g = lane; g < n3; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 4]); });
+            warp.each([&](int lane) { for (int g = lane; g < n4; g += 32) S.GA[g] = agg(agg(S.GB[g], S.GB[g + 8]), S.GB[g + 16]); });
+        }
+        warp.each([&](int lane) {
+            for (int cg = lane; cg < G.NCG; cg += 32) step_score<SMOOTH>(P, G, S, tab, dmp, hsub, cg, want_p, want_win, env);
+        });
+    }
+    // the packed cuts, the window sums and the sequence words are dead from here on: the next item's raw data starts
+    // its way into them now and arrives while this item's windows are evaluated
+    if (next) {
+        const ItemGeo Gn = item_geometry(*next, wh);
+        const StageGeo sg = {Gn.G0, Gn.B0, Gn.NXG};
+        warp.each([&](int lane) { env.stage(stage_src(P), sg, S, lane); });
+    }
+    if (good && want_win) {
         warp.each([&](int lane) {
             for (int cg = lane; cg < G.NCG; cg += 32) step_windows<WM == 0 ? 1 : WM>(P, G, S, cg, env);
         });
     }
-    return true;
+    return good || !cur;
 }
 
 }  // namespace wk

@@ -30,6 +30,7 @@ inline bool warp_params_finish(ScoreParams &p, const fpt_score_args *a, int wh_m
     p.win_h[0] = p.win_h[1] = p.win_h[2] = -1;
     if (windows) {
         for (int s = 0; s < a->n_scales; ++s) {
+            p.win_row_off[s] = (long long)s * (long long)a->total;
             if (al(a->winp_out + (size_t)s * (size_t)a->total, 31)) p.winp_vec |= 1u << s;
             p.h_rows[a->win_half_width[s]] |= 1u << s;
         }

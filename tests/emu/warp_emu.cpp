@@ -46,6 +46,12 @@ struct HostEnv {
         FPT_EMU_ASSERT((reinterpret_cast<uintptr_t>(p) & 31) == 0);
         p[0] = a; p[1] = b; p[2] = c; p[3] = d;
     }
+    // asynchronous copies: done at once here (the order of issue / wait / pack is what the emulation checks)
+    void cp16(uint32_t *dst, const uint32_t *src) { memcpy(dst, src, 16); }
+    void cp4(uint32_t *dst, const uint32_t *src, bool ok) { *dst = ok ? *src : 0u; }
+    void stage(const StageSrc T, const StageGeo g, WarpSmem &S, int lane) { stage_issue(T, g, S, lane, *this); }
+    void cp_commit() {}
+    void cp_wait() {}
     void atomic_inc_shared(unsigned *p) { *p += 1; }
     void atomic_inc_u64(unsigned long long *p) { *p += 1; }
     void direct_pz(const double *dmp, double ex, int kobs, double *pv, double *z) {
@@ -105,19 +111,24 @@ extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double 
         }
     }
     // one "SM": the fp32 table, the model, a sub-histogram and one warp's shared memory, poisoned before every item
-    std::vector<float> tab(4096, 0.f);  // 1.0 everywhere for the uniform model
-    for (int i = 0; i < 4096; ++i) tab[i] = uniform ? 1.0f : (float)bias_le[i];
+    std::vector<float> tab(2 * 4096, 0.f);  // {P[k], P[revcomp k]}; 1.0 everywhere for the uniform model
+    for (int i = 0; i < 4096; ++i) fill_pair_table(tab.data(), bias_le, uniform, i);
     double dmp[kModelDoubles];
     for (int i = 0; i < kModelDoubles; ++i) dmp[i] = dm ? dm[i] : 0.0;
     std::vector<unsigned> hsub(kWHistSubE * kWHistSubO, 0u);
     WarpSmem *S = static_cast<WarpSmem *>(aligned_alloc(64, sizeof(WarpSmem)));
     HostWarp W;
     HostEnv env;
+    memset(S, 0xEE, sizeof(WarpSmem));  // anything read before it is written is loud
     int n_redo = 0;
-    for (const WItem &it : items) {
-        memset(S, 0xEE, sizeof(WarpSmem));  // anything read before it is written is loud
+    // pass -1 issues the copies of item 0 (no current item), as the kernel's first loop iteration does
+    for (long long ii = -1; ii < (long long)items.size(); ++ii) {
+        const WItem *cur = ii >= 0 ? &items[(size_t)ii] : nullptr;
+        const WItem *nx = ii + 1 < (long long)items.size() ? &items[(size_t)(ii + 1)] : nullptr;
+        // poison everything the item must not inherit from its predecessor (all but the staged raw data)
+        memset(S->GA, 0xEE, sizeof S->GA); memset(S->GB, 0xEE, sizeof S->GB); memset(S->zsT, 0xEE, sizeof S->zsT);
         bool ok;
-#define EMU_RUN(SM, WMODE) ok = process_item<SM, WMODE>(p, it, *S, tab.data(), dmp, hsub.data(), W, env)
+#define EMU_RUN(SM, WMODE) ok = process_item<SM, WMODE>(p, cur, nx, *S, tab.data(), dmp, hsub.data(), W, env)
         if (shw != 0) {
             switch (p.wmode) {
                 case 0: EMU_RUN(true, 0); break;
@@ -135,6 +146,7 @@ extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double 
         }
 #undef EMU_RUN
         if (!ok) {
+            const WItem &it = *cur;
             if (n_redo < redo_cap) {
                 redo_ranges[3 * n_redo] = it.o0 + it.ta;
                 redo_ranges[3 * n_redo + 1] = it.o0 + it.tb;
