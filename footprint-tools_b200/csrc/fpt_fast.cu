@@ -142,19 +142,12 @@ __global__ void __launch_bounds__(256, 2) window_fast_kernel(const WindowParams 
 #ifndef FPT_WIN_WAVES
 #define FPT_WIN_WAVES 4
 #endif
-#ifndef FPT_WIN_TABLE
-#define FPT_WIN_TABLE 0  // 1: table + Hermite-step normal tail (experimental, see fpt_tile.cuh)
-#endif
 template <int H0, int H1, int H2>
 __global__ void __launch_bounds__(256, FPT_WIN_CTAS) window_fixed_kernel(const WindowParams W) {
     constexpr int HMAX = H2 >= 0 ? H2 : (H1 >= 0 ? H1 : H0);
     constexpr int QLO = (8 - HMAX) / 4, QHI = (11 + HMAX) / 4;  // 256-bit loads q covering z[-HMAX .. 3 + HMAX]
     __shared__ double s4[kNdTab];
     ndtr4_table_init(s4, threadIdx.x);
-#if FPT_WIN_TABLE
-    __shared__ __align__(16) double ndt[kNdtEntries * kNdtStride];
-    ndtr_table_init(ndt, threadIdx.x, blockDim.x);
-#endif
     __syncthreads();
     const long long ngroups = (W.total + 3) >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -202,8 +195,6 @@ __global__ void __launch_bounds__(256, FPT_WIN_CTAS) window_fixed_kernel(const W
             double res[4];
 #if defined(FPT_WIN_NOMATH)
             res[0] = A[k][0]; res[1] = A[k][1]; res[2] = A[k][2]; res[3] = A[k][3];  // experiment: memory floor
-#elif FPT_WIN_TABLE
-            ndtr4_table(A[k], ndt, s4, res);
 #else
             ndtr4(A[k], s4, res);
 #endif

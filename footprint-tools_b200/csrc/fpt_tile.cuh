@@ -385,65 +385,6 @@ __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, d
 __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, double (&res)[4]) { ndtr4(a, s4, res); }
 #endif
 
-// ---- experimental (FPT_WIN_TABLE=1, off by default; DESIGN.md §9 item 3, tools/fit_ndtr_table.py) ---------------
-// Phi for |a| < 8 from a shared-memory table of the lower tail on a 1/64 grid and a Hermite-polynomial step:
-//   Phi(-t) = P0 + f0 d (1 + c1 d + c2 d^2 + c3 d^3 + c4 d^4),  d = t0 - t, entry i = {P0 = Phi(-t0), f0 = phi(t0), c1..c4}
-// with t0 = i/64 the grid point nearest to t (|d| <= 1/128): maximum relative error of the tail 7.4e-11 (order 5).
-// 10 FP64 instructions and three 128-bit shared loads per value instead of 24 FP64 + 10 FP32; anything else
-// (|a| >= 8, inf, NaN) makes the whole group of four take ndtr4. Not the default until it has been measured.
-constexpr int kNdtEntries = 513;  // t0 = 0 .. 8
-constexpr int kNdtStride = 6;     // doubles per entry
-
-__device__ __forceinline__ void ndtr_table_init(double *ndt, int tid, int nthreads) {
-    for (int i = tid; i < kNdtEntries; i += nthreads) {
-        const double t0 = (double)i * 0.015625, x0 = -t0;
-        double *e = ndt + i * kNdtStride;
-        e[0] = ndtr_fn(x0);
-        e[1] = exp(-0.5 * t0 * t0) * 0.398942280401432677939946;
-        e[2] = -x0 * 0.5;
-        e[3] = (x0 * x0 - 1.0) * (1.0 / 6.0);
-        e[4] = -(x0 * x0 * x0 - 3.0 * x0) * (1.0 / 24.0);
-        e[5] = (x0 * x0 * x0 * x0 - 6.0 * x0 * x0 + 3.0) * (1.0 / 120.0);
-    }
-}
-
-__device__ __forceinline__ void ndtr4_table(const double (&a)[4], const double *ndt, const double *s4, double (&res)[4]) {
-    bool far = false;
-    double d[4];
-    const double *ent[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const unsigned ahi = (unsigned)__double2hiint(a[e]) & 0x7FFFFFFFu;
-        far |= ahi >= 0x40200000u;  // |a| >= 8, infinite or NaN
-        const double t = __hiloint2double((int)ahi, __double2loint(a[e]));
-        const double kf = fma(t, 64.0, 6755399441055744.0);  // rint(64 t) in the low word
-        const int i = __double2loint(kf) & 1023;
-        const double nf = __dadd_rn(kf, -6755399441055744.0);
-        d[e] = fma(nf, 0.015625, -t);  // t0 - t, exact
-        ent[e] = ndt + (i < kNdtEntries ? i : 0) * kNdtStride;
-    }
-    if (far) {
-#if FPT_WIN_TABLE == 2  // instruction-count experiment only: no fallback code in the kernel
-        res[0] = res[1] = res[2] = res[3] = 0.0;
-#else
-        ndtr4(a, s4, res);
-#endif
-        return;
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const double2 pf = *reinterpret_cast<const double2 *>(ent[e]);
-        const double2 c12 = *reinterpret_cast<const double2 *>(ent[e] + 2);
-        const double2 c34 = *reinterpret_cast<const double2 *>(ent[e] + 4);
-        double acc = fma(c34.y, d[e], c34.x);
-        acc = fma(acc, d[e], c12.y);
-        acc = fma(acc, d[e], c12.x);
-        acc = fma(acc, d[e], 1.0);
-        const double tail = fma(__dmul_rn(pf.y, d[e]), acc, pf.x);
-        res[e] = a[e] < 0.0 ? tail : __dadd_rn(1.0, -tail);
-    }
-}
-
 __device__ __forceinline__ int fregion_of(const int *bases, int nreg, int v) {
     int r = 0;
 #pragma unroll 4

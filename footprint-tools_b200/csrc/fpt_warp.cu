@@ -1,5 +1,5 @@
 // fpt_warp.cu — device side of the warp-autonomous scoring kernel (steps in fpt_warp_core.cuh): the item planner,
-// the persistent kernel (one 16-warp CTA per SM, every warp fetches work items from a global counter and runs an
+// the persistent kernel (one 12-warp CTA per SM, every warp fetches work items from a global counter and runs an
 // item from the packed track to its outputs with no block barrier), and the launchers.
 #include "fpt_tile.cuh"
 #include "fpt_warp_core.cuh"
@@ -10,7 +10,10 @@ namespace {
 
 using namespace wk;
 
-constexpr int kWWarps = 16;                 // warps per CTA (one CTA per SM)
+#ifndef FPT_WARP_WARPS
+#define FPT_WARP_WARPS 12  // measured on C3: 8 warps 2.52 ms, 12 warps 2.03 ms, 14 warps 2.19 ms, 16 warps 2.10 ms (profiles/r2_warp_variants.txt)
+#endif
+constexpr int kWWarps = FPT_WARP_WARPS;     // warps per CTA (one CTA per SM)
 constexpr int kWThreads = 32 * kWWarps;
 
 // ---- planner: intervals -> work items (cli/detect.py scores an interval per call; a long interval is cut into
@@ -115,24 +118,32 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
     WarpSmem &S = WS[warp];
     DeviceWarp W{lane};
     DeviceEnv env{s4};
-    auto fetch = [&]() {
+    // the next work-item index: lane 0 asks the global counter; the answer is broadcast only where it is needed, a whole
+    // item later, so the round trip of the atomic is never waited for
+    // (inline PTX: atomicAdd() by one lane is rewritten by the compiler into its warp-aggregated form, whose
+    // shuffle waits for the answer on the spot)
+    auto ask = [&]() {
         int v = 0;
-        if (lane == 0) v = atomicAdd(P.work_counter, 1);
-        return __shfl_sync(0xffffffffu, v, 0);
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(P.work_counter) : "memory");
+        return v;
     };
     // Software pipeline over the items of this warp: while item i is processed, the raw cut counts of item i+1 are
-    // copied into shared memory asynchronously (issued inside process_item, before the window step) and the index of
-    // item i+2 is on its way back from the global counter — no step of an item waits for a global round trip.
+    // copied into shared memory asynchronously (issued inside process_item, before the window step), its record was
+    // copied into S.next the same way at the top of the pass, and the index of item i+2 is on its way back from the
+    // global counter — no step of an item waits for a global round trip.
     int cur = -1;          // no current item in the first pass: it only issues the copies of the warp's first item
-    int nxt = fetch();
+    int nxt = __shfl_sync(0xffffffffu, ask(), 0);
     WItem it = {};
     while (cur >= 0 || nxt < n_items) {
-        const int nn = nxt < n_items ? fetch() : nxt;
+        const bool have_next = nxt < n_items;
+        const int asked = have_next ? ask() : 0;
         if (cur >= 0) it = S.next;   // parked by the previous pass
         __syncwarp();
-        const bool have_next = nxt < n_items;
-        if (have_next && lane == 0) S.next = P.items[nxt];   // the load is waited for only at this store
-        __syncwarp();
+        if (have_next && lane == 0) {  // record of the next item: global -> shared, asynchronously
+            env.cp16(reinterpret_cast<uint32_t *>(&S.next), reinterpret_cast<const uint32_t *>(P.items + nxt));
+            env.cp16(reinterpret_cast<uint32_t *>(&S.next) + 4, reinterpret_cast<const uint32_t *>(P.items + nxt) + 4);
+        }
+        env.cp_commit();
         const bool ok = process_item<SMOOTH, WM>(P, cur >= 0 ? &it : nullptr, have_next ? &S.next : nullptr, S, tab, dmp,
                                                   hsub, W, env);
         if (!ok && lane == 0) {
@@ -143,7 +154,7 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
         }
         __syncwarp();
         cur = have_next ? nxt : -1;
-        nxt = nn;
+        nxt = have_next ? __shfl_sync(0xffffffffu, asked, 0) : nxt;
     }
     if (P.hist) {  // flush the shared-memory part of the histogram
         __syncthreads();

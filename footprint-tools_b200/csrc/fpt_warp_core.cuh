@@ -31,13 +31,18 @@
 namespace fpt {
 namespace wk {
 
-constexpr int kWC = 384;                      // c-space capacity of an item (computed positions, 3 rounds of 128)
+#ifndef FPT_WARP_KWC
+#define FPT_WARP_KWC 384
+#endif
+constexpr int kWC = FPT_WARP_KWC;             // c-space capacity of an item (computed positions, rounds of 128)
 constexpr int kWPad = 56;                     // slots staged before and after the computed range (>= 5 + 50 + 1)
 constexpr int kWX = kWC + 2 * kWPad;          // 496 staged slots
 constexpr int kWXG = kWX / 4;                 // 124 groups of 4 slots
 constexpr int kWPre = 8;                      // readable slots before / after the packed-cut array
 constexpr int kWZS = kWC / 4 + 4;             // row stride of the transposed z array (2 pad entries each side)
-constexpr int kWSeqWords = 32, kWMaskWords = 16;
+// staged sequence words: the lane windows start at bit position q <= kWC - 4 + 31 and read words q/16 .. q/16 + 2
+// (2-bit codes) and q/32, q/32 + 1 (N bits)
+constexpr int kWSeqWords = (((kWC + 27) >> 4) + 3 + 3) & ~3, kWMaskWords = (((kWC + 27) >> 5) + 2 + 3) & ~3;
 constexpr unsigned kWPackedCutLimit = 0x3FFu;  // largest cut count the packed format carries
 constexpr int kWHistSubE = 16, kWHistSubO = 64;  // learn_dm bins counted in shared memory first
 
@@ -182,12 +187,14 @@ FPT_HD void stage_issue(const StageSrc P, const StageGeo G, WarpSmem &S, int lan
         env.cp4(rawM - 1, P.cuts_m + (ok ? g : 0), ok);
     }
     if (!P.uniform) {
-        // lane l: seq[l] = bases B0 + 16 l .., msk[l] = bases B0 + 32 l .. (l < 16); stage_pack turns what lies outside
-        // the track into N
+        // seq[l] = bases B0 + 16 l .., msk[l] = bases B0 + 32 l ..; stage_fix_mask turns what lies outside the track
+        // into N
         const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
-        const long long ws = (G.B0 >> 4) + lane;
-        const bool oks = ws >= 0 && ws < nw2;
-        env.cp4(S.seq + lane, P.seq2 + (oks ? ws : 0), oks);
+        for (int l = lane; l < kWSeqWords; l += 32) {
+            const long long ws = (G.B0 >> 4) + l;
+            const bool oks = ws >= 0 && ws < nw2;
+            env.cp4(S.seq + l, P.seq2 + (oks ? ws : 0), oks);
+        }
         if (lane < kWMaskWords) {
             const long long wm = (G.B0 >> 5) + lane;
             const bool okm = wm >= 0 && wm < nwm;
@@ -380,6 +387,7 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
     unsigned nw = 0;
     if (!P.uniform) {
         const int q = (int)(G.gbase - 8 - G.B0) + c0;  // bit position of base g0-8 in the staged words
+        static_assert(kWMaskWords <= 32, "one mask word per lane");
         FPT_EMU_ASSERT(q >= 0 && (q >> 4) + 2 < kWSeqWords && (q >> 5) + 1 < kWMaskWords);
         const int w = q >> 4, wm = q >> 5, sh = (q & 15) * 2;
         const unsigned s0 = S.seq[w], s1 = S.seq[w + 1], s2 = S.seq[w + 2];
@@ -680,9 +688,11 @@ FPT_HD bool process_item(const ScoreParams &P, const WItem *cur, const WItem *ne
     const int wh = want_win ? P.wh_max : 0;
     ItemGeo G;
     bool good = false;
+    // this lane's copies — the raw data of `cur`, issued by the previous pass — have landed; the warp barrier publishes
+    // all lanes' copies
+    warp.each([&](int) { env.cp_wait(); });
     if (cur) {
         G = item_geometry(*cur, wh);
-        warp.each([&](int) { env.cp_wait(); });  // this lane's copies have landed; the warp barrier publishes all of them
         const unsigned seen = warp.or_reduce([&](int lane) {
             unsigned s = 0;
             for (int xg = lane; xg < G.NXG; xg += 32) s |= stage_pack(S, xg);
@@ -713,6 +723,7 @@ FPT_HD bool process_item(const ScoreParams &P, const WItem *cur, const WItem *ne
     // the packed cuts, the window sums and the sequence words are dead from here on: the next item's raw data starts
     // its way into them now and arrives while this item's windows are evaluated
     if (next) {
+        warp.each([&](int) { env.cp_wait(); });  // the record of `next` (copied asynchronously since the top of the pass)
         const ItemGeo Gn = item_geometry(*next, wh);
         const StageGeo sg = {Gn.G0, Gn.B0, Gn.NXG};
         warp.each([&](int lane) { env.stage(stage_src(P), sg, S, lane); });

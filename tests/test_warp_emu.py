@@ -26,11 +26,12 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(CUDA_INC), reason="CUDA header
 
 @pytest.fixture(scope="module")
 def emu(oracle):
-    so = os.path.join(EMU_DIR, "libwarp_emu.so")
+    extra = os.environ.get("FPT_EMU_FLAGS", "").split()   # e.g. -DFPT_WARP_KWC=512 to emulate a build variant
+    so = os.path.join(EMU_DIR, "libwarp_emu%s.so" % ("_" + "_".join(f.strip("-D").replace("=", "") for f in extra) if extra else ""))
     srcs = [os.path.join(EMU_DIR, "warp_emu.cpp")] + [os.path.join(CSRC, f) for f in
                                                       ("fpt_warp_core.cuh", "fpt_portable.cuh", "fpt_internal.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + CSRC,
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", *extra, "-I" + CUDA_INC, "-I" + CSRC,
                         "-o", so, srcs[0], "-L" + os.path.join(ROOT, "oracle"), "-loracle",
                         "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
     lib = C.CDLL(so)
@@ -186,7 +187,7 @@ def test_one_long_interval_and_misaligned_outputs(emu, oracle, table, lut):
     out, redo, stats = run_emu(emu, oracle, batch, table, 50, (3, 5, 7), lut, misalign=1)
     ref = oracle_ref(oracle, batch, info, table, 50, (3, 5, 7))
     check(out, ref, redo, (3, 5, 7), "60 kb")
-    assert stats[0] > 300
+    assert stats[0] > 200   # ~170 pieces per interval at kWC = 384
 
 
 @pytest.mark.parametrize("scales", [(5,), (0, 2, 8), (3, 3, 7), (7, 3, 5), (1, 4)])
