@@ -95,7 +95,7 @@ struct fpt_ctx {
     int allow_fused = 1;    // FPT_B200_PATH=fast: skip the fused kernel (two-kernel throughput path instead)
     int allow_warp = 1;     // FPT_B200_PATH=fused / fast: skip the warp-autonomous kernel (the CTA-tiled kernels instead)
     bool warp_prepared = false;
-    DevBuf items;           // [n_items | work counter | redo count | pad] ints, then the WItem records, then the redo ranges
+    DevBuf items;           // planner scratch of the warp-autonomous kernel (warp_plan_layout): head ints, stream offsets, records, redo ranges
     int fused_inwin = 0;    // FPT_B200_FUSED_WIN=1: Stouffer windows inside the fused kernel instead of the streaming kernel
     bool fused_prepared = false;
     DevBuf direct;          // [count | list] of positions whose NB p-value is evaluated by direct_fix_kernel
@@ -467,20 +467,18 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
     // and nothing intermediate in HBM.
     if (fused && ctx->allow_warp && wk::warp_geometry_ok(hw, shw, ktrim, wh_max, p.combine != 0, a->win_out != nullptr) &&
         wk::warp_params_finish(p, a, wh_max)) {
-        const size_t cap = warp_items_capacity(a->n_iv, a->total);
-        const size_t head = 64, items_bytes = (cap * sizeof(WItem) + 63) & ~(size_t)63;
-        CU(ctx->items.need(head + items_bytes + cap * 3 * sizeof(long long)));
-        int *hd = ctx->items.as<int>();
-        WItem *items = reinterpret_cast<WItem *>(ctx->items.as<char>() + head);
-        p.items = items;
-        p.n_items = hd;
-        p.work_counter = hd + 1;
-        p.redo_count = hd + 2;
-        p.redo_ranges = reinterpret_cast<long long *>(ctx->items.as<char>() + head + items_bytes);
-        CU(cudaMemsetAsync(hd, 0, head, ctx->stream));
+        const size_t need = warp_plan_layout(nullptr, a->n_iv, a->total).bytes;
+        CU(ctx->items.need(need));
+        const WarpPlanBufs pb = warp_plan_layout(ctx->items.as<char>(), a->n_iv, a->total);
+        p.items = pb.items;
+        p.n_items = pb.head;
+        p.work_counter = pb.head + 1;
+        p.redo_count = pb.head + 2;
+        p.redo_ranges = pb.redo_ranges;
+        CU(cudaMemsetAsync(pb.head, 0, 64, ctx->stream));
         {
             ProfScope ps(ctx, FPT_KERNEL_PLAN);
-            CU(launch_plan_items(ctx->stream, p.out_off, p.iv_start, p.n_iv, p.wh_max, items, hd));
+            CU(launch_plan_items(ctx->stream, p.out_off, p.iv_start, p.n_iv, p.wh_max, pb, ctx->sm_count));
         }
         ctx->launches++;
         if (!ctx->warp_prepared) {

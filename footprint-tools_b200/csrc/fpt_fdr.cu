@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
                         double acc = z[0];
                         for (int h = 1; h <= P.hw; ++h) acc += z[-h] + z[h];
                         const double a = acc * (-P.inv_sqrt_k);
-                        v = fabs(a) < 26.0 ? ndtr_fast1(a, s4) : ndtr_slow(a);
+                        // (a non-finite sum — a null draw with p < 2^-53 has z = +inf — is NaN in the reference: ndtr.c:34-59)
+                        v = fabs(a) < 26.0 ? ndtr_fast1(a, s4) : (fabs(a) <= 1.79769313486231570815e308 ? ndtr_slow(a) : a - a);
                     }
                     count_null(v);
                 }

@@ -31,13 +31,20 @@ constexpr int kFastXCap = 8 * kFastThreads;       // staged slots per sub-tile
 constexpr int kFastHalfWin = 5;                   // half_win_width it is instantiated for
 constexpr int kFastMaxScaleHalfWin = 8;           // Stouffer half-width limit of the fast kernel
 
-// Work item of the warp-autonomous kernel (fpt_warp.cu): outputs [ta, tb) (interval-local) of interval iv.
+// Work of the warp-autonomous kernel (fpt_warp.cu). A sub-item = outputs [ta, tb) (interval-local) of interval iv;
+// a work item = a pack of up to kWMaxSub sub-items that together fill the warp's lane-groups (fpt_warp_core.cuh).
 struct alignas(16) WItem {
     long long o0;  // out_off[iv]
     long long st;  // iv_start[iv]
     int len;       // interval length
     int ta, tb;
     int iv;
+};
+constexpr int kWMaxSub = 4;
+struct alignas(16) WPack {
+    int nsub;
+    int cgs[kWMaxSub - 1];  // first lane-group of sub-items 1 .. 3 in the item
+    WItem sub[kWMaxSub];
 };
 
 struct ScoreParams {
@@ -89,11 +96,12 @@ struct ScoreParams {
     // warp-autonomous kernel (fpt_warp.cu)
     int wmode;                 // windows: 0 none, 1 = {3}, 2 = {3, 5, 7}, 3 = win_h[0 .. n_win_h) (ascending, <= 3)
     int win_h[3], n_win_h;
+    int k_row[3];              // first output row of half-width win_h[k]
     long long win_row_off[FPT_MAX_SCALES];  // s * total: offset of output row s in winp_out
-    const WItem *items;        // built by plan_items_kernel
+    const WPack *items;        // built by the planner kernels
     const int *n_items;
     int *work_counter;         // next item to hand out
-    long long *redo_ranges;    // 3 per item whose cut counts exceed the packed range; count in redo_count
+    long long *redo_ranges;    // 3 per sub-item of an item whose cut counts exceed the packed range; count in redo_count
 };
 
 // window kernel of the fast path (fpt_fast.cu)
@@ -123,9 +131,19 @@ cudaError_t launch_score_fused(cudaStream_t st, const ScoreParams &p, int grid, 
 cudaError_t launch_direct_fix(cudaStream_t st, const ScoreParams &p, int sm_count);
 
 // fpt_warp.cu: the warp-autonomous fused kernel (one launch: track -> exp / obs / p / windowed p)
-size_t warp_items_capacity(long long n_iv, long long total);
+struct WarpPlanBufs {       // carved out of one device allocation by warp_plan_layout()
+    int *head;              // [n_items | work counter | redo count | ticket | ...] (64 bytes, zeroed before every plan)
+    long long *pw;          // n_iv: weighted group offset of every interval
+    long long *bsum;        // per planner block
+    int *first_iv;          // per item: the interval whose weighted range holds the item's first stream unit
+    WPack *items;
+    long long *redo_ranges; // 3 per handed-back sub-item
+    size_t cap_items;
+    size_t bytes;           // total size
+};
+WarpPlanBufs warp_plan_layout(void *base, long long n_iv, long long total);
 cudaError_t launch_plan_items(cudaStream_t st, const long long *out_off, const long long *iv_start, long long n_iv, int wh,
-                              WItem *items, int *n_items);
+                              const WarpPlanBufs &b, int sm_count);
 cudaError_t score_warp_prepare();
 cudaError_t launch_score_warp(cudaStream_t st, const ScoreParams &p, int sm_count, bool smooth);  // p.wmode selects the window variant
 

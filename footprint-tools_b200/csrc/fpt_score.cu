@@ -635,6 +635,8 @@ cudaError_t score_kernel_prepare(size_t smem) {
     if (rc != cudaSuccess) return rc;
     std::lock_guard<std::mutex> lock(mu);
     if (dev >= 0 && dev < 64 && smem <= prepared[dev]) return cudaSuccess;
+    // (maximum shared-memory carve-out, like the warp-autonomous kernel this one follows in list mode)
+    cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     rc = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc == cudaSuccess && dev >= 0 && dev < 64) prepared[dev] = smem;
     return rc;

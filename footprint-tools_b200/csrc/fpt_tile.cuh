@@ -375,10 +375,15 @@ __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, d
         const double one0 = __hiloint2double(~(ah >> 31) & 0x3FF00000, 0);
         res[e] = __fma_rn(ers, G[e], one0);  // tail for a < 0, 1 - tail otherwise (see ndtr_fast1)
     }
-    if (slow) {  // |a| >= 26, infinite or NaN: the Cephes replica (rare)
+    if (slow) {
+        // |a| >= 26, infinite or NaN. Infinite sums are common — a p-value below 2^-53 has z = ndtri(1 - p) = +inf — and
+        // need no arithmetic: hcephes_ndtr (ndtr.c:34-59) returns NaN for +inf, -inf and NaN alike (erfce(inf) is
+        // inf / inf; the "NaN windows" of DESIGN.md §4). Only a finite |a| >= 26 takes the Cephes replica.
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (!(fabs(a[e]) < 26.0)) res[e] = ndtr_slow(a[e]);
+        for (int e = 0; e < 4; ++e) {
+            const double ae = a[e];
+            if (!(fabs(ae) < 26.0)) res[e] = fabs(ae) <= 1.79769313486231570815e308 ? ndtr_slow(ae) : ae - ae;
+        }
     }
 }
 #else

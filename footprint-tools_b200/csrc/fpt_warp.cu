@@ -1,6 +1,7 @@
 // fpt_warp.cu — device side of the warp-autonomous scoring kernel (steps in fpt_warp_core.cuh): the item planner,
-// the persistent kernel (one 12-warp CTA per SM, every warp fetches work items from a global counter and runs an
-// item from the packed track to its outputs with no block barrier), and the launchers.
+// the persistent kernel (one 12-warp CTA per SM, every warp fetches work items — packs of interval pieces that fill
+// its 96 lane-groups — from a global counter and runs an item from the packed track to its outputs with no block
+// barrier), and the launchers.
 #include "fpt_tile.cuh"
 #include "fpt_warp_core.cuh"
 
@@ -16,44 +17,105 @@ using namespace wk;
 constexpr int kWWarps = FPT_WARP_WARPS;     // warps per CTA (one CTA per SM)
 constexpr int kWThreads = 32 * kWWarps;
 
-// ---- planner: intervals -> work items (cli/detect.py scores an interval per call; a long interval is cut into
-// pieces of at most kWC computed positions whose outputs start on multiples of 4 of the flat output index) ----------
-__global__ void __launch_bounds__(256) plan_items_kernel(const long long *__restrict__ out_off,
-                                                         const long long *__restrict__ iv_start, long long n_iv, int wh,
-                                                         WItem *__restrict__ items, int *__restrict__ n_items) {
-    __shared__ int wsum[8];
-    __shared__ int block_base;
-    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+// ---- planner: intervals -> packs (fpt_warp_core.cuh "planning"). ONE kernel of at most one 1024-thread block per SM
+// (all co-resident) whose three phases are separated by a grid-wide barrier — three separate launches cost more in
+// launch gaps on the scoring stream than the planning itself:
+//   1  stream weight of every interval, exclusive scan inside each chunk of 1024 intervals, chunk totals
+//   2  global stream offset of every interval (chunk prefix + local offset); the interval that holds an item's first
+//      stream unit writes itself into first_iv[item]; block 0 publishes the number of items
+//   3  one thread per item: the sub-items of its stream range -> the WPack record
+constexpr int kPlanThreads = 1024;
+
+// exclusive scan over the block; *total = the block's sum (shared memory; valid after the call)
+__device__ __forceinline__ long long plan_block_excl(long long v, long long *wsum, long long *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long o0 = 0, len = 0, st = 0;
-    int cnt = 0;
-    if (k < n_iv) {
-        o0 = __ldg(out_off + k);
-        len = __ldg(out_off + k + 1) - o0;
-        st = __ldg(iv_start + k);
-        cnt = item_count(o0, len, wh);
-    }
-    int incl = cnt;
+    long long incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
+        const long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
     }
+    __syncthreads();  // wsum / *total of a previous call have been read
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int w = 0; w < 8; ++w) { const int v = wsum[w]; wsum[w] = tot; tot += v; }
-        block_base = tot ? atomicAdd(n_items, tot) : 0;
+    if (warp == 0) {
+        const long long x = wsum[lane];
+        long long xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= d) xi += t;
+        }
+        wsum[lane] = xi - x;
+        if (lane == 31) *total = xi;
     }
     __syncthreads();
-    int slot = block_base + wsum[warp] + incl - cnt;
-    for (int j = 0; j < cnt; ++j) {
-        WItem it;
-        it.o0 = o0; it.st = st; it.len = (int)len; it.iv = (int)k;
-        item_range(o0, len, wh, j, cnt, &it.ta, &it.tb);
-        items[slot + j] = it;
+    return wsum[warp] + incl - v;
+}
+
+// grid-wide barrier over a monotonic counter (zeroed by the host before the launch); every block of the grid is resident
+__device__ __forceinline__ void plan_grid_sync(int *counter, int &round) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++round;
+        __threadfence();
+        atomicAdd(counter, 1);
+        const int want = round * (int)gridDim.x;
+        int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < want);
+        __threadfence();
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPlanThreads, 1) plan_kernel(const long long *__restrict__ out_off,
+                                                               const long long *__restrict__ iv_start, long long n_iv, int OG, int wh,
+                                                               long long *pw, long long *bsum, int *first_iv, int *head,
+                                                               WPack *__restrict__ items) {
+    __shared__ long long wsum[32];
+    __shared__ long long tot;
+    const long long n_chunks = (n_iv + kPlanThreads - 1) / kPlanThreads;
+    int round = 0;
+    // phase 1
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const long long k = c * kPlanThreads + threadIdx.x;
+        long long w = 0;
+        if (k < n_iv) {
+            const long long o0 = __ldg(out_off + k);
+            w = group_weight(group_count(o0, __ldg(out_off + k + 1) - o0));
+        }
+        const long long ex = plan_block_excl(w, wsum, &tot);
+        if (k < n_iv) pw[k] = ex;
+        if (threadIdx.x == 0) bsum[c] = tot;
+    }
+    plan_grid_sync(head + 3, round);
+    // phase 2
+    for (long long c = blockIdx.x; c <= n_chunks; c += gridDim.x) {   // (chunk n_chunks: the grand total only)
+        // stream offset of the chunk = sum of the totals of the chunks before it
+        long long part = 0;
+        for (long long q = threadIdx.x; q < c; q += kPlanThreads) part += __ldcg(bsum + q);
+        plan_block_excl(part, wsum, &tot);
+        const long long base = tot;
+        if (c == n_chunks) {
+            if (threadIdx.x == 0) head[0] = (int)((base + OG - 1) / OG);
+            break;
+        }
+        const long long k = c * kPlanThreads + threadIdx.x;
+        if (k < n_iv) {
+            const long long o0 = __ldg(out_off + k);
+            const long long w = group_weight(group_count(o0, __ldg(out_off + k + 1) - o0));
+            const long long a = __ldcg(pw + k) + base;
+            pw[k] = a;
+            for (long long j = (a + OG - 1) / OG; j * OG < a + w; ++j) first_iv[j] = (int)k;
+        }
+    }
+    plan_grid_sync(head + 3, round);
+    // phase 3
+    const int n_items = *reinterpret_cast<volatile int *>(head);
+    for (long long j = blockIdx.x * (long long)kPlanThreads + threadIdx.x; j < n_items; j += (long long)gridDim.x * kPlanThreads)
+        plan_pack(out_off, iv_start, pw, n_iv, __ldcg(first_iv + j), j, OG, wh, items + j);  // in place (sub-items beyond nsub stay unwritten)
 }
 
 struct DeviceWarp {
@@ -82,7 +144,7 @@ struct DeviceEnv {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
                      "r"(ok ? 4 : 0) : "memory");
     }
-    __device__ __forceinline__ void stage(const StageSrc T, const StageGeo g, WarpSmem &S, int lane) { stage_issue(T, g, S, lane, *this); }
+    __device__ __forceinline__ void stage(const StageSrc T, const PackGeo &Q, WarpSmem &S, int lane) { stage_issue(T, Q, S, lane, *this); }
     __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
     __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
     __device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) { fpt::st256(p, a, b, c, d); }
@@ -128,32 +190,32 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
         return v;
     };
     // Software pipeline over the items of this warp: while item i is processed, the raw cut counts of item i+1 are
-    // copied into shared memory asynchronously (issued inside process_item, before the window step), its record was
-    // copied into S.next the same way at the top of the pass, and the index of item i+2 is on its way back from the
-    // global counter — no step of an item waits for a global round trip.
-    int cur = -1;          // no current item in the first pass: it only issues the copies of the warp's first item
+    // copied into shared memory asynchronously (issued inside process_item, before the window step, from the geometry
+    // built there into the other PackGeo set), its record was copied into S.next the same way at the top of the pass,
+    // and the index of item i+2 is on its way back from the global counter — no step of an item waits for a global
+    // round trip.
+    bool have_cur = false;  // no current item in the first pass: it only issues the copies of the warp's first item
+    int par = 0;
     int nxt = __shfl_sync(0xffffffffu, ask(), 0);
-    WItem it = {};
-    while (cur >= 0 || nxt < n_items) {
+    constexpr int kRecChunks = (int)(sizeof(WPack) / 16);
+    static_assert(kRecChunks <= 32 && sizeof(WPack) % 16 == 0, "one 16-byte chunk of the record per lane");
+    while (have_cur || nxt < n_items) {
         const bool have_next = nxt < n_items;
         const int asked = have_next ? ask() : 0;
-        if (cur >= 0) it = S.next;   // parked by the previous pass
-        __syncwarp();
-        if (have_next && lane == 0) {  // record of the next item: global -> shared, asynchronously
-            env.cp16(reinterpret_cast<uint32_t *>(&S.next), reinterpret_cast<const uint32_t *>(P.items + nxt));
-            env.cp16(reinterpret_cast<uint32_t *>(&S.next) + 4, reinterpret_cast<const uint32_t *>(P.items + nxt) + 4);
-        }
+        if (have_next && lane < kRecChunks)  // record of the next item: global -> shared, asynchronously
+            env.cp16(reinterpret_cast<uint32_t *>(&S.next) + 4 * lane, reinterpret_cast<const uint32_t *>(P.items + nxt) + 4 * lane);
         env.cp_commit();
-        const bool ok = process_item<SMOOTH, WM>(P, cur >= 0 ? &it : nullptr, have_next ? &S.next : nullptr, S, tab, dmp,
-                                                  hsub, W, env);
-        if (!ok && lane == 0) {
+        const bool ok = process_item<SMOOTH, WM>(P, have_cur, par, have_next ? &S.next : nullptr, S, tab, dmp, hsub, W, env);
+        if (!ok && lane < S.pg[par].nsub) {
+            const SubStage &t = S.pg[par].s[lane];
             const int slot = atomicAdd(P.redo_count, 1);
-            P.redo_ranges[3 * slot] = it.o0 + it.ta;
-            P.redo_ranges[3 * slot + 1] = it.o0 + it.tb;
-            P.redo_ranges[3 * slot + 2] = it.iv;
+            P.redo_ranges[3 * slot] = t.ra;
+            P.redo_ranges[3 * slot + 1] = t.rb;
+            P.redo_ranges[3 * slot + 2] = t.iv;
         }
         __syncwarp();
-        cur = have_next ? nxt : -1;
+        have_cur = have_next;
+        par ^= 1;
         nxt = have_next ? __shfl_sync(0xffffffffu, asked, 0) : nxt;
     }
     if (P.hist) {  // flush the shared-memory part of the histogram
@@ -172,16 +234,37 @@ size_t score_warp_smem_bytes(bool hist) {
 
 }  // namespace
 
-size_t warp_items_capacity(long long n_iv, long long total) {
-    const int os_min = (kWC - 3 - 2 * kFastMaxScaleHalfWin) & ~3;
-    return (size_t)n_iv + (size_t)(total / os_min) + 2;
+WarpPlanBufs warp_plan_layout(void *base, long long n_iv, long long total) {
+    // stream units: every interval weighs at most its groups (<= len / 4 + 2) + kWMinW; items hold >= out_groups(max) units
+    const int og_min = out_groups(kFastMaxScaleHalfWin);
+    const size_t units = (size_t)(total / 4) + (size_t)n_iv * (2 + kWMinW);
+    WarpPlanBufs b;
+    b.cap_items = units / og_min + 2;
+    const size_t n_blocks = ((size_t)n_iv + kPlanThreads - 1) / kPlanThreads;
+    auto up = [](size_t v) { return (v + 63) & ~(size_t)63; };
+    char *p = static_cast<char *>(base);
+    size_t off = 0;
+    b.head = reinterpret_cast<int *>(p + off); off += 64;
+    b.pw = reinterpret_cast<long long *>(p + off); off += up((size_t)n_iv * sizeof(long long));
+    b.bsum = reinterpret_cast<long long *>(p + off); off += up((n_blocks + 1) * sizeof(long long));
+    b.first_iv = reinterpret_cast<int *>(p + off); off += up(b.cap_items * sizeof(int));
+    b.items = reinterpret_cast<WPack *>(p + off); off += up(b.cap_items * sizeof(WPack));
+    b.redo_ranges = reinterpret_cast<long long *>(p + off); off += up(((size_t)n_iv + b.cap_items) * 3 * sizeof(long long));
+    b.bytes = off;
+    return b;
 }
 
 cudaError_t launch_plan_items(cudaStream_t st, const long long *out_off, const long long *iv_start, long long n_iv, int wh,
-                              WItem *items, int *n_items) {
+                              const WarpPlanBufs &b, int sm_count) {
     if (n_iv <= 0) return cudaSuccess;
-    const long long blocks = (n_iv + 255) / 256;
-    plan_items_kernel<<<(unsigned)blocks, 256, 0, st>>>(out_off, iv_start, n_iv, wh, items, n_items);
+    const int OG = out_groups(wh);
+    const long long chunks = (n_iv + kPlanThreads - 1) / kPlanThreads + 1;
+    const long long work = (long long)(b.cap_items + kPlanThreads - 1) / kPlanThreads;
+    long long blocks = chunks > work ? chunks : work;
+    if (blocks > sm_count) blocks = sm_count;   // one block per SM: the grid barrier needs every block resident
+    // the same shared-memory carve-out as the scoring kernel that follows: no reconfiguration of the SMs between them
+    cudaFuncSetAttribute(plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    plan_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(out_off, iv_start, n_iv, OG, wh, b.pw, b.bsum, b.first_iv, b.head, b.items);
     return cudaGetLastError();
 }
 

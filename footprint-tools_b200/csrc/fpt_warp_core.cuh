@@ -11,10 +11,14 @@
 //   Stouffer windows             footprint_tools/stats/windowing.h:53-84, windowing.pyx:34-58
 //   learn_dm histogram           footprint_tools/cli/learn_dm.py:276-287
 //
-// Design: one WARP owns one work item — an interval, or a piece of at most kWC positions of a long
-// one — from the packed track to exp / obs / p and the windowed p-values. Nothing intermediate touches HBM, no
-// block barrier exists: the five steps of an item are separated by __syncwarp only, and the 16 warps of an SM
-// run desynchronised, so that the memory latency of one warp's staging is covered by the arithmetic of the others.
+// Design: one WARP owns one work item from the packed track to exp / obs / p and the windowed
+// p-values. An item is a PACK of up to kWMaxSub sub-items — whole intervals or pieces of intervals — that together
+// fill the warp's kWC / 4 = 96 lane-groups of 4 positions: the planner divides the stream of 4-position output groups
+// of all intervals into equal runs, so that every round of the scoring and window steps has all 32 lanes at work
+// whatever the interval lengths are (one interval per item left a quarter of the lanes idle on 150-1200 bp DHS
+// intervals). Nothing intermediate touches HBM, no block barrier exists: the five steps of an item are separated by
+// __syncwarp only, and the warps of an SM run desynchronised, so that the memory latency of one warp's staging is
+// covered by the arithmetic of the others.
 //   A  stage    cut counts of the item's slots (halo of 56 on both sides), strand-PACKED: slot x = lo16 cuts+[x] |
 //               hi16 cuts-[x-1] (the pair cli/detect.py:121-122 adds); the item's sequence words
 //   B  sums     10-wide window sums of both strands at once (16x2 adds); per group of 4 slots {min, max, sum+, sum-}
@@ -35,30 +39,73 @@ namespace wk {
 #define FPT_WARP_KWC 384
 #endif
 constexpr int kWC = FPT_WARP_KWC;             // c-space capacity of an item (computed positions, rounds of 128)
-constexpr int kWPad = 56;                     // slots staged before and after the computed range (>= 5 + 50 + 1)
-constexpr int kWX = kWC + 2 * kWPad;          // 496 staged slots
-constexpr int kWXG = kWX / 4;                 // 124 groups of 4 slots
+constexpr int kWCG = kWC / 4;                 // 96 lane-groups of 4 positions
+constexpr int kWPad = 56;                     // slots staged before and after a sub-item's computed range (>= 5 + 50 + 1)
+constexpr int kWHaloG = 2 * kWPad / 4;        // 28 groups of halo per sub-item
+constexpr int kWXG = kWCG + kWMaxSub * kWHaloG;  // 208 groups of 4 staged slots
+constexpr int kWX = 4 * kWXG;                 // 832 staged slots
 constexpr int kWPre = 8;                      // readable slots before / after the packed-cut array
-constexpr int kWZS = kWC / 4 + 4;             // row stride of the transposed z array (2 pad entries each side)
-// staged sequence words: the lane windows start at bit position q <= kWC - 4 + 31 and read words q/16 .. q/16 + 2
-// (2-bit codes) and q/32, q/32 + 1 (N bits)
-constexpr int kWSeqWords = (((kWC + 27) >> 4) + 3 + 3) & ~3, kWMaskWords = (((kWC + 27) >> 5) + 2 + 3) & ~3;
+constexpr int kWZS = kWCG + 4;                // row stride of the transposed z array (2 pad entries each side)
+// An interval's groups weigh at least kWMinW in the planner's stream, which bounds the sub-items of a pack: a run of
+// OG <= kWCG stream units touches at most two whole intervals and two partial ones when 3 kWMinW + 2 > OG.
+constexpr int kWMinW = (kWCG - 2) / 3 + 1;
+static_assert(kWMaxSub == 4 && 3 * kWMinW + 2 > kWCG, "sub-item bound of a pack");
+// staged sequence words of a sub-item of n c-groups: its lane windows start at bit position q <= 4 n - 4 + 31 and
+// read words q/16 .. q/16 + 2 (2-bit codes) and q/32, q/32 + 1 (N bits)
+FPT_HD int sub_seq_words(int ncg) { return ((4 * ncg + 27) >> 4) + 3; }
+FPT_HD int sub_mask_words(int ncg) { return ((4 * ncg + 27) >> 5) + 2; }
+constexpr int kWSeqWords = (((kWC + 27 * kWMaxSub) >> 4) + 3 * kWMaxSub + 3) & ~3;
+constexpr int kWMaskWords = 32;               // one per lane (stage_fix_mask)
+static_assert(((kWC + 27 * kWMaxSub) >> 5) + 2 * kWMaxSub <= kWMaskWords, "one mask word per lane");
 constexpr unsigned kWPackedCutLimit = 0x3FFu;  // largest cut count the packed format carries
 constexpr int kWHistSubE = 16, kWHistSubO = 64;  // learn_dm bins counted in shared memory first
 
-// per-warp shared memory (11 488 bytes)
+// What steps D and E need of one sub-item, in the ITEM's c-space: lane-group cg holds item positions 4 cg + e.
+struct alignas(16) SubGeo {
+    long long Fb;      // flat output index of the group: Fb + 4 cg
+    int cb, ce;        // computed positions: 4 cg + e in [cb, ce)
+    int oa, oz;        // outputs:            4 cg + e in [oa, oz)
+    int xs;            // staged slot of element 0: 4 cg + xs
+    int qs, qm;        // bit position of base g0 - 8 in the staged sequence / mask words: qs + 4 cg, qm + 4 cg
+    int Tb;            // interval-local index of element 0: Tb + 4 cg
+    int len;           // interval length
+    int pad_;
+};
+// What staging (and the hand-back of the item) needs of one sub-item.
+struct alignas(16) SubStage {
+    long long G0, B0;  // track coordinate of the sub-item's slot 0 / of bit 0 of its first staged sequence word
+    long long ra, rb;  // flat output range of the sub-item
+    int xg0, nxg;      // first staged group, number of staged groups
+    int sw, mw;        // first staged sequence / mask word
+    int nsw, nmw;      // number of them
+    int iv, pad_;
+};
+// Geometry of a pack, built by prepare_pack one item ahead (two sets per warp, used alternately).
+struct alignas(16) PackGeo {
+    int nsub, ncg, nxg, nmw;   // sub-items, c-groups, staged groups, staged mask words of the whole item
+    int cge[kWMaxSub];         // c-group where sub-item i ends (INT_MAX beyond the last)
+    int xge[kWMaxSub];         // staged group where sub-item i ends
+    SubGeo g[kWMaxSub];
+    SubStage s[kWMaxSub];
+};
+
+// per-warp shared memory (15 152 bytes)
 struct alignas(16) WarpSmem {
     uint32_t cw_[kWPre + kWX + kWPre];   // packed cuts, slot x at cw_[kWPre + x]
     uint32_t wcw[kWX + 16];              // packed 10-wide sums
     uint4 GA[kWXG];                      // group aggregates (ping)
-    uint4 GB[kWXG];                      //                  (pong)
-    uint32_t seq[kWSeqWords];            // 2-bit codes of the item's bases, word 0 = bases [B0, B0 + 16)
-    uint32_t msk[kWMaskWords];           // N bits, word 0 = bases [B0, B0 + 32)
-    double zsT[4 * kWZS];                // z of the item, transposed: zsT[e * kWZS + 2 + cg] = z[4 cg + e]
-    WItem next;                          // record of the warp's next item (device: parked here by the kernel loop)
+    union {
+        uint4 GB[kWXG];                  //                  (pong) — dead once the 24-group aggregates are in GA,
+        double zsT[4 * kWZS];            // z of the item, transposed: zsT[e * kWZS + 2 + cg] = z[4 cg + e]
+    };
+    uint32_t seq[kWSeqWords];            // 2-bit codes, sub-item i from word s[i].sw: word 0 = bases [B0, B0 + 16)
+    uint32_t msk[kWMaskWords];           // N bits, sub-item i from word s[i].mw: word 0 = bases [B0, B0 + 32)
+    PackGeo pg[2];                       // geometry of the current item and of the next one
+    WPack next;                          // record of the warp's next item (copied in asynchronously)
 };
+static_assert(sizeof(double) * 4 * kWZS <= sizeof(uint4) * kWXG, "z rows fit the pong array");
 
-// geometry of one item, identical in every lane
+// geometry of one sub-item in its own frame, identical in every lane
 struct ItemGeo {
     long long F0;      // flat output index of c = 0 (multiple of 4)
     long long gbase;   // track coordinate of c = 0
@@ -71,25 +118,56 @@ struct ItemGeo {
     int NCG, NXG;      // groups of 4 in c-space / x-space
 };
 
-FPT_HD int item_count(long long o0, long long len, int WH) {
-    if (len <= 0) return 0;
-    if (len <= kWC - 3) return 1;
-    const int OS = (kWC - 3 - 2 * WH) & ~3;
-    const long long base = o0 & ~3LL;
-    return (int)((o0 + len - base + OS - 1) / OS);
+// ---- planning (shared by the planner kernels of fpt_warp.cu and the host emulation) ----------------------------------
+// Every interval is a run of 4-position output groups aligned on multiples of 4 of the FLAT output index (so that a
+// lane's group of 4 outputs is one aligned 32-byte store): interval (o0, len) has group_count groups, the first and
+// the last possibly partial. In the planner's stream the run weighs max(groups, kWMinW) units; item j is the stream
+// range [j OG, (j + 1) OG), OG = out_groups(wh): the lane-groups of a warp minus the two groups of positions a piece
+// cut out of an interval computes beyond each cut for its windows.
+FPT_HD long long group_count(long long o0, long long len) { return len <= 0 ? 0 : ((o0 + len - (o0 & ~3LL) + 3) >> 2); }
+FPT_HD long long group_weight(long long ng) { return ng == 0 ? 0 : (ng < kWMinW ? (long long)kWMinW : ng); }
+FPT_HD int out_groups(int wh) { return kWCG - 2 * ((wh + 3) >> 2); }
+
+// the part of interval (o0, len) — weighted stream offset pw — that falls into item j; false when none does
+FPT_HD bool plan_sub(long long o0, long long len, long long st, int iv, long long pw, long long j, int OG, WItem *out) {
+    const long long ng = group_count(o0, len);
+    const long long lo = j * OG - pw;
+    const long long ga = lo > 0 ? lo : 0, gb = lo + OG < ng ? lo + OG : ng;
+    if (gb <= ga) return false;
+    const long long off = o0 & 3;
+    const long long ta = 4 * ga - off, tb = 4 * gb - off;
+    out->o0 = o0; out->st = st; out->len = (int)len; out->iv = iv;
+    out->ta = (int)(ta > 0 ? ta : 0);
+    out->tb = (int)(tb < len ? tb : len);
+    return true;
 }
 
-// piece j of n of an interval: outputs [ta, tb) in interval-local coordinates; pieces start on multiples of 4 of the
-// flat output index so that every lane's group of 4 outputs is one aligned 32-byte store
-FPT_HD void item_range(long long o0, long long len, int WH, int j, int n, int *ta, int *tb) {
-    if (n == 1) { *ta = 0; *tb = (int)len; return; }
-    const int OS = (kWC - 3 - 2 * WH) & ~3;
-    const long long base = o0 & ~3LL;
-    long long fa = base + (long long)j * OS, fb = fa + OS;
-    if (fa < o0) fa = o0;
-    if (fb > o0 + len) fb = o0 + len;
-    *ta = (int)(fa - o0);
-    *tb = (int)(fb - o0);
+// item j from the interval arrays: first = the interval whose weighted range holds stream unit j OG
+// c-groups of a sub-item: its computed positions [ta - wh, tb + wh) clipped to the interval, from the multiple of 4 of
+// the flat output index below them
+FPT_HD int sub_groups(const WItem &it, int wh) {
+    int ca = it.ta - wh, cz = it.tb + wh;
+    if (ca < 0) ca = 0;
+    if (cz > it.len) cz = it.len;
+    const long long f0 = (it.o0 + ca) & ~3LL;
+    return (int)((it.o0 + cz - f0 + 3) >> 2);
+}
+FPT_HD void plan_pack(const long long *out_off, const long long *iv_start, const long long *pw, long long n_iv, long long first,
+                      long long j, int OG, int wh, WPack *out) {
+    int n = 0, cgs = 0;
+    out->cgs[0] = out->cgs[1] = out->cgs[2] = 0;
+    for (long long k = first; k < n_iv && pw[k] < (j + 1) * OG; ++k) {
+        const long long o0 = out_off[k];
+        WItem sub;
+        if (!plan_sub(o0, out_off[k + 1] - o0, iv_start[k], (int)k, pw[k], j, OG, &sub)) continue;
+        FPT_EMU_ASSERT(n < kWMaxSub);
+        if (n >= kWMaxSub) break;
+        if (n > 0) out->cgs[n - 1] = cgs;   // first lane-group of sub-item n
+        cgs += sub_groups(sub, wh);
+        out->sub[n++] = sub;
+    }
+    FPT_EMU_ASSERT(cgs <= kWCG);
+    out->nsub = n;
 }
 
 FPT_HD ItemGeo item_geometry(const WItem &it, int WH) {
@@ -108,9 +186,64 @@ FPT_HD ItemGeo item_geometry(const WItem &it, int WH) {
     G.oa = G.cb + (it.ta - ca);
     G.oz = G.oa + (it.tb - it.ta);
     G.NCG = (G.cb + G.cn + 3) >> 2;
-    G.NXG = G.NCG + 2 * kWPad / 4;
+    G.NXG = G.NCG + kWHaloG;
     FPT_EMU_ASSERT(G.cb + G.cn <= kWC && G.NXG <= kWXG);
     return G;
+}
+
+// The geometry of a pack (executed by lanes 0 .. kWMaxSub - 1, one sub-item each; the others idle): every sub-item's
+// frame is laid into the item's c-space (lane-groups), x-space (staged slots: its groups plus kWHaloG of halo) and
+// staged sequence / mask words one after the other.
+FPT_HD void prepare_pack(const WPack &R, int wh, PackGeo &Q, int lane) {
+    if (lane >= kWMaxSub) return;
+    const int nsub = R.nsub;
+    if (lane >= nsub) {
+        Q.cge[lane] = 0x7FFFFFFF;
+        Q.xge[lane] = 0x7FFFFFFF;
+        if (nsub == 0 && lane == 0) { Q.nsub = 0; Q.ncg = 0; Q.nxg = 0; Q.nmw = 0; }
+        return;
+    }
+    // first lane-group of this sub-item (planned: R.cgs) and the staged words of the sub-items before it
+    const int cgs = lane ? R.cgs[lane - 1] : 0;
+    int sw = 0, mw = 0;
+    for (int i = 0; i < lane; ++i) {
+        const int n = R.cgs[i] - (i ? R.cgs[i - 1] : 0);
+        sw += sub_seq_words(n); mw += sub_mask_words(n);
+    }
+    const WItem &it = R.sub[lane];
+    const ItemGeo G = item_geometry(it, wh);
+    FPT_EMU_ASSERT(G.NCG == sub_groups(it, wh));
+    const int xgs = cgs + lane * kWHaloG;
+    SubGeo g;
+    g.Fb = G.F0 - 4 * cgs;
+    g.cb = G.cb + 4 * cgs; g.ce = g.cb + G.cn;
+    g.oa = G.oa + 4 * cgs; g.oz = G.oz + 4 * cgs;
+    g.xs = kWPad + 4 * lane * kWHaloG;
+    const int qb = (int)(G.gbase - 8 - G.B0) - 4 * cgs;
+    g.qs = qb + 16 * sw; g.qm = qb + 32 * mw;
+    g.Tb = G.T0 - 4 * cgs;
+    g.len = G.len;
+    g.pad_ = 0;
+    Q.g[lane] = g;
+    SubStage t;
+    t.G0 = G.G0; t.B0 = G.B0;
+    t.ra = it.o0 + it.ta; t.rb = it.o0 + it.tb;
+    t.xg0 = xgs; t.nxg = G.NXG;
+    t.sw = sw; t.mw = mw;
+    t.nsw = sub_seq_words(G.NCG); t.nmw = sub_mask_words(G.NCG);
+    t.iv = it.iv; t.pad_ = 0;
+    Q.s[lane] = t;
+    Q.cge[lane] = cgs + G.NCG;
+    Q.xge[lane] = xgs + G.NXG;
+    if (lane == nsub - 1) {
+        Q.nsub = nsub; Q.ncg = cgs + G.NCG; Q.nxg = xgs + G.NXG; Q.nmw = mw + t.nmw;
+        FPT_EMU_ASSERT(Q.ncg <= kWCG && Q.nxg <= kWXG && sw + t.nsw <= kWSeqWords && Q.nmw <= kWMaskWords);
+    }
+}
+// the sub-item of lane-group cg / staged group xg
+FPT_HD int sub_of(const int (&ends)[kWMaxSub], int v) {
+    const int4 e = *reinterpret_cast<const int4 *>(ends);
+    return (v >= e.x ? 1 : 0) + (v >= e.y ? 1 : 0) + (v >= e.z ? 1 : 0);
 }
 
 // reverse complement of a little-endian 6-mer index (first base in the two low bits; A0 C1 G2 T3)
@@ -157,22 +290,21 @@ FPT_HD StageSrc stage_src(const ScoreParams &P) {
     T.n_track = P.n_track; T.cuts_vec = P.cuts_vec; T.uniform = P.uniform;
     return T;
 }
-struct StageGeo {
-    long long G0, B0;
-    int NXG;
-};
 template <class Env>
-FPT_HD void stage_issue(const StageSrc P, const StageGeo G, WarpSmem &S, int lane, Env &env) {
-    const bool aligned = P.cuts_vec && ((G.G0 & 3) == 0);
+FPT_HD void stage_issue(const StageSrc P, const PackGeo &Q, WarpSmem &S, int lane, Env &env) {
     uint32_t *rawP = S.cw_ + kWPre, *rawM = S.wcw + 4;
-    for (int xg = lane; xg < G.NXG; xg += 32) {
+    const int nxg = Q.nxg;
+#pragma unroll 1
+    for (int xg = lane; xg < nxg; xg += 32) {
+        const int i = sub_of(Q.xge, xg);
         const int x = xg << 2;
-        const long long g = G.G0 + x;
-        if (aligned && g >= 0 && g + 4 <= P.n_track) {
+        const long long g = Q.s[i].G0 + ((xg - Q.s[i].xg0) << 2);
+        if (P.cuts_vec && (g & 3) == 0 && g >= 0 && g + 4 <= P.n_track) {
             env.cp16(rawP + x, P.cuts_p + g);
             env.cp16(rawM + x, P.cuts_m + g);
         } else {
-#pragma unroll
+            // (rolled: the kernel's hot code has to fit the SM's 32 KB instruction cache, and this is the rare path)
+#pragma unroll 1
             for (int e = 0; e < 4; ++e) {
                 const long long ge = g + e;
                 const bool ok = ge >= 0 && ge < P.n_track;
@@ -181,24 +313,34 @@ FPT_HD void stage_issue(const StageSrc P, const StageGeo G, WarpSmem &S, int lan
             }
         }
     }
-    if (lane == 0) {  // the minus-strand partner of slot 0
-        const long long g = G.G0 - 1;
+    // (the minus-strand partner of a sub-item's slot 0 belongs to packed slot 0, which no window reaches: the staged
+    // halo is one slot wider than the windows need. It is staged for the item's first slot all the same, so that the
+    // overflow test of stage_pack never reads shared memory nobody wrote.)
+    if (lane == 0 && nxg > 0) {
+        const long long g = Q.s[0].G0 - 1;
         const bool ok = g >= 0 && g < P.n_track;
         env.cp4(rawM - 1, P.cuts_m + (ok ? g : 0), ok);
     }
     if (!P.uniform) {
-        // seq[l] = bases B0 + 16 l .., msk[l] = bases B0 + 32 l ..; stage_fix_mask turns what lies outside the track
-        // into N
+        // seq[sw + l] = bases B0 + 16 l .., msk[mw + l] = bases B0 + 32 l ..; stage_fix_mask turns what lies outside the
+        // track into N
         const long long nw2 = (P.n_track + 15) >> 4, nwm = (P.n_track + 31) >> 5;
-        for (int l = lane; l < kWSeqWords; l += 32) {
-            const long long ws = (G.B0 >> 4) + l;
-            const bool oks = ws >= 0 && ws < nw2;
-            env.cp4(S.seq + l, P.seq2 + (oks ? ws : 0), oks);
-        }
-        if (lane < kWMaskWords) {
-            const long long wm = (G.B0 >> 5) + lane;
-            const bool okm = wm >= 0 && wm < nwm;
-            env.cp4(S.msk + lane, P.nmask + (okm ? wm : 0), okm);
+        const int nsub = Q.nsub;
+#pragma unroll 1
+        for (int i = 0; i < nsub; ++i) {
+            const long long B0 = Q.s[i].B0;
+            const int nsw = Q.s[i].nsw, nmw = Q.s[i].nmw;
+#pragma unroll 1
+            for (int l = lane; l < nsw; l += 32) {
+                const long long ws = (B0 >> 4) + l;
+                const bool oks = ws >= 0 && ws < nw2;
+                env.cp4(S.seq + Q.s[i].sw + l, P.seq2 + (oks ? ws : 0), oks);
+            }
+            if (lane < nmw) {
+                const long long wm = (B0 >> 5) + lane;
+                const bool okm = wm >= 0 && wm < nwm;
+                env.cp4(S.msk + Q.s[i].mw + lane, P.nmask + (okm ? wm : 0), okm);
+            }
         }
     }
     env.cp_commit();
@@ -221,10 +363,13 @@ FPT_HD unsigned stage_pack(WarpSmem &S, int xg) {
 }
 
 // N bits of the staged mask words that lie outside the track (the copy zero-filled them)
-FPT_HD void stage_fix_mask(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int lane) {
-    if (lane >= kWMaskWords) return;
+FPT_HD void stage_fix_mask(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, int lane) {
+    if (lane >= Q.nmw) return;
+    int i = 0;
+    for (int k = 1; k < kWMaxSub; ++k)
+        if (k < Q.nsub && lane >= Q.s[k].mw) i = k;
     const long long nwm = (P.n_track + 31) >> 5;
-    const long long wm = (G.B0 >> 5) + lane;
+    const long long wm = (Q.s[i].B0 >> 5) + (lane - Q.s[i].mw);
     if (wm < 0 || wm >= nwm) {
         S.msk[lane] = 0xFFFFFFFFu;
     } else {
@@ -365,20 +510,21 @@ FPT_HD void store_partial(double *dst, unsigned omask, double v0, double v1, dou
 // Env supplies what differs between the device and the host emulation: the direct NB evaluation, the 256-bit
 // store, the atomics.
 template <bool SMOOTH, class Env>
-FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, const float *tab, const double *dmp,
+FPT_HD void step_score(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, const float *tab, const double *dmp,
                        unsigned *hsub, int cg, bool want_p, bool want_z, Env &env) {
     constexpr int SHW = SMOOTH ? 50 : 0;
     constexpr int WSM = 2 * SHW + 1;
     const float dWf = SMOOTH ? (float)(WSM - 2) : 1.0f;
     const int c0 = cg << 2;
+    const SubGeo &G = Q.g[sub_of(Q.cge, cg)];  // the sub-item this lane-group belongs to
     // elements e with lo <= c0 + e < hi
     auto range4 = [&](int lo, int hi) {
         const int a = lo - c0 > 0 ? lo - c0 : 0, b = hi - c0 < 4 ? hi - c0 : 4;
         return b > a ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
     };
-    const unsigned vmask = range4(G.cb, G.cb + G.cn);   // computed positions
+    const unsigned vmask = range4(G.cb, G.ce);          // computed positions
     const unsigned omask = vmask & range4(G.oa, G.oz);  // outputs of this item
-    const int x0 = c0 + kWPad;
+    const int x0 = c0 + G.xs;
     const uint32_t *cw = S.cw_ + kWPre;
     const uint32_t *wcw = S.wcw;
 
@@ -386,14 +532,13 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
     unsigned long long kw = 0;
     unsigned nw = 0;
     if (!P.uniform) {
-        const int q = (int)(G.gbase - 8 - G.B0) + c0;  // bit position of base g0-8 in the staged words
-        static_assert(kWMaskWords <= 32, "one mask word per lane");
-        FPT_EMU_ASSERT(q >= 0 && (q >> 4) + 2 < kWSeqWords && (q >> 5) + 1 < kWMaskWords);
-        const int w = q >> 4, wm = q >> 5, sh = (q & 15) * 2;
+        const int q = G.qs + c0, qm = G.qm + c0;  // bit position of base g0-8 in the staged sequence / mask words
+        FPT_EMU_ASSERT(q >= 0 && (q >> 4) + 2 < kWSeqWords && qm >= 0 && (qm >> 5) + 1 < kWMaskWords);
+        const int w = q >> 4, wm = qm >> 5, sh = (q & 15) * 2;
         const unsigned s0 = S.seq[w], s1 = S.seq[w + 1], s2 = S.seq[w + 2];
         const unsigned lo32 = pt::funnel_r(s0, s1, sh), hi32 = pt::funnel_r(s1, s2, sh);
         kw = (((unsigned long long)hi32 << 32) | lo32) & 0xFFFFFFFFFull;
-        nw = pt::funnel_r(S.msk[wm], S.msk[wm + 1], q & 31) & 0x3FFFFu;
+        nw = pt::funnel_r(S.msk[wm], S.msk[wm + 1], qm & 31) & 0x3FFFFu;
     }
 
     // -- trimmed window sums T[strand][e] (exact integers)
@@ -410,7 +555,7 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
         using pt::vminu2;
         using pt::vadd2;
         const int g = x0 >> 2;
-        FPT_EMU_ASSERT(g - 12 >= 0 && g - 11 + 24 <= G.NXG && x0 + 56 <= 4 * G.NXG);
+        FPT_EMU_ASSERT(g - 12 >= 0 && g - 11 + 24 <= Q.nxg && x0 + 56 <= 4 * Q.nxg);
         const uint4 Ha = S.GA[g - 12], Hb = S.GA[g - 11];
         const uint4 Lq = lds128(wcw + x0 - 52), Aq = lds128(wcw + x0 - 48);
         const uint4 Bq = lds128(wcw + x0 + 48), Rq = lds128(wcw + x0 + 52);
@@ -550,7 +695,7 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
             direct = vmask;
         }
     }
-    const long long f0 = G.F0 + c0;
+    const long long f0 = G.Fb + c0;
     {
         const double exv[4] = {(double)exi[0], (double)exi[1], (double)exi[2], (double)exi[3]};
         const double obv[4] = {(double)obi[0], (double)obi[1], (double)obi[2], (double)obi[3]};
@@ -605,14 +750,16 @@ FPT_HD void step_score(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, cons
 // instructions of ndtr4 in the kernel instead of one per half-width (16 desynchronised warps share the SM's
 // instruction cache).
 template <int WM, class Env>
-FPT_HD void step_windows(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, int cg, Env &env) {
+FPT_HD void step_windows(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, int cg, Env &env) {
     constexpr int HTOP = WM == 1 ? 3 : (WM == 2 ? 7 : kFastMaxScaleHalfWin);
     const int c0 = cg << 2;
+    const SubGeo &G = Q.g[sub_of(Q.cge, cg)];
     const int a = G.oa - c0 > 0 ? G.oa - c0 : 0, b = G.oz - c0 < 4 ? G.oz - c0 : 4;
     if (b <= a) return;
     const unsigned omask = ((1u << b) - 1u) & ~((1u << a) - 1u);
-    const long long f0 = G.F0 + c0;
-    const int dl = G.T0 + c0;  // interval-local index of element 0
+    const long long f0 = G.Fb + c0;
+    const int dl = G.Tb + c0;  // interval-local index of element 0
+    const int glen = G.len;
     const double *zt = S.zsT + 2 + cg;
     int h0 = WM == 3 ? P.win_h[0] : 3, h1 = WM == 3 ? P.win_h[1] : (WM == 2 ? 5 : -1), h2 = WM == 3 ? P.win_h[2] : (WM == 2 ? 7 : -1);
     const int ns = WM == 3 ? P.n_win_h : (WM == 2 ? 3 : 1);
@@ -655,17 +802,21 @@ FPT_HD void step_windows(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, in
         const int h = h0;
         {
             // edge rule: valid iff 0 <= t - h and t + h <= len - 1, i.e. (unsigned)(t - h) < len - 2h (none when len <= 2h)
-            const int lim = G.len - 2 * h;
+            const int lim = glen - 2 * h;
             const unsigned ulim = lim > 0 ? (unsigned)lim : 0u;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if ((unsigned)(dl + e - h) >= ulim) res[e] = 1.0;
         }
-        for (unsigned m = P.h_rows[h]; m; m &= m - 1) {
-            const int s = pt::ffs32(m) - 1;
+        {   // the output row of this half-width (P.k_row: its first row; further rows with the same half-width are rare)
+            const int s = P.k_row[k];
             double *dst = P.winp_out + (P.win_row_off[s] + f0);
             if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) env.st256(dst, res[0], res[1], res[2], res[3]);
             else store_partial(dst, omask, res[0], res[1], res[2], res[3]);
+        }
+        for (unsigned m = P.h_rows[h] & (P.h_rows[h] - 1); m; m &= m - 1) {
+            const int s = pt::ffs32(m) - 1;
+            store_partial(P.winp_out + (P.win_row_off[s] + f0), omask, res[0], res[1], res[2], res[3]);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) { A0[e] = A1[e]; A1[e] = A2[e]; }
@@ -674,66 +825,74 @@ FPT_HD void step_windows(const ScoreParams &P, const ItemGeo &G, WarpSmem &S, in
 }
 
 // ---- one item, all five steps. W runs a per-lane body on every lane of the warp and synchronises the warp after
-// it (device: the calling lane + __syncwarp; host emulation: a loop over 32 lanes). On entry the item's raw cut
-// counts are on their way into shared memory (stage_issue was called for it); before the window step — or before
-// returning — the copies of `next` (the warp's next item, or NULL) are issued. Returns false when the item holds a
-// cut count the packed format cannot carry (nothing was written: the caller hands the item to the general kernel).
-// `cur` may be NULL (the warp's first pass: nothing to score yet, only the copies of `next` are issued — the kernel
-// thus holds ONE copy of the staging code).
+// it (device: the calling lane + __syncwarp; host emulation: a loop over 32 lanes). On entry the geometry of the
+// current item is in S.pg[par] and its raw cut counts are on their way into shared memory (both done by the previous
+// pass); before the window step — or before returning — the geometry of `next` (the record of the warp's next item,
+// or NULL) is built into S.pg[par ^ 1] and its copies are issued. Returns false when the item holds a cut count the
+// packed format cannot carry (nothing was written: the caller hands its sub-items to the general kernel).
+// have_cur is false in the warp's first pass: nothing to score yet, only the copies of `next` are issued — the
+// kernel thus holds ONE copy of the staging code.
 template <bool SMOOTH, int WM, class W, class Env>
-FPT_HD bool process_item(const ScoreParams &P, const WItem *cur, const WItem *next, WarpSmem &S, const float *tab,
+FPT_HD bool process_item(const ScoreParams &P, bool have_cur, int par, const WPack *next, WarpSmem &S, const float *tab,
                          const double *dmp, unsigned *hsub, W &warp, Env &env) {
     constexpr bool want_win = WM != 0;
     const bool want_p = (P.pval_out != nullptr) || want_win;
     const int wh = want_win ? P.wh_max : 0;
-    ItemGeo G;
+    const PackGeo &Q = S.pg[par];
     bool good = false;
-    // this lane's copies — the raw data of `cur`, issued by the previous pass — have landed; the warp barrier publishes
-    // all lanes' copies
+    // this lane's copies — the raw data of the current item, issued by the previous pass — have landed; the warp
+    // barrier publishes all lanes' copies
     warp.each([&](int) { env.cp_wait(); });
-    if (cur) {
-        G = item_geometry(*cur, wh);
+    const int nxg = have_cur ? Q.nxg : 0, ncg = have_cur ? Q.ncg : 0;
+    if (nxg > 0) {
         const unsigned seen = warp.or_reduce([&](int lane) {
             unsigned s = 0;
-            for (int xg = lane; xg < G.NXG; xg += 32) s |= stage_pack(S, xg);
-            if (!P.uniform) stage_fix_mask(P, G, S, lane);
-            if (want_win && lane < 16) {  // the 2 + 2 pad entries of each z row
-                const int e = lane >> 2, k = lane & 3;
-                S.zsT[e * kWZS + (k < 2 ? k : G.NCG + k)] = 0.0;
-            }
+            for (int xg = lane; xg < nxg; xg += 32) s |= stage_pack(S, xg);
+            if (!P.uniform) stage_fix_mask(P, Q, S, lane);
             return s;
         });
         good = !(seen & ~kWPackedCutLimit);
     }
     if (good) {
         warp.each([&](int lane) {
-            for (int xg = lane; xg < G.NXG; xg += 32) step_sums<SMOOTH>(S, xg);
+            for (int xg = lane; xg < nxg; xg += 32) step_sums<SMOOTH>(S, xg);
         });
         if (SMOOTH) {
-            const int n1 = G.NXG - 1, n2 = G.NXG - 3, n3 = G.NXG - 7, n4 = G.NXG - 23;
-            warp.each([&](int lane) { for (int g = lane; g < n1; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 1]); });
-            warp.each([&](int lane) { for (int g = lane; g < n2; g += 32) S.GA[g] = agg(S.GB[g], S.GB[g + 2]); });
-            warp.each([&](int lane) { for (int g = lane; g < n3; g += 32) S.GB[g] = agg(S.GA[g], S.GA[g + 4]); });
-            warp.each([&](int lane) { for (int g = lane; g < n4; g += 32) S.GA[g] = agg(agg(S.GB[g], S.GB[g + 8]), S.GB[g + 16]); });
+            // step C in two passes (each a handful of independent loads per group, so that the shared-memory latency
+            // overlaps): aggregates of 4 consecutive groups, then of six of those 4 groups apart = 24 groups
+            const int n2 = nxg - 3, n4 = nxg - 23;
+            warp.each([&](int lane) {
+#pragma unroll 2
+                for (int g = lane; g < n2; g += 32) S.GB[g] = agg(agg(S.GA[g], S.GA[g + 1]), agg(S.GA[g + 2], S.GA[g + 3]));
+            });
+            warp.each([&](int lane) {
+#pragma unroll 2
+                for (int g = lane; g < n4; g += 32)
+                    S.GA[g] = agg(agg(agg(S.GB[g], S.GB[g + 4]), agg(S.GB[g + 8], S.GB[g + 12])), agg(S.GB[g + 16], S.GB[g + 20]));
+            });
         }
         warp.each([&](int lane) {
-            for (int cg = lane; cg < G.NCG; cg += 32) step_score<SMOOTH>(P, G, S, tab, dmp, hsub, cg, want_p, want_win, env);
+            if (want_win && lane < 16) {  // the 2 + 2 pad entries of each z row (the rows live where the pong array was)
+                const int e = lane >> 2, k = lane & 3;
+                S.zsT[e * kWZS + (k < 2 ? k : ncg + k)] = 0.0;
+            }
+            for (int cg = lane; cg < ncg; cg += 32) step_score<SMOOTH>(P, Q, S, tab, dmp, hsub, cg, want_p, want_win, env);
         });
     }
     // the packed cuts, the window sums and the sequence words are dead from here on: the next item's raw data starts
     // its way into them now and arrives while this item's windows are evaluated
     if (next) {
         warp.each([&](int) { env.cp_wait(); });  // the record of `next` (copied asynchronously since the top of the pass)
-        const ItemGeo Gn = item_geometry(*next, wh);
-        const StageGeo sg = {Gn.G0, Gn.B0, Gn.NXG};
-        warp.each([&](int lane) { env.stage(stage_src(P), sg, S, lane); });
+        PackGeo &Qn = S.pg[par ^ 1];
+        warp.each([&](int lane) { prepare_pack(*next, wh, Qn, lane); });
+        warp.each([&](int lane) { env.stage(stage_src(P), Qn, S, lane); });
     }
     if (good && want_win) {
         warp.each([&](int lane) {
-            for (int cg = lane; cg < G.NCG; cg += 32) step_windows<WM == 0 ? 1 : WM>(P, G, S, cg, env);
+            for (int cg = lane; cg < ncg; cg += 32) step_windows<WM == 0 ? 1 : WM>(P, Q, S, cg, env);
         });
     }
-    return good || !cur;
+    return good || nxg == 0;
 }
 
 }  // namespace wk

@@ -28,6 +28,7 @@ inline bool warp_params_finish(ScoreParams &p, const fpt_score_args *a, int wh_m
     p.wmode = 0;
     p.n_win_h = 0;
     p.win_h[0] = p.win_h[1] = p.win_h[2] = -1;
+    p.k_row[0] = p.k_row[1] = p.k_row[2] = 0;
     if (windows) {
         for (int s = 0; s < a->n_scales; ++s) {
             p.win_row_off[s] = (long long)s * (long long)a->total;
@@ -37,6 +38,9 @@ inline bool warp_params_finish(ScoreParams &p, const fpt_score_args *a, int wh_m
         for (int h = 0; h <= kFastMaxScaleHalfWin; ++h)
             if (p.h_rows[h]) {
                 if (p.n_win_h == 3) return false;
+                int first = 0;
+                while (!((p.h_rows[h] >> first) & 1u)) ++first;
+                p.k_row[p.n_win_h] = first;
                 p.win_h[p.n_win_h++] = h;
             }
         p.wmode = (p.n_win_h == 1 && p.win_h[0] == 3) ? 1

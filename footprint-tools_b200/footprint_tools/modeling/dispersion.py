@@ -228,11 +228,13 @@ def write_dispersion_model(model, extra=None):
     out = {
         "mu_params": enc(model.mu_params),
         "r_params": enc(model.r_params),
-        "h": enc(model.h),
-        "p": enc(model.p),
-        "r": enc(model.r),
+    }
+    for key in ("h", "p", "r"):   # the fit's histogram and per-row estimates; absent from a model that was not fitted here
+        if getattr(model, key, None) is not None:
+            out[key] = enc(getattr(model, key))
+    out.update({
         "version": "%s %s" % (footprint_tools.__name__, footprint_tools.__version__),
         "date": "on %s" % datetime.now().strftime("%Y-%m-%d %H:%M:%S"),
         "metadata": extra if extra else "",
-    }
+    })
     return json.dumps(out, indent=4)

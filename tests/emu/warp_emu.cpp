@@ -49,7 +49,7 @@ struct HostEnv {
     // asynchronous copies: done at once here (the order of issue / wait / pack is what the emulation checks)
     void cp16(uint32_t *dst, const uint32_t *src) { memcpy(dst, src, 16); }
     void cp4(uint32_t *dst, const uint32_t *src, bool ok) { *dst = ok ? *src : 0u; }
-    void stage(const StageSrc T, const StageGeo g, WarpSmem &S, int lane) { stage_issue(T, g, S, lane, *this); }
+    void stage(const StageSrc T, const PackGeo &Q, WarpSmem &S, int lane) { stage_issue(T, Q, S, lane, *this); }
     void cp_commit() {}
     void cp_wait() {}
     void atomic_inc_shared(unsigned *p) { *p += 1; }
@@ -71,7 +71,7 @@ struct HostEnv {
 // Scores a batch exactly as score_device + score_warp_kernel would. bias_le: 4096 doubles, little-endian k-mer index;
 // dm: 24 doubles; lut: lut_e x lut_o (p, z) pairs or NULL. Returns the number of items handed to the general kernel
 // (their ranges are written to redo_ranges, 3 long long each, capacity redo_cap), or -1 on a geometry this kernel
-// does not serve. stats[0] = items, stats[1] = direct evaluations.
+// does not serve. stats[0] = items (packs), stats[1] = direct evaluations, stats[2] = sub-items.
 extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double dflt, int uniform, const double *dm,
                          const double *lut, int lut_e, int lut_o, long long *redo_ranges, int redo_cap, long long *stats) {
     const int hw = a->half_win_width, shw = a->smoothing_half_win_width;
@@ -98,17 +98,24 @@ extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double 
     p.hist_d0 = a->hist_d0; p.hist_d1 = a->hist_d1;
     if (!warp_params_finish(p, a, wh_max)) return -1;
 
-    // planner (plan_items_kernel)
-    std::vector<WItem> items;
+    // planner (plan_weights_kernel / plan_first_kernel / plan_packs_kernel)
+    const int OG = out_groups(p.wh_max);
+    std::vector<long long> pw((size_t)p.n_iv + 1, 0);
     for (long long k = 0; k < p.n_iv; ++k) {
-        const long long o0 = p.out_off[k], len = p.out_off[k + 1] - o0;
-        const int cnt = item_count(o0, len, p.wh_max);
-        for (int j = 0; j < cnt; ++j) {
-            WItem it;
-            it.o0 = o0; it.st = p.iv_start[k]; it.len = (int)len; it.iv = (int)k;
-            item_range(o0, len, p.wh_max, j, cnt, &it.ta, &it.tb);
-            items.push_back(it);
-        }
+        const long long o0 = p.out_off[k];
+        pw[(size_t)k + 1] = pw[(size_t)k] + group_weight(group_count(o0, p.out_off[k + 1] - o0));
+    }
+    const long long n_items = (pw[(size_t)p.n_iv] + OG - 1) / OG;
+    std::vector<int> first_iv((size_t)n_items, -1);
+    for (long long k = 0; k < p.n_iv; ++k)
+        for (long long j = (pw[(size_t)k] + OG - 1) / OG; j * OG < pw[(size_t)k + 1]; ++j) first_iv[(size_t)j] = (int)k;
+    std::vector<WPack> items((size_t)n_items);
+    long long n_sub = 0;
+    for (long long j = 0; j < n_items; ++j) {
+        FPT_EMU_ASSERT(first_iv[(size_t)j] >= 0);
+        memset(&items[(size_t)j], 0, sizeof(WPack));
+        plan_pack(p.out_off, p.iv_start, pw.data(), p.n_iv, first_iv[(size_t)j], j, OG, p.wh_max, &items[(size_t)j]);
+        n_sub += items[(size_t)j].nsub;
     }
     // one "SM": the fp32 table, the model, a sub-histogram and one warp's shared memory, poisoned before every item
     std::vector<float> tab(2 * 4096, 0.f);  // {P[k], P[revcomp k]}; 1.0 everywhere for the uniform model
@@ -116,19 +123,25 @@ extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double 
     double dmp[kModelDoubles];
     for (int i = 0; i < kModelDoubles; ++i) dmp[i] = dm ? dm[i] : 0.0;
     std::vector<unsigned> hsub(kWHistSubE * kWHistSubO, 0u);
-    WarpSmem *S = static_cast<WarpSmem *>(aligned_alloc(64, sizeof(WarpSmem)));
+    WarpSmem *S = static_cast<WarpSmem *>(aligned_alloc(64, (sizeof(WarpSmem) + 63) & ~(size_t)63));
     HostWarp W;
     HostEnv env;
     memset(S, 0xEE, sizeof(WarpSmem));  // anything read before it is written is loud
     int n_redo = 0;
     // pass -1 issues the copies of item 0 (no current item), as the kernel's first loop iteration does
-    for (long long ii = -1; ii < (long long)items.size(); ++ii) {
-        const WItem *cur = ii >= 0 ? &items[(size_t)ii] : nullptr;
-        const WItem *nx = ii + 1 < (long long)items.size() ? &items[(size_t)(ii + 1)] : nullptr;
+    int par = 0;
+    for (long long ii = -1; ii < n_items; ++ii, par ^= 1) {
+        const bool have_cur = ii >= 0;
+        const WPack *nx = nullptr;
+        if (ii + 1 < n_items) {  // the record travels through S.next, as on the device
+            memcpy(&S->next, &items[(size_t)(ii + 1)], sizeof(WPack));
+            nx = &S->next;
+        }
         // poison everything the item must not inherit from its predecessor (all but the staged raw data)
-        memset(S->GA, 0xEE, sizeof S->GA); memset(S->GB, 0xEE, sizeof S->GB); memset(S->zsT, 0xEE, sizeof S->zsT);
+        memset(S->GA, 0xEE, sizeof S->GA); memset(S->GB, 0xEE, sizeof S->GB);
+        memset(&S->pg[par ^ 1], 0xEE, sizeof(PackGeo));
         bool ok;
-#define EMU_RUN(SM, WMODE) ok = process_item<SM, WMODE>(p, cur, nx, *S, tab.data(), dmp, hsub.data(), W, env)
+#define EMU_RUN(SM, WMODE) ok = process_item<SM, WMODE>(p, have_cur, par, nx, *S, tab.data(), dmp, hsub.data(), W, env)
         if (shw != 0) {
             switch (p.wmode) {
                 case 0: EMU_RUN(true, 0); break;
@@ -146,19 +159,21 @@ extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double 
         }
 #undef EMU_RUN
         if (!ok) {
-            const WItem &it = *cur;
-            if (n_redo < redo_cap) {
-                redo_ranges[3 * n_redo] = it.o0 + it.ta;
-                redo_ranges[3 * n_redo + 1] = it.o0 + it.tb;
-                redo_ranges[3 * n_redo + 2] = it.iv;
+            const PackGeo &Q = S->pg[par];
+            for (int i = 0; i < Q.nsub; ++i) {
+                if (n_redo < redo_cap) {
+                    redo_ranges[3 * n_redo] = Q.s[i].ra;
+                    redo_ranges[3 * n_redo + 1] = Q.s[i].rb;
+                    redo_ranges[3 * n_redo + 2] = Q.s[i].iv;
+                }
+                ++n_redo;
             }
-            ++n_redo;
         }
     }
     if (p.hist)
         for (int i = 0; i < kWHistSubE * kWHistSubO; ++i)
             p.hist[(size_t)(i / kWHistSubO) * p.hist_d1 + (i % kWHistSubO)] += hsub[i];
     free(S);
-    if (stats) { stats[0] = (long long)items.size(); stats[1] = env.n_direct; }
+    if (stats) { stats[0] = n_items; stats[1] = env.n_direct; stats[2] = n_sub; }
     return n_redo;
 }

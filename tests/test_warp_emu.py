@@ -78,7 +78,7 @@ def run_emu(emu, oracle, batch, table, shw, scales, lut, hist=False, uniform=Fal
     h = np.zeros((200, 1000), dtype=np.int64) if hist else None
     args = engine.make_args(batch, 5, shw, 0.01, True, scales, out["exp"], out["obs"], None, out["pval"], winp, h)
     redo = np.zeros((4096, 3), dtype=np.int64)
-    stats = np.zeros(2, dtype=np.int64)
+    stats = np.zeros(3, dtype=np.int64)
     le = _le_table(table)
     dm = np.concatenate([synth.MU_PARAMS, synth.R_PARAMS]).astype(np.float64)
     lut_e, lut_o = (lut.e, lut.o) if lut is not None else (0, 0)
@@ -95,6 +95,16 @@ def oracle_ref(oracle, batch, info, table, shw, scales, uniform=False):
     seq, cp, cm, in_off = synth.oracle_inputs(batch, info)
     return oracle.score_batch(seq, cp, cm, in_off, batch.out_off, table, uniform=uniform, mu=synth.MU_PARAMS,
                               r=synth.R_PARAMS, hw=5, shw=shw, clip=0.01, scales=scales, nthreads=4)
+
+
+def planned_items(batch, wh, kwcg=96):
+    """Items of the planner (fpt_warp_core.cuh 'planning'): the stream of 4-position output groups of all intervals — an
+    interval weighs at least kWMinW = 32 units — divided into runs of OG = 96 - 2 ceil(wh / 4) units."""
+    o = np.asarray(batch.out_off, dtype=np.int64)
+    ng = np.where(o[1:] > o[:-1], (o[1:] + 3) // 4 - o[:-1] // 4, 0)
+    w = np.where(ng > 0, np.maximum(ng, (kwcg - 2) // 3 + 1), 0)
+    og = kwcg - 2 * ((wh + 3) // 4)
+    return -(-int(w.sum()) // og)
 
 
 def check(out, ref, redo, scales, what):
@@ -137,21 +147,28 @@ def test_emulated_kernel_matches_oracle(emu, oracle, table, lut, shw, scales, al
     assert len(redo) == 0
     ref = oracle_ref(oracle, batch, info, table, shw, scales)
     check(out, ref, redo, scales, "shw=%d aligned=%s" % (shw, aligned))
-    assert stats[0] >= batch.n_iv    # intervals beyond kWC - 3 positions are cut into pieces
+    assert stats[2] >= batch.n_iv and stats[0] == planned_items(batch, max(scales) if scales else 0)
 
 
 def test_deep_counts_hand_items_back_and_leave_the_table(emu, oracle, table, lut):
     """400x depth: cut counts beyond the packed 16-bit format (items handed to the general kernel untouched), expected /
     observed counts outside the (exp, obs) table (evaluated in place), windows over both."""
-    batch, info = synth.make_batch(150, 55, seed=71, table=table, depth_scale=30.0)
+    batch, info = synth.make_batch(150, 55, seed=71, table=table, depth_scale=12.0)
     out, redo, stats = run_emu(emu, oracle, batch, table, 50, (3, 5, 7), lut)
     ref = oracle_ref(oracle, batch, info, table, 50, (3, 5, 7))
     assert len(redo) > 0 and stats[1] > 0
     cp, cm = np.asarray(batch.cuts_plus), np.asarray(batch.cuts_minus)
-    for lo, hi, k in redo:   # a handed-back item really holds a count beyond the packed range within its staged span
+    # a handed-back item really holds a count beyond the packed range within the staged span of one of its sub-items
+    # (the whole pack — at most 96 groups of 4 consecutive outputs — is handed back with it)
+    deep = []
+    for lo, hi, k in redo:
         t0 = int(batch.iv_start[k] + (lo - batch.out_off[k]))
         a, b = max(t0 - 64, 0), min(t0 + int(hi - lo) + 64, batch.n_track)
-        assert max(cp[a:b].max(), cm[a:b].max()) > 1023
+        deep.append(max(cp[a:b].max(), cm[a:b].max()) > 1023)
+    deep = np.array(deep)
+    assert deep.any()
+    for (lo, hi, _), d in zip(redo, deep):
+        assert d or np.any(deep & (np.abs(redo[:, 0] - lo) <= 400))
     check(out, ref, redo, (3, 5, 7), "deep")
     keep = np.ones(batch.total, dtype=bool)
     for lo, hi, _ in redo:
@@ -170,14 +187,15 @@ def test_no_table_uniform_model_and_histogram(emu, oracle, table):
 
 @pytest.mark.parametrize("fixed_len", [1, 2, 3, 7, 15, 381, 382, 383, 1500])
 def test_interval_lengths_around_the_edge_rules_and_piece_boundaries(emu, oracle, table, lut, fixed_len):
-    """Intervals shorter than a window (all 1.0), exactly at the one-piece limit (kWC - 3 = 381), one beyond, and long
-    ones cut into several pieces whose windows read z across the piece boundaries."""
+    """Intervals shorter than a window (all 1.0; several per item, each weighing the planner's minimum), around the old
+    one-piece limit, and long ones cut into several pieces whose windows read z across the piece boundaries."""
     batch, info = synth.make_batch(9 if fixed_len > 100 else 40, 55, seed=100 + fixed_len, table=table, fixed_len=fixed_len)
     out, redo, stats = run_emu(emu, oracle, batch, table, 50, (3, 5, 7), lut)
     ref = oracle_ref(oracle, batch, info, table, 50, (3, 5, 7))
     check(out, ref, redo, (3, 5, 7), "len %d" % fixed_len)
-    per_iv = stats[0] / batch.n_iv
-    assert per_iv == (1 if fixed_len <= 381 else (2 if fixed_len < 700 else 5))
+    assert stats[0] == planned_items(batch, 7) and stats[2] >= batch.n_iv
+    if fixed_len >= 381:   # full lane-groups: every item but the last holds 92 output groups
+        assert stats[0] == -(-int(np.sum((batch.out_off[1:] + 3) // 4 - batch.out_off[:-1] // 4)) // 92)
 
 
 def test_one_long_interval_and_misaligned_outputs(emu, oracle, table, lut):
@@ -187,7 +205,7 @@ def test_one_long_interval_and_misaligned_outputs(emu, oracle, table, lut):
     out, redo, stats = run_emu(emu, oracle, batch, table, 50, (3, 5, 7), lut, misalign=1)
     ref = oracle_ref(oracle, batch, info, table, 50, (3, 5, 7))
     check(out, ref, redo, (3, 5, 7), "60 kb")
-    assert stats[0] > 200   # ~170 pieces per interval at kWC = 384
+    assert stats[0] > 200   # ~163 items per interval at kWC = 384
 
 
 @pytest.mark.parametrize("scales", [(5,), (0, 2, 8), (3, 3, 7), (7, 3, 5), (1, 4)])
@@ -209,3 +227,20 @@ def test_more_than_three_distinct_half_widths_are_not_served(emu, oracle, table,
     le = _le_table(table)
     dm = np.concatenate([synth.MU_PARAMS, synth.R_PARAMS]).astype(np.float64)
     assert emu.emu_score(C.byref(args), le.ctypes.data, 1e-6, 0, dm.ctypes.data, None, 0, 0, None, 0, None) == -1
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_packs_of_mixed_interval_lengths(emu, oracle, table, lut, seed, monkeypatch):
+    """Tiny, short and long intervals mixed at random (1 .. 900 bp, a third below the planner's minimum weight): packs of
+    one to four sub-items, pieces cut anywhere, sub-items whose windows all fall under the edge rule."""
+    def lens(n_iv, rng, fixed=None):
+        kind = rng.integers(0, 3, n_iv)
+        return np.where(kind == 0, rng.integers(1, 40, n_iv), np.where(kind == 1, rng.integers(40, 200, n_iv),
+                                                                        rng.integers(200, 900, n_iv))).astype(np.int64)
+    monkeypatch.setattr(synth, "interval_lengths", lens)
+    batch, info = synth.make_batch(300, 55, seed=40 + seed, table=table, aligned=bool(seed & 1))
+    out, redo, stats = run_emu(emu, oracle, batch, table, 50, (3, 5, 7), lut)
+    assert len(redo) == 0
+    ref = oracle_ref(oracle, batch, info, table, 50, (3, 5, 7))
+    check(out, ref, redo, (3, 5, 7), "mixed lengths")
+    assert stats[0] == planned_items(batch, 7) and stats[2] >= batch.n_iv
