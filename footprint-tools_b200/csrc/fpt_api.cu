@@ -94,6 +94,8 @@ struct fpt_ctx {
     int force_general = 0;  // FPT_B200_GENERAL=1 / FPT_B200_PATH=general: route everything through the general kernel
     int allow_fused = 1;    // FPT_B200_PATH=fast: skip the fused kernel (two-kernel throughput path instead)
     int allow_warp = 1;     // FPT_B200_PATH=fused / fast: skip the warp-autonomous kernel (the CTA-tiled kernels instead)
+    int fdr_one_cta_max = kFdrOneCtaMax;  // FPT_B200_FDR_ONE_CTA_MAX lowers it (tests: the global-memory path on short intervals)
+    int dbg_skip = 0;       // FPT_B200_DEBUG_SKIP (measurement only, results are WRONG): 1 = no hand-back launch, 2 = reuse the plan
     bool warp_prepared = false;
     DevBuf items;           // planner scratch of the warp-autonomous kernel (warp_plan_layout): head ints, stream offsets, records, redo ranges
     int fused_inwin = 0;    // FPT_B200_FUSED_WIN=1: Stouffer windows inside the fused kernel instead of the streaming kernel
@@ -165,6 +167,8 @@ int check_status(fpt_ctx *ctx, const char *what) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (st != 0) {
         CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+        if (st == 2)
+            return fail(FPT_ERR_RANGE, "%s: a cut count exceeds fpt_score_args.max_cut (scores of the affected intervals were not written)", what);
         return fail(FPT_ERR_RANGE, "%s: a cut count exceeds the exact-integer range of this window geometry", what);
     }
     return FPT_OK;
@@ -228,10 +232,15 @@ int fpt_ctx_create(int device, fpt_ctx **out) {
     if (path && !strcmp(path, "general")) c->force_general = 1;
     if (path && !strcmp(path, "fast")) c->allow_fused = 0;
     if (path && (!strcmp(path, "fast") || !strcmp(path, "fused"))) c->allow_warp = 0;
+    if (const char *dbg = getenv("FPT_B200_DEBUG_SKIP")) c->dbg_skip = atoi(dbg);
+    if (const char *lim = getenv("FPT_B200_FDR_ONE_CTA_MAX")) {
+        const int v = atoi(lim);
+        if (v >= 64 && v <= kFdrOneCtaMax) c->fdr_one_cta_max = v;
+    }
     const char *pl = getenv("FPT_B200_PIPELINE");
     c->pipeline = (pl && pl[0] == '0') ? 0 : 1;
     const char *nr = getenv("FPT_B200_NARROW");
-    c->narrow = (nr && nr[0] == '0') ? 0 : 1;
+    c->narrow = (nr && nr[0] == '0') ? 0 : ((nr && nr[0] == '2') ? 2 : 1);  // 2: narrow whatever the host thread count
     const char *inw = getenv("FPT_B200_FUSED_WIN");
     c->fused_inwin = (inw && inw[0] == '1') ? 1 : 0;
     *out = c;
@@ -475,10 +484,17 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
         p.work_counter = pb.head + 1;
         p.redo_count = pb.head + 2;
         p.redo_ranges = pb.redo_ranges;
-        CU(cudaMemsetAsync(pb.head, 0, 64, ctx->stream));
-        {
+        // a caller-supplied bound on the cut counts within the packed range: no item can be handed back, and the launch of
+        // the general kernel over the (empty) hand-back list — 30 us of launch cost per call on a B200 — is skipped
+        p.no_redo = a->max_cut > 0 && a->max_cut <= (int64_t)kWPackedCutLimit;
+        static bool planned_once = false;
+        if ((ctx->dbg_skip & 2) && planned_once) {
+            CU(cudaMemsetAsync(pb.head + 1, 0, 8, ctx->stream));   // measurement only: the previous call's plan, counters reset
+        } else {
+            CU(cudaMemsetAsync(pb.head, 0, 64, ctx->stream));
             ProfScope ps(ctx, FPT_KERNEL_PLAN);
             CU(launch_plan_items(ctx->stream, p.out_off, p.iv_start, p.n_iv, p.wh_max, pb, ctx->sm_count));
+            planned_once = true;
         }
         ctx->launches++;
         if (!ctx->warp_prepared) {
@@ -500,11 +516,11 @@ static int score_device(fpt_ctx *ctx, const fpt_score_args *a) {
         const size_t gsmem = score_smem_bytes(hw, q.uniform != 0);
         CU(score_kernel_prepare(gsmem));
         long long rgrid = ctx->sm_count;
-        {
+        if (!p.no_redo && !(ctx->dbg_skip & 1)) {
             ProfScope ps(ctx, FPT_KERNEL_REDO);
             CU(launch_score(ctx->stream, q, (int)rgrid));
+            ctx->launches++;
         }
-        ctx->launches++;
         return FPT_OK;
     }
     if (fused) {
@@ -753,7 +769,19 @@ static int score_host_pipelined(fpt_ctx *ctx, const fpt_score_args *a, int n_chu
     // Expected / observed counts are integers: they are narrowed to uint32 on the device, cross PCIe as 4
     // bytes each, land in pinned staging and are widened into the caller's float64 arrays by host
     // threads while later chunks are still in flight (format conversion only, like fpt_pack_sequence).
-    const bool narrow = ctx->narrow && (a->exp_out || a->obs_out);
+    // host threads that widen the uint32 counts: half the cores, shared among the ranks of this node (torchrun exports
+    // LOCAL_WORLD_SIZE), at most 8 — eight ranks must not put 64 spinning threads on a small host. Narrowing pays only
+    // while the host can widen faster than the link delivers: one thread converts ~3 GB/s of float64, a PCIe 5 x16 link
+    // delivers ~55 GB/s, and measured on a 16-core host (SCALE_r01: e2e 1.07e9 bases/s on one GPU, 1.53e9 on eight) a
+    // rank left with one or two widening threads spends 0.4 s per 80 M bases in them — the whole 8-GPU e2e figure.
+    // Below 8 threads per rank the counts therefore cross as float64 (48 B instead of 40 B per base, no host work).
+    unsigned ranks_here = 1;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) {
+        const int v = atoi(lw);
+        if (v > 1) ranks_here = (unsigned)v;
+    }
+    const unsigned widen_threads = std::thread::hardware_concurrency() / (2 * ranks_here);
+    const bool narrow = ctx->narrow && (a->exp_out || a->obs_out) && (widen_threads >= 8 || ctx->narrow > 1);
     const size_t nrows = 2 * mult;  // staging rows: exp rows then obs rows, each `tot` long
     if (narrow) {
         const size_t need = nrows * tot;
@@ -768,15 +796,7 @@ static int score_host_pipelined(fpt_ctx *ctx, const fpt_score_args *a, int n_chu
     std::atomic<int> enqueued{0};
     std::atomic<bool> aborted{false};
     std::vector<std::thread> workers;
-    // host threads that widen the uint32 counts: half the cores, shared among the ranks of this node (torchrun exports
-    // LOCAL_WORLD_SIZE), at most 8, at least 1 — eight ranks must not put 64 spinning threads on a small host
-    unsigned ranks_here = 1;
-    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) {
-        const int v = atoi(lw);
-        if (v > 1) ranks_here = (unsigned)v;
-    }
-    const int n_workers =
-        narrow ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / (2 * ranks_here))) : 0;
+    const int n_workers = narrow ? (int)std::min<unsigned>(8u, std::max(1u, widen_threads)) : 0;
     if (narrow) {
         double *hosts[2] = {a->exp_out, a->obs_out};
         uint32_t *pin = ctx->pin_counts;
@@ -1049,16 +1069,33 @@ int fpt_null_sample(fpt_ctx *ctx, const double *exp, int64_t n, int times, uint6
     return FPT_OK;
 }
 
+// h_off: host copy of the interval offsets (needed only when an interval is longer than the one-CTA kernel takes)
 static int efdr_common(fpt_ctx *ctx, const char *what, const double *d_exp, const double *d_winp, const long long *d_off,
-                       int64_t n_iv, int64_t max_len, int hw, int times, uint64_t seed, const double *d_nulls, int64_t m,
-                       double *d_out) {
+                       const int64_t *h_off, int64_t n_iv, int64_t max_len, int hw, int times, uint64_t seed, const double *d_nulls,
+                       int64_t m, double *d_out) {
+    (void)what;
+    const int one_max = ctx->fdr_one_cta_max;
+    const bool any_long = max_len > one_max;
     {
         ProfScope ps(ctx, FPT_KERNEL_FDR);
-        CU(launch_efdr(ctx->stream, ctx->d_dm, ctx->d_lut, ctx->d_guide, ctx->lut_e, ctx->lut_o, d_exp, d_winp, d_off, n_iv, (int)max_len,
-                       hw, times, seed, d_nulls, m, d_out, ctx->d_status, ctx->sm_count));
+        if (!d_nulls || !any_long) {
+            CU(launch_efdr(ctx->stream, ctx->d_dm, ctx->d_lut, ctx->d_guide, ctx->lut_e, ctx->lut_o, d_exp, d_winp, d_off, n_iv,
+                           (int)(any_long ? one_max : max_len), hw, times, seed, d_nulls, m, d_out, ctx->d_status, ctx->sm_count,
+                           any_long));
+            ctx->launches++;
+        }
+        if (any_long) {
+            // intervals beyond the shared-memory sort: one at a time through the global-memory path (fpt_fdr.cu)
+            for (int64_t k = 0; k < n_iv; ++k) {
+                const long long o0 = h_off ? h_off[k] : 0, len = h_off ? h_off[k + 1] - h_off[k] : max_len;
+                if (len <= one_max) continue;
+                CU(ctx->scratch.need(efdr_long_scratch_bytes(len)));
+                CU(launch_efdr_long(ctx->stream, ctx->d_dm, ctx->d_lut, ctx->d_guide, ctx->lut_e, ctx->lut_o, d_exp, d_winp, o0, len, hw,
+                                    times, seed, d_nulls, m, d_out, ctx->scratch.p, ctx->sm_count));
+                ctx->launches += 5;
+            }
+        }
     }
-    ctx->launches++;
-    (void)what;
     return FPT_OK;
 }
 
@@ -1070,14 +1107,22 @@ int fpt_detect_fdr(fpt_ctx *ctx, const double *exp, const double *winp, const in
         return fail(FPT_ERR_ARG, "fpt_detect_fdr: bad argument (0 <= hw <= %d, times >= 1)", kFastMaxScaleHalfWin);
     if (n_iv == 0 || total == 0) return FPT_OK;
     if (!exp || !winp || !out_off || !efdr_out) return fail(FPT_ERR_ARG, "fpt_detect_fdr: NULL array");
-    if (max_len > 4096) return fail(FPT_ERR_ARG, "fpt_detect_fdr: intervals longer than 4096 positions are not supported");
+    if (max_len > 0x3FFFFFFF) return fail(FPT_ERR_ARG, "fpt_detect_fdr: intervals longer than 2^30 - 1 positions are not supported");
     if (max_len == 0) return FPT_OK;
     DeviceGuard g(ctx->device);
     cudaStream_t st = ctx->stream;
     if (mem == FPT_MEM_DEVICE) {
-        int rc = efdr_common(ctx, "fpt_detect_fdr", exp, winp, reinterpret_cast<const long long *>(out_off), n_iv, max_len, hw,
-                             times, seed, nullptr, 0, efdr_out);
-        return rc;
+        std::vector<int64_t> h_off;
+        if (max_len > ctx->fdr_one_cta_max) {  // the long intervals are dispatched from the host: it needs the offsets
+            h_off.resize((size_t)n_iv + 1);
+            CU(cudaMemcpyAsync(h_off.data(), out_off, h_off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (int64_t k = 0; k < n_iv; ++k)
+                if (h_off[k + 1] - h_off[k] > max_len)
+                    return fail(FPT_ERR_ARG, "fpt_detect_fdr: interval %lld is longer than max_len", (long long)k);
+        }
+        return efdr_common(ctx, "fpt_detect_fdr", exp, winp, reinterpret_cast<const long long *>(out_off),
+                           h_off.empty() ? nullptr : h_off.data(), n_iv, max_len, hw, times, seed, nullptr, 0, efdr_out);
     }
     for (int64_t k = 0; k < n_iv; ++k)
         if (out_off[k + 1] - out_off[k] > max_len)
@@ -1088,7 +1133,8 @@ int fpt_detect_fdr(fpt_ctx *ctx, const double *exp, const double *winp, const in
     CU(cudaMemcpyAsync(ctx->h_in[1].p, winp, bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->h_in[2].p, out_off, ob, cudaMemcpyHostToDevice, st));
     int rc = efdr_common(ctx, "fpt_detect_fdr", ctx->h_in[0].as<double>(), ctx->h_in[1].as<double>(),
-                         ctx->h_in[2].as<long long>(), n_iv, max_len, hw, times, seed, nullptr, 0, ctx->h_out[0].as<double>());
+                         ctx->h_in[2].as<long long>(), out_off, n_iv, max_len, hw, times, seed, nullptr, 0,
+                         ctx->h_out[0].as<double>());
     if (rc != FPT_OK) return rc;
     CU(cudaMemcpyAsync(efdr_out, ctx->h_out[0].p, bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1100,17 +1146,17 @@ int fpt_empirical_fdr(fpt_ctx *ctx, const double *pvals_null, int64_t m, const d
     if (!ctx) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: ctx is NULL");
     if (m < 0 || n < 0) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: bad argument");
     if (n == 0) return FPT_OK;
-    if (n > 4096) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: more than 4096 observed values are not supported");
+    if (n > 0x3FFFFFFF) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: more than 2^30 - 1 observed values are not supported");
     if (m == 0) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: empty null distribution");
     if (!pvals_null || !pvals || !out) return fail(FPT_ERR_ARG, "fpt_empirical_fdr: NULL array");
     DeviceGuard g(ctx->device);
     cudaStream_t st = ctx->stream;
     if (mem == FPT_MEM_DEVICE)
-        return efdr_common(ctx, "fpt_empirical_fdr", nullptr, pvals, nullptr, 1, n, 0, 0, 0, pvals_null, m, out);
+        return efdr_common(ctx, "fpt_empirical_fdr", nullptr, pvals, nullptr, nullptr, 1, n, 0, 0, 0, pvals_null, m, out);
     CU(ctx->h_in[0].need((size_t)m * 8)); CU(ctx->h_in[1].need((size_t)n * 8)); CU(ctx->h_out[0].need((size_t)n * 8));
     CU(cudaMemcpyAsync(ctx->h_in[0].p, pvals_null, (size_t)m * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->h_in[1].p, pvals, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    int rc = efdr_common(ctx, "fpt_empirical_fdr", nullptr, ctx->h_in[1].as<double>(), nullptr, 1, n, 0, 0, 0,
+    int rc = efdr_common(ctx, "fpt_empirical_fdr", nullptr, ctx->h_in[1].as<double>(), nullptr, nullptr, 1, n, 0, 0, 0,
                          ctx->h_in[0].as<double>(), m, ctx->h_out[0].as<double>());
     if (rc != FPT_OK) return rc;
     CU(cudaMemcpyAsync(out, ctx->h_out[0].p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));

@@ -213,6 +213,7 @@ struct FdrParams {
     const double *nulls;
     long long m;
     int *status;  // set to 1 if an interval is longer than nmax
+    int skip_long;  // intervals longer than nmax are left to the global-memory path (launch_efdr_long) instead
 };
 
 // Empirical FDR of one interval per CTA (grid-stride over intervals).
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
         const long long len = (P.off ? P.off[iv + 1] : (long long)P.nmax) - o0;
         if (len <= 0) continue;
         if (len > P.nmax) {
-            if (tid == 0) *P.status = 1;
+            if (tid == 0 && !P.skip_long) *P.status = 1;
             continue;
         }
         const int n = (int)len;
@@ -361,6 +362,176 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
     }
 }
 
+
+// ---- intervals of any length (cli/detect.py:132-135 and fdr.emperical_fdr have no limit) ------------------------------
+// The same algorithm with the interval's arrays in global memory and the work spread over the whole grid: the observed
+// values are sorted by a bitonic network (steps with a partner distance below 2048 run in shared memory, 2048 elements
+// per CTA; the others one launch per step), every (1024-position chunk, null column) pair is one CTA's work item —
+// draws for the chunk and its window halo (counter-based, so a halo draw is the same double its own chunk computes),
+// windows, location among the sorted keys by binary search (L2-resident), one global atomic per null value — then a
+// scan of the buckets and the same closing formula. Results are identical to the one-CTA kernel's for an interval both
+// can take (tests/test_gpu_fdr.py).
+constexpr int kLongSortBlock = 2048;   // elements sorted per CTA in shared memory
+constexpr int kLongChunk = 1024;       // positions per work item of the counting kernel
+
+struct FdrLong {
+    unsigned long long *keys;  // np2
+    int *idx;                  // np2
+    unsigned *bucket;          // n + 1 (+ padding), bucket[n + 1] = count of NaN nulls
+    int n, np2;
+};
+
+__global__ void efdr_long_init_kernel(const double *__restrict__ winp, long long o0, FdrLong L) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.np2; i += gridDim.x * blockDim.x) {
+        L.keys[i] = i < L.n ? order_key(winp[o0 + i]) : kKeyPad;
+        L.idx[i] = i;
+        if (i <= L.n + 1) L.bucket[i] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { L.bucket[L.n] = 0; L.bucket[L.n + 1] = 0; }
+}
+
+// all steps (k, j) with k in [k_begin, k_end] and j <= 1024 for the CTA's 2048 elements (j starts at min(k / 2, 1024))
+__global__ void __launch_bounds__(1024) bitonic_local_kernel(FdrLong L, int k_begin, int k_end) {
+    __shared__ unsigned long long sk[kLongSortBlock];
+    __shared__ int si[kLongSortBlock];
+    const int base = blockIdx.x * kLongSortBlock, tid = threadIdx.x;
+    for (int t = tid; t < kLongSortBlock; t += 1024) { sk[t] = L.keys[base + t]; si[t] = L.idx[base + t]; }
+    __syncthreads();
+    for (int k = k_begin; k <= k_end; k <<= 1) {
+        for (int j = (k >> 1) < 1024 ? (k >> 1) : 1024; j > 0; j >>= 1) {
+            const int a = ((tid & ~(j - 1)) << 1) | (tid & (j - 1)), b = a | j;
+            const bool up = ((base + a) & k) == 0;
+            const unsigned long long ka = sk[a], kb = sk[b];
+            if ((ka > kb) == up) {
+                sk[a] = kb; sk[b] = ka;
+                const int ia = si[a]; si[a] = si[b]; si[b] = ia;
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = tid; t < kLongSortBlock; t += 1024) { L.keys[base + t] = sk[t]; L.idx[base + t] = si[t]; }
+}
+
+// one step (k, j), j >= 2048
+__global__ void bitonic_global_kernel(FdrLong L, int k, int j) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < (L.np2 >> 1); t += gridDim.x * blockDim.x) {
+        const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1)), b = a | j;
+        const bool up = (a & k) == 0;
+        const unsigned long long ka = L.keys[a], kb = L.keys[b];
+        if ((ka > kb) == up) {
+            L.keys[a] = kb; L.keys[b] = ka;
+            const int ia = L.idx[a]; L.idx[a] = L.idx[b]; L.idx[b] = ia;
+        }
+    }
+}
+
+__device__ __forceinline__ void long_count(const FdrLong &L, double v) {
+    if (v != v) { atomicAdd(&L.bucket[L.n + 1], 1u); return; }
+    const unsigned long long kv = order_key(v);
+    int a = 0, b = L.n;  // first k in [0, n] with keys[k] >= kv
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (__ldg(&L.keys[m]) >= kv) b = m; else a = m + 1;
+    }
+    atomicAdd(&L.bucket[a], 1u);
+}
+
+__global__ void __launch_bounds__(kFdrThreads) efdr_long_count_kernel(const FdrParams P, long long o0, FdrLong L) {
+    __shared__ double z[kLongChunk + 2 * kFastMaxScaleHalfWin];
+    __shared__ double s4[kNdTab];
+    const int tid = threadIdx.x, n = L.n;
+    ndtr4_table_init(s4, tid);
+    const int n_chunks = (n + kLongChunk - 1) / kLongChunk;
+    const long long items = (long long)n_chunks * P.times;
+    for (long long w = blockIdx.x; w < items; w += gridDim.x) {
+        const int c = (int)(w % n_chunks), j = (int)(w / n_chunks);
+        const int p0 = c * kLongChunk, p1 = min(p0 + kLongChunk, n);
+        const int lo = max(p0 - P.hw, 0), hi = min(p1 + P.hw, n);
+        __syncthreads();  // z of the previous item has been read
+        for (int q = tid; q < hi - lo; q += 2 * kFdrThreads) {
+            const int q1 = q + kFdrThreads;
+            const bool has1 = q1 < hi - lo;
+            const int i0 = lo + q, i1 = has1 ? lo + q1 : i0;
+            NullDraw d0, d1;
+            d1.z = 0.0;
+            null_draw2(P.dm, P.lut, P.guide, P.lut_e, P.lut_o, P.ex[o0 + i0], null_uniform(P.seed, o0 + i0, j), P.ex[o0 + i1],
+                       null_uniform(P.seed, o0 + i1, j), has1, d0, d1);
+            z[q] = d0.z;
+            if (has1) z[q1] = d1.z;
+        }
+        __syncthreads();
+        for (int i = p0 + tid; i < p1; i += kFdrThreads) {
+            double v = 1.0;  // windowing.pyx:51-54
+            if (i >= P.hw && i < n - P.hw) {
+                const double *zz = z + (i - lo);
+                double acc = zz[0];
+                for (int h = 1; h <= P.hw; ++h) acc += zz[-h] + zz[h];
+                const double a = acc * (-P.inv_sqrt_k);
+                v = fabs(a) < 26.0 ? ndtr_fast1(a, s4) : (fabs(a) <= 1.79769313486231570815e308 ? ndtr_slow(a) : a - a);
+            }
+            long_count(L, v);
+        }
+    }
+}
+
+__global__ void efdr_long_given_kernel(const double *__restrict__ nulls, long long m, FdrLong L) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x)
+        long_count(L, nulls[q]);
+}
+
+// inclusive scan of bucket[0 .. n] in place (one CTA)
+__global__ void __launch_bounds__(1024) efdr_long_scan_kernel(FdrLong L) {
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 <= L.n; b0 += 1024) {
+        const int i = b0 + tid;
+        const unsigned v = i <= L.n ? L.bucket[i] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned x = wsum[lane];
+            unsigned xi = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, xi, d);
+                if (lane >= d) xi += t;
+            }
+            wsum[lane] = xi - x;
+        }
+        __syncthreads();
+        const unsigned res = carry_s + wsum[warp] + incl;
+        if (i <= L.n) L.bucket[i] = res;
+        __syncthreads();
+        if (tid == 1023) carry_s = res;
+        __syncthreads();
+    }
+}
+
+// utils.bisect semantics + the division and cap of emperical_fdr (as at the end of efdr_kernel)
+__global__ void efdr_long_final_kernel(FdrLong L, long long M, long long o0, double *__restrict__ out) {
+    const unsigned nanc = L.bucket[L.n + 1];
+    const long long finite = M - nanc;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L.n; k += gridDim.x * blockDim.x) {
+        long long c;
+        if (L.keys[k] == kKeyNaN) c = M;
+        else {
+            c = L.bucket[k];
+            if (c == finite) c += nanc;
+        }
+        const double rate = (double)c / (double)M;
+        out[o0 + L.idx[k]] = rate > 1.0 ? 1.0 : rate;
+    }
+}
+
 }  // namespace
 
 size_t efdr_smem_bytes(int np, int nmax, int jb) {
@@ -383,9 +554,11 @@ cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 
 cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e, int lut_o,
                         const double *ex,
                         const double *winp, const long long *off, long long n_iv, int nmax, int hw, int times,
-                        unsigned long long seed, const double *nulls, long long m, double *out, int *status, int sm_count) {
+                        unsigned long long seed, const double *nulls, long long m, double *out, int *status, int sm_count,
+                        bool skip_long) {
     if (n_iv <= 0 || nmax <= 0) return cudaSuccess;
     FdrParams P;
+    P.skip_long = skip_long ? 1 : 0;
     P.ex = ex; P.winp = winp; P.off = off; P.n_iv = n_iv; P.hw = hw; P.times = times; P.seed = seed;
     P.inv_sqrt_k = 1.0 / sqrt((double)(2 * hw + 1));
     P.out = out; P.dm = dm; P.lut = lut; P.guide = guide; P.lut_e = lut_e; P.lut_o = lut_o;
@@ -405,6 +578,55 @@ cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, c
     long long grid = (long long)sm_count * per_sm;
     if (grid > n_iv) grid = n_iv;
     efdr_kernel<<<(unsigned)grid, kFdrThreads, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+size_t efdr_long_scratch_bytes(long long n) {
+    long long np2 = kLongSortBlock;
+    while (np2 < n) np2 <<= 1;
+    return (size_t)np2 * 12 + ((size_t)n + 2 + 15) / 16 * 64 + 256;
+}
+
+// One interval of any length: winp[o0 .. o0 + n) (and exp, for generated nulls) -> out[o0 .. o0 + n).
+cudaError_t launch_efdr_long(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e, int lut_o,
+                             const double *ex, const double *winp, long long o0, long long n, int hw, int times,
+                             unsigned long long seed, const double *nulls, long long m, double *out, void *scratch, int sm_count) {
+    if (n <= 0) return cudaSuccess;
+    if (n > 0x3FFFFFFFLL) return cudaErrorInvalidValue;
+    FdrLong L;
+    L.n = (int)n;
+    L.np2 = kLongSortBlock;
+    while (L.np2 < n) L.np2 <<= 1;
+    char *p = static_cast<char *>(scratch);
+    L.keys = reinterpret_cast<unsigned long long *>(p);
+    L.idx = reinterpret_cast<int *>(p + (size_t)L.np2 * 8);
+    L.bucket = reinterpret_cast<unsigned *>(p + (size_t)L.np2 * 12);
+    const int wide = sm_count * 8;
+    efdr_long_init_kernel<<<wide, 256, 0, st>>>(winp, o0, L);
+    const int n_blocks = L.np2 / kLongSortBlock;
+    bitonic_local_kernel<<<n_blocks, 1024, 0, st>>>(L, 2, kLongSortBlock);
+    for (int k = 2 * kLongSortBlock; k <= L.np2; k <<= 1) {
+        for (int j = k >> 1; j >= kLongSortBlock; j >>= 1) bitonic_global_kernel<<<wide, 256, 0, st>>>(L, k, j);
+        bitonic_local_kernel<<<n_blocks, 1024, 0, st>>>(L, k, k);
+    }
+    long long M;
+    if (nulls) {
+        M = m;
+        efdr_long_given_kernel<<<wide, 256, 0, st>>>(nulls, m, L);
+    } else {
+        M = n * (long long)times;
+        FdrParams P;
+        P.ex = ex; P.winp = winp; P.off = nullptr; P.n_iv = 1; P.hw = hw; P.times = times; P.seed = seed;
+        P.inv_sqrt_k = 1.0 / sqrt((double)(2 * hw + 1));
+        P.out = out; P.dm = dm; P.lut = lut; P.guide = guide; P.lut_e = lut_e; P.lut_o = lut_o;
+        P.np = 0; P.nmax = 0; P.jb = 1; P.nulls = nullptr; P.m = 0; P.status = nullptr; P.skip_long = 0;
+        const long long items = ((n + kLongChunk - 1) / kLongChunk) * (long long)times;
+        long long grid = (long long)sm_count * 8;
+        if (grid > items) grid = items;
+        efdr_long_count_kernel<<<(unsigned)grid, kFdrThreads, 0, st>>>(P, o0, L);
+    }
+    efdr_long_scan_kernel<<<1, 1024, 0, st>>>(L);
+    efdr_long_final_kernel<<<wide, 256, 0, st>>>(L, M, o0, out);
     return cudaGetLastError();
 }
 

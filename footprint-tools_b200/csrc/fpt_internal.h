@@ -41,6 +41,9 @@ struct alignas(16) WItem {
     int iv;
 };
 constexpr int kWMaxSub = 4;
+// Largest cut count the kernel's packed 16-bit format carries (the test is an OR mask, hence 2^k - 1): a 10-wide window
+// sum is then at most 20 470 and the sum of TWO of them still fits a 16-bit half — wider sums are taken in 32 bits.
+constexpr unsigned kWPackedCutLimit = 0x7FFu;
 struct alignas(16) WPack {
     int nsub;
     int cgs[kWMaxSub - 1];  // first lane-group of sub-items 1 .. 3 in the item
@@ -102,6 +105,8 @@ struct ScoreParams {
     const int *n_items;
     int *work_counter;         // next item to hand out
     long long *redo_ranges;    // 3 per sub-item of an item whose cut counts exceed the packed range; count in redo_count
+    int no_redo;               // the caller bounds the cut counts within the packed range (fpt_score_args.max_cut): no hand-back
+                               // launch follows; an item that would need one sets *status = 2
 };
 
 // window kernel of the fast path (fpt_fast.cu)
@@ -160,7 +165,13 @@ cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 
 cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e, int lut_o,
                         const double *ex,
                         const double *winp, const long long *off, long long n_iv, int nmax, int hw, int times,
-                        unsigned long long seed, const double *nulls, long long m, double *out, int *status, int sm_count);
+                        unsigned long long seed, const double *nulls, long long m, double *out, int *status, int sm_count,
+                        bool skip_long = false);
+constexpr int kFdrOneCtaMax = 4096;  // longest interval the one-CTA kernel takes (shared-memory sort)
+size_t efdr_long_scratch_bytes(long long n);
+cudaError_t launch_efdr_long(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e, int lut_o,
+                             const double *ex, const double *winp, long long o0, long long n, int hw, int times,
+                             unsigned long long seed, const double *nulls, long long m, double *out, void *scratch, int sm_count);
 
 cudaError_t launch_guide_build(cudaStream_t st, const double2 *lut, int lut_e, int lut_o, unsigned short *guide);
 cudaError_t launch_lut_build(cudaStream_t st, const double *dm, double2 *lut, int lut_e, int lut_o);

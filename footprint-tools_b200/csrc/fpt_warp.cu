@@ -149,6 +149,8 @@ struct DeviceEnv {
     __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
     __device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) { fpt::st256(p, a, b, c, d); }
     __device__ __forceinline__ void atomic_inc_shared(unsigned *p) { atomicAdd(p, 1u); }
+    __device__ __forceinline__ unsigned atomic_add_shared(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+    __device__ __forceinline__ void atomic_or_shared(unsigned *p, unsigned v) { atomicOr(p, v); }
     __device__ __forceinline__ void atomic_inc_u64(unsigned long long *p) { atomicAdd(p, 1ULL); }
     // dispersion.pyx:291-316 -> nbinom.pyx:121-138 -> incbet.c, and z = ndtri(1 - p) for the windows
     __device__ __noinline__ void direct_pz(const double *dmp, double ex, int kobs, double *pv, double *z) {
@@ -178,6 +180,9 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
 
     const int n_items = *P.n_items;
     WarpSmem &S = WS[warp];
+    if (lane == 0) { S.pg[0].ndirect = 0; S.pg[0].nheads = 0; }
+    if (lane < kWC / 32) S.dmask[lane] = 0;
+    __syncwarp();
     DeviceWarp W{lane};
     DeviceEnv env{s4};
     // the next work-item index: lane 0 asks the global counter; the answer is broadcast only where it is needed, a whole
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(kWThreads, 1) score_warp_kernel(const ScorePar
             env.cp16(reinterpret_cast<uint32_t *>(&S.next) + 4 * lane, reinterpret_cast<const uint32_t *>(P.items + nxt) + 4 * lane);
         env.cp_commit();
         const bool ok = process_item<SMOOTH, WM>(P, have_cur, par, have_next ? &S.next : nullptr, S, tab, dmp, hsub, W, env);
+        if (!ok && P.no_redo && lane == 0) *P.status = 2;  // the caller's bound on the cut counts does not hold
         if (!ok && lane < S.pg[par].nsub) {
             const SubStage &t = S.pg[par].s[lane];
             const int slot = atomicAdd(P.redo_count, 1);

@@ -57,7 +57,6 @@ FPT_HD int sub_mask_words(int ncg) { return ((4 * ncg + 27) >> 5) + 2; }
 constexpr int kWSeqWords = (((kWC + 27 * kWMaxSub) >> 4) + 3 * kWMaxSub + 3) & ~3;
 constexpr int kWMaskWords = 32;               // one per lane (stage_fix_mask)
 static_assert(((kWC + 27 * kWMaxSub) >> 5) + 2 * kWMaxSub <= kWMaskWords, "one mask word per lane");
-constexpr unsigned kWPackedCutLimit = 0x3FFu;  // largest cut count the packed format carries
 constexpr int kWHistSubE = 16, kWHistSubO = 64;  // learn_dm bins counted in shared memory first
 
 // What steps D and E need of one sub-item, in the ITEM's c-space: lane-group cg holds item positions 4 cg + e.
@@ -83,6 +82,8 @@ struct alignas(16) SubStage {
 // Geometry of a pack, built by prepare_pack one item ahead (two sets per warp, used alternately).
 struct alignas(16) PackGeo {
     int nsub, ncg, nxg, nmw;   // sub-items, c-groups, staged groups, staged mask words of the whole item
+    unsigned ndirect, nheads;  // step D2's counters (those of set 0 are the warp's; zero between items)
+    int pad_[2];
     int cge[kWMaxSub];         // c-group where sub-item i ends (INT_MAX beyond the last)
     int xge[kWMaxSub];         // staged group where sub-item i ends
     SubGeo g[kWMaxSub];
@@ -100,6 +101,7 @@ struct alignas(16) WarpSmem {
     };
     uint32_t seq[kWSeqWords];            // 2-bit codes, sub-item i from word s[i].sw: word 0 = bases [B0, B0 + 16)
     uint32_t msk[kWMaskWords];           // N bits, sub-item i from word s[i].mw: word 0 = bases [B0, B0 + 32)
+    unsigned dmask[kWC / 32 + 4];        // step D2: bit c set = item position c awaits its direct evaluation (zero between items)
     PackGeo pg[2];                       // geometry of the current item and of the next one
     WPack next;                          // record of the warp's next item (copied in asynchronously)
 };
@@ -400,9 +402,9 @@ FPT_HD void step_sums(WarpSmem &S, int xg) {
     w.w = vadd2(vadd2(core, p34), c[15]);
     *reinterpret_cast<uint4 *>(S.wcw + x0) = w;
     if (SMOOTH) {
-        const unsigned sg = vadd2(vadd2(w.x, w.y), vadd2(w.z, w.w));  // <= 4 * 10230 per half
+        const unsigned s1 = vadd2(w.x, w.y), s2 = vadd2(w.z, w.w);  // <= 2 * 20470 per half
         S.GA[xg] = make_uint4(pt::vminu2(pt::vminu2(w.x, w.y), pt::vminu2(w.z, w.w)),
-                              pt::vmaxu2(pt::vmaxu2(w.x, w.y), pt::vmaxu2(w.z, w.w)), lo16(sg), hi16(sg));
+                              pt::vmaxu2(pt::vmaxu2(w.x, w.y), pt::vmaxu2(w.z, w.w)), lo16(s1) + lo16(s2), hi16(s1) + hi16(s2));
     }
 }
 
@@ -506,6 +508,17 @@ FPT_HD void store_partial(double *dst, unsigned omask, double v0, double v1, dou
     if (omask & 8u) dst[3] = v3;
 }
 
+// (shared-memory arrays of step D2, below)
+constexpr int kWDirectCap = 512;
+static_assert(kWC <= kWDirectCap, "one key per item position");
+FPT_HD unsigned long long *direct_keys(WarpSmem &S) { return reinterpret_cast<unsigned long long *>(S.cw_); }
+FPT_HD unsigned *direct_heads(WarpSmem &S) { return reinterpret_cast<unsigned *>(S.cw_) + 2 * kWDirectCap; }
+static_assert(sizeof(unsigned long long) * kWDirectCap + sizeof(unsigned) * kWDirectCap <=
+                  sizeof(uint32_t) * (2 * kWPre + kWX) + sizeof(uint32_t) * (kWX + 16), "direct keys + heads fit cw_ + wcw");
+FPT_HD unsigned long long direct_key(unsigned ex, unsigned kobs, unsigned cpos, unsigned is_out) {
+    return ((unsigned long long)ex << 32) | ((unsigned long long)(kobs & 0x7FFFu) << 17) | ((unsigned long long)is_out << 16) | cpos;
+}
+
 // ---- step D: the 4 positions c0 .. c0+3 of group cg -------------------------------------------------------------
 // Env supplies what differs between the device and the host emulation: the direct NB evaluation, the 256-bit
 // store, the atomics.
@@ -578,9 +591,10 @@ FPT_HD void step_score(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, cons
             mx[2] = vmaxu2(hab, Rq.x);
             mx[3] = vmaxu2(vmaxu2(Hb.y, ta), tr);
         }
-        const unsigned p0 = vadd2(vadd2(vadd2(Bq.x, Bq.y), Bq.z), vadd2(Lq.z, Lq.w));  // <= 5 * 10230
+        const unsigned p1 = vadd2(Bq.x, Bq.y), p2 = vadd2(Lq.z, Lq.w);  // <= 2 * 20470 per half
         unsigned Sl[4], Sh[4];
-        Sl[0] = Ha.z + lo16(p0);                 Sh[0] = Ha.w + hi16(p0);
+        Sl[0] = Ha.z + lo16(p1) + lo16(p2) + lo16(Bq.z);
+        Sh[0] = Ha.w + hi16(p1) + hi16(p2) + hi16(Bq.z);
         Sl[1] = Sl[0] + lo16(Bq.w) - lo16(Lq.z); Sh[1] = Sh[0] + hi16(Bq.w) - hi16(Lq.z);
         Sl[2] = Sl[1] + lo16(Rq.x) - lo16(Lq.w); Sh[2] = Sh[1] + hi16(Rq.x) - hi16(Lq.w);
         Sl[3] = Sl[2] + lo16(Rq.y) - lo16(Aq.x); Sh[3] = Sh[2] + hi16(Rq.y) - hi16(Aq.x);
@@ -717,20 +731,6 @@ FPT_HD void step_score(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, cons
                 else env.atomic_inc_u64(P.hist + (size_t)exi[e] * P.hist_d1 + obi[e]);
             }
     }
-    if (direct) {  // outside the table: evaluated in place — only this warp waits for it
-#pragma unroll 1
-        for (int e = 0; e < 4; ++e) {
-            if (!((direct >> e) & 1u)) continue;
-            const double ex = (double)(e == 0 ? exi[0] : e == 1 ? exi[1] : e == 2 ? exi[2] : exi[3]);
-            const int kobs = e == 0 ? obi[0] : e == 1 ? obi[1] : e == 2 ? obi[2] : obi[3];
-            double pv, z;
-            env.direct_pz(dmp, ex, kobs, &pv, &z);
-            if (e == 0) { pvv[0] = pv; zv[0] = z; }
-            else if (e == 1) { pvv[1] = pv; zv[1] = z; }
-            else if (e == 2) { pvv[2] = pv; zv[2] = z; }
-            else { pvv[3] = pv; zv[3] = z; }
-        }
-    }
     if (P.pval_out && omask) {
         if (omask == 0xFu && P.vec_ok) env.st256(P.pval_out + f0, pvv[0], pvv[1], pvv[2], pvv[3]);
         else store_partial(P.pval_out + f0, omask, pvv[0], pvv[1], pvv[2], pvv[3]);
@@ -739,6 +739,79 @@ FPT_HD void step_score(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) S.zsT[e * kWZS + 2 + cg] = ((vmask >> e) & 1u) ? zv[e] : 0.0;
     }
+    if (direct) {
+        // outside the table: left to step D2 (sorted, every distinct (exp, obs) pair evaluated once), which overwrites the
+        // p-value stored above. Until then the element's z slot holds its key and its bit in S.dmask is set — the arrays
+        // D2 sorts in are still being read by the other lanes of this step.
+#pragma unroll 1
+        for (int e = 0; e < 4; ++e) {
+            if (!((direct >> e) & 1u)) continue;
+            const unsigned ex = (unsigned)(e == 0 ? exi[0] : e == 1 ? exi[1] : e == 2 ? exi[2] : exi[3]);
+            const unsigned kobs = (unsigned)(e == 0 ? obi[0] : e == 1 ? obi[1] : e == 2 ? obi[2] : obi[3]);
+            const unsigned c = (unsigned)(c0 + e);
+            reinterpret_cast<unsigned long long *>(S.zsT)[e * kWZS + 2 + cg] = direct_key(ex, kobs, c, (omask >> e) & 1u);
+            env.atomic_or_shared(&S.dmask[c >> 5], 1u << (c & 31));
+        }
+        env.atomic_add_shared(&S.pg[0].ndirect, 1u);
+    }
+}
+
+// ---- step D2: NB p-values outside the table (dispersion.pyx:291-316 -> nbinom.pyx:121-138 -> incbet.c) -----------------
+// Step D records every such element as one 64-bit key {exp : 32 | obs : 15 | output flag : 1 | item position : 16} in
+// the shared-memory arrays that are dead after D (packed cuts + window sums: one contiguous block). The keys are sorted
+// (bitonic, the warp's 32 lanes), so that equal (exp, obs) pairs are neighbours: the first key of every run is a "head",
+// heads are evaluated once each — 32 at a time, in sorted order, which keeps the continued fractions of a warp's lanes
+// alike in branch and iteration count (SURVEY hard part 9) — and the lane that evaluated a head writes p / z for the
+// whole run. With the table in place this is a handful of elements per million; with the table off (--no-lut, the
+// FP64-bound regime) it is every element, and the sort + de-duplication is what the throughput rests on.
+template <class W, class Env>
+FPT_HD void step_direct(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, const double *dmp, bool want_z, W &warp, Env &env) {
+    unsigned long long *keys = direct_keys(S);
+    unsigned *heads = direct_heads(S);
+    // the flagged elements' keys, out of their z slots into the (now dead) sort array
+    warp.each([&](int lane) { if (lane == 0) { S.pg[0].ndirect = 0; S.pg[0].nheads = 0; } });
+    warp.each([&](int lane) {
+        for (int c = lane; c < 4 * Q.ncg; c += 32)
+            if ((S.dmask[c >> 5] >> (c & 31)) & 1u)
+                keys[env.atomic_add_shared(&S.pg[0].ndirect, 1u)] = reinterpret_cast<const unsigned long long *>(S.zsT)[(c & 3) * kWZS + 2 + (c >> 2)];
+    });
+    const int n = (int)S.pg[0].ndirect;
+    int np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    warp.each([&](int lane) {
+        for (int i = n + lane; i < np2; i += 32) keys[i] = ~0ull;
+        if (lane < kWC / 32) S.dmask[lane] = 0;
+    });
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1)
+            warp.each([&](int lane) {
+                for (int t = lane; t < (np2 >> 1); t += 32) {
+                    const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1)), b = a | j;
+                    const bool up = (a & k) == 0;
+                    const unsigned long long ka = keys[a], kb = keys[b];
+                    if ((ka > kb) == up) { keys[a] = kb; keys[b] = ka; }
+                }
+            });
+    // heads, in (roughly) sorted order: passes of 32 consecutive keys append theirs
+    warp.each([&](int lane) {
+        for (int i = lane; i < n; i += 32)
+            if (i == 0 || (keys[i - 1] >> 17) != (keys[i] >> 17)) heads[env.atomic_add_shared(&S.pg[0].nheads, 1u)] = (unsigned)i;
+    });
+    const int nh = (int)S.pg[0].nheads;
+    warp.each([&](int lane) {
+        for (int u = lane; u < nh; u += 32) {
+            const int i0 = (int)heads[u];
+            const unsigned long long k0 = keys[i0];
+            double pv, z;
+            env.direct_pz(dmp, (double)(unsigned)(k0 >> 32), (int)((k0 >> 17) & 0x7FFFu), &pv, &z);
+            for (int i = i0; i < n && (keys[i] >> 17) == (k0 >> 17); ++i) {
+                const unsigned c = (unsigned)keys[i] & 0xFFFFu;
+                if (want_z) S.zsT[(c & 3) * kWZS + 2 + (c >> 2)] = z;
+                if (P.pval_out && ((keys[i] >> 16) & 1u)) P.pval_out[Q.g[sub_of(Q.cge, (int)(c >> 2))].Fb + c] = pv;
+            }
+        }
+    });
+    warp.each([&](int lane) { if (lane == 0) S.pg[0].ndirect = 0; });
 }
 
 // ---- step E: multi-scale Stouffer windows (windowing.h:53-67) of the 4 outputs of group cg from shared-memory z ----
@@ -878,6 +951,7 @@ FPT_HD bool process_item(const ScoreParams &P, bool have_cur, int par, const WPa
             }
             for (int cg = lane; cg < ncg; cg += 32) step_score<SMOOTH>(P, Q, S, tab, dmp, hsub, cg, want_p, want_win, env);
         });
+        if (S.pg[0].ndirect) step_direct(P, Q, S, dmp, want_win, warp, env);
     }
     // the packed cuts, the window sums and the sequence words are dead from here on: the next item's raw data starts
     // its way into them now and arrives while this item's windows are evaluated

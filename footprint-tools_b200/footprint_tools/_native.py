@@ -53,6 +53,7 @@ class ScoreArgs(C.Structure):
         ("hist", C.c_void_p),
         ("hist_d0", C.c_int),
         ("hist_d1", C.c_int),
+        ("max_cut", C.c_int64),
     ]
 
 

@@ -75,6 +75,12 @@ class IntervalBatch(object):
     def total(self):
         return int(self.out_off[-1]) if len(self.out_off) else 0
 
+    def max_cut(self):
+        """Largest cut count of the track, as it is now (the arrays are the caller's and may be rewritten in place, so
+        nothing is cached: the device copy made by to_device carries the value as fpt_score_args.max_cut)."""
+        cp, cm = np.asarray(self.cuts_plus), np.asarray(self.cuts_minus)
+        return int(max(cp.max() if cp.size else 0, cm.max() if cm.size else 0))
+
     @staticmethod
     def from_padded(seqs, cuts_plus, cuts_minus, pad, per_strand=False):
         """seqs[k]: str of L_k+6; cuts_*[k]: array of L_k, where L_k = len_k + 2*pad + 1.
@@ -148,13 +154,14 @@ class IntervalBatch(object):
             return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=False)
 
         return DeviceBatch(dev(self.seq2), dev(self.nmask), dev(self.cuts_plus), dev(self.cuts_minus), self.n_track,
-                           dev(self.iv_start), dev(self.out_off), self.n_iv, self.total)
+                           dev(self.iv_start), dev(self.out_off), self.n_iv, self.total, max_cut=self.max_cut())
 
 
 class DeviceBatch(object):
-    def __init__(self, seq2, nmask, cuts_plus, cuts_minus, n_track, iv_start, out_off, n_iv, total):
+    def __init__(self, seq2, nmask, cuts_plus, cuts_minus, n_track, iv_start, out_off, n_iv, total, max_cut=0):
         self.seq2, self.nmask, self.cuts_plus, self.cuts_minus = seq2, nmask, cuts_plus, cuts_minus
         self.n_track, self.iv_start, self.out_off, self.n_iv, self.total = n_track, iv_start, out_off, n_iv, total
+        self.max_cut = int(max_cut)   # 0 = unknown (the cut counts live on the device)
 
 
 def make_args(batch, hw, shw, clip, combine=True, scales=(), exp=None, obs=None, win=None, pval=None, winp=None,
@@ -178,6 +185,8 @@ def make_args(batch, hw, shw, clip, combine=True, scales=(), exp=None, obs=None,
     if hist is not None:
         a.hist = p(hist)
         a.hist_d0, a.hist_d1 = int(hist.shape[0]), int(hist.shape[1])
+    # (only a device-resident batch carries the bound: it was computed from the very arrays that were uploaded)
+    a.max_cut = int(batch.max_cut) if isinstance(batch, DeviceBatch) else 0
     return a
 
 

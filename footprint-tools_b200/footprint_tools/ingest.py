@@ -327,6 +327,9 @@ class DeviceTrack(object):
     def __init__(self, track, seq2, nmask, cuts_plus, cuts_minus, device):
         self.track, self.device = track, device
         self.seq2, self.nmask, self.cuts_plus, self.cuts_minus = seq2, nmask, cuts_plus, cuts_minus
+        # largest cut count of the whole track at upload time: an upper bound for every batch (fpt_score_args.max_cut)
+        cp, cm = np.asarray(track.cuts_plus), np.asarray(track.cuts_minus)
+        self.max_cut = int(max(cp.max() if cp.size else 0, cm.max() if cm.size else 0))
 
     def batch(self, intervals, pad, per_strand=False):
         """DeviceBatch of `intervals` over the resident track (same geometry as GenomeTrack.batch)."""
@@ -335,7 +338,7 @@ class DeviceTrack(object):
         hb = self.track.batch(intervals, pad, per_strand=per_strand)
         return DeviceBatch(self.seq2, self.nmask, self.cuts_plus, self.cuts_minus, hb.n_track,
                            torch.from_numpy(hb.iv_start).to(self.device), torch.from_numpy(hb.out_off).to(self.device),
-                           hb.n_iv, hb.total)
+                           hb.n_iv, hb.total, max_cut=self.max_cut)
 
 
 def load_posterior_inputs(sample_files, intervals, delim="\t", chunk_bytes=64 << 20):

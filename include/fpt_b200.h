@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FPT_ABI_VERSION 1
+#define FPT_ABI_VERSION 2 /* 2: fpt_score_args.max_cut */
 
 /* error codes */
 #define FPT_OK 0
@@ -185,6 +185,11 @@ typedef struct fpt_score_args {
      * exp < hist_d0, obs < hist_d1, accumulated into (not zeroed). NULL to skip. */
     int64_t *hist;
     int hist_d0, hist_d1;
+    /* An upper bound of the cut counts in the part of the track the intervals read, 0 = unknown. The throughput kernel
+     * carries cut counts up to 2047 (16-bit packed window sums) and hands every item that holds a larger one to the
+     * general kernel in a second launch; a caller that knows the bound (the ingest computes it once per track) saves
+     * that launch. A bound that turns out too small is reported by fpt_ctx_check (FPT_ERR_RANGE), not ignored. */
+    int64_t max_cut;
 } fpt_score_args;
 
 /* Fused scoring of a batch of intervals: 6-mer bias lookup -> window sums -> trimmed-mean

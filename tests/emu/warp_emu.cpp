@@ -53,6 +53,8 @@ struct HostEnv {
     void cp_commit() {}
     void cp_wait() {}
     void atomic_inc_shared(unsigned *p) { *p += 1; }
+    unsigned atomic_add_shared(unsigned *p, unsigned v) { const unsigned o = *p; *p += v; return o; }
+    void atomic_or_shared(unsigned *p, unsigned v) { *p |= v; }
     void atomic_inc_u64(unsigned long long *p) { *p += 1; }
     void direct_pz(const double *dmp, double ex, int kobs, double *pv, double *z) {
         const double rr = orc_fit_r(dmp + 9, ex), mu = orc_fit_mu(dmp, ex);
@@ -127,6 +129,8 @@ extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double 
     HostWarp W;
     HostEnv env;
     memset(S, 0xEE, sizeof(WarpSmem));  // anything read before it is written is loud
+    S->pg[0].ndirect = 0; S->pg[0].nheads = 0;   // (the kernel's prologue)
+    memset(S->dmask, 0, sizeof S->dmask);
     int n_redo = 0;
     // pass -1 issues the copies of item 0 (no current item), as the kernel's first loop iteration does
     int par = 0;
@@ -139,7 +143,11 @@ extern "C" int emu_score(const fpt_score_args *a, const double *bias_le, double 
         }
         // poison everything the item must not inherit from its predecessor (all but the staged raw data)
         memset(S->GA, 0xEE, sizeof S->GA); memset(S->GB, 0xEE, sizeof S->GB);
-        memset(&S->pg[par ^ 1], 0xEE, sizeof(PackGeo));
+        {
+            const unsigned nd = S->pg[0].ndirect, nh = S->pg[0].nheads;   // the warp's D2 counters live in set 0
+            memset(&S->pg[par ^ 1], 0xEE, sizeof(PackGeo));
+            S->pg[0].ndirect = nd; S->pg[0].nheads = nh;
+        }
         bool ok;
 #define EMU_RUN(SM, WMODE) ok = process_item<SM, WMODE>(p, have_cur, par, nx, *S, tab.data(), dmp, hsub.data(), W, env)
         if (shw != 0) {

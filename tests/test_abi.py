@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_table_matches_header():
     assert sorted(_native.SIGNATURES) == declared_symbols()
-    assert _native.lib().fpt_abi_version() == 1
+    assert _native.lib().fpt_abi_version() == 2
 
 
 def test_header_constants_match_python():
@@ -62,7 +62,7 @@ def test_score_args_struct_layout():
         for part in decl.split(","):
             fields.append(re.search(r"([A-Za-z_0-9]+)\s*(\[.*\])?$", part.strip()).group(1))
     assert fields == [f[0] for f in _native.ScoreArgs._fields_]
-    assert C.sizeof(_native.ScoreArgs) == 184
+    assert C.sizeof(_native.ScoreArgs) == 192
 
 
 def test_pack_sequence_host_only():

@@ -202,3 +202,86 @@ def test_detect_batch_columns_and_files(ctx, oracle):
     for line in bed[0.5].getvalue().splitlines()[:20]:
         f = line.split("\t")
         assert len(f) == 5 and f[3] == "." and float(f[4]) <= 0.5
+
+
+# ---- intervals of any length (the reference's detect has no limit: cli/detect.py:132-135, stats/fdr/__init__.py:12-33) ----
+def test_empirical_fdr_any_number_of_observed_values(ctx):
+    """fdr.emperical_fdr beyond the 4096 values the one-CTA kernel sorts in shared memory: global-memory bitonic sort,
+    binary search, bucket scan — exact against the reference formula, ties and NaN included."""
+    rng = np.random.default_rng(11)
+    for n, m in ((4097, 9000), (20000, 100000), (70001, 50000)):
+        nulls = rng.uniform(0, 1, m)
+        nulls[rng.integers(0, m, m // 50)] = 1.0
+        nulls[rng.integers(0, m, 5)] = np.nan
+        pv = rng.uniform(0, 1, n)
+        pv[rng.integers(0, n, n // 20)] = 1.0
+        pv[: n // 10] = rng.choice(nulls[np.isfinite(nulls)], n // 10)  # exact ties
+        pv[rng.integers(0, n, 3)] = np.nan
+        got = ctx.empirical_fdr(nulls, pv)
+        assert np.array_equal(got, ref_emperical_fdr(nulls, pv)), (n, m)
+
+
+def test_long_interval_path_equals_the_one_cta_kernel(monkeypatch):
+    """The same batch through the one-CTA kernel (intervals up to 4096) and, with the limit lowered to 1024, through the
+    global-memory path: the draws are counter-based and the window arithmetic is shared, so every value is equal."""
+    table = synth.vierstra_table()
+    rng = np.random.default_rng(3)
+
+    def lens(n_iv, r, fixed=None):
+        return rng.integers(200, 4000, n_iv).astype(np.int64)
+    monkeypatch.setattr(synth, "interval_lengths", lens)
+    batch, info = synth.make_batch(12, 55, seed=17, table=table, depth_scale=4.0)
+
+    def run(limit):
+        if limit:
+            monkeypatch.setenv("FPT_B200_FDR_ONE_CTA_MAX", str(limit))
+        else:
+            monkeypatch.delenv("FPT_B200_FDR_ONE_CTA_MAX", raising=False)
+        c = _native.Context(0)
+        try:
+            c.set_bias(table, 1e-6)
+            c.set_dm(synth.MU_PARAMS, synth.R_PARAMS)
+            res = engine.score_host(c, batch, 5, 50, 0.01, (3,))
+            return res, engine.detect_fdr_host(c, res["exp"], res["winp"][0], batch.out_off, hw=3, times=20, seed=77)
+        finally:
+            c.close()
+    res_a, a = run(0)
+    res_b, b = run(1024)
+    assert np.array_equal(res_a["winp"], res_b["winp"], equal_nan=True)
+    assert (np.diff(batch.out_off) > 1024).sum() >= 5
+    assert np.array_equal(a, b, equal_nan=True), (int((a != b).sum()), float(np.nanmax(np.abs(a - b))))
+
+
+def test_detect_fdr_on_a_20_kb_and_a_1_mb_interval(ctx, oracle, monkeypatch):
+    """A 20 kb interval between short ones, exact at hw = 0 against the reference formula on the device's own draws
+    (as test_detect_fdr_exact_without_neighbour_sums); a 1 Mb interval (config C5 tiles 1 Mb intervals) at hw = 3:
+    deterministic, a probability, monotone in the observed windowed p-value, and calibrated — the observed p-values
+    are draws from the model itself, so the empirical FDR of a position is ~uniform."""
+    rng = np.random.default_rng(21)
+    table = synth.vierstra_table()
+    want = np.array([300, 20000, 450, 4097, 120], dtype=np.int64)
+    monkeypatch.setattr(synth, "interval_lengths", lambda n_iv, r, fixed=None: want[:n_iv])
+    batch, info = synth.make_batch(len(want), 55, seed=23, table=table, depth_scale=3.0)
+    res = engine.score_host(ctx, batch, 5, 50, 0.01, (0,))
+    exp, pval, winp0 = res["exp"], res["pval"], res["winp"][0]
+    out_off = batch.out_off
+    assert int(np.diff(out_off).max()) == 20000
+    times, seed = 12, 31337
+    got = engine.detect_fdr_host(ctx, exp, winp0, out_off, hw=0, times=times, seed=seed)
+    _, pn = ctx.null_sample(exp, times, seed)
+    ref = _ref_fdr(oracle, pn, pval, out_off, 0, times)
+    assert np.array_equal(got, ref), (int((got != ref).sum()), float(np.abs(got - ref).max()))
+    # 1 Mb
+    n = 1 << 20
+    exp = np.round(rng.gamma(2.0, 8.0, n))
+    _, pobs = ctx.null_sample(exp, 1, 777)
+    winp = np.empty(n)
+    off1 = np.array([0, n], dtype=np.int64)
+    ctx.window(np.ascontiguousarray(pobs[:, 0]), None, n, off1, 1, 3, _native.WIN_STOUFFER, winp, _native.MEM_HOST)
+    f1 = engine.detect_fdr_host(ctx, exp, winp, off1, hw=3, times=10, seed=5)
+    assert np.array_equal(f1, engine.detect_fdr_host(ctx, exp, winp, off1, hw=3, times=10, seed=5))
+    assert np.all((f1 >= 0) & (f1 <= 1))
+    order = np.argsort(winp, kind="stable")
+    assert np.all(np.diff(f1[order]) >= 0)
+    inner = f1[3:-3]                              # the 3 positions at both ends are 1.0 by the edge rule
+    assert abs(inner.mean() - 0.5) < 0.01 and abs(np.mean(inner < 0.1) - 0.1) < 0.01
