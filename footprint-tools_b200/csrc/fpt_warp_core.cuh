@@ -951,7 +951,10 @@ FPT_HD bool process_item(const ScoreParams &P, bool have_cur, int par, const WPa
             }
             for (int cg = lane; cg < ncg; cg += 32) step_score<SMOOTH>(P, Q, S, tab, dmp, hsub, cg, want_p, want_win, env);
         });
-        if (S.pg[0].ndirect) step_direct(P, Q, S, dmp, want_win, warp, env);
+        // (every lane reads the counter before any lane of step D2 resets it: the lanes of a warp are not in lock-step,
+        // and a lane that saw 0 here would miss the warp barriers of the step)
+        const unsigned any_direct = warp.or_reduce([&](int) { return S.pg[0].ndirect; });
+        if (any_direct) step_direct(P, Q, S, dmp, want_win, warp, env);
     }
     // the packed cuts, the window sums and the sequence words are dead from here on: the next item's raw data starts
     // its way into them now and arrives while this item's windows are evaluated
