@@ -317,6 +317,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # one process per GPU: threads and first-touch host memory on the GPU's own NUMA node (the e2e leg moves 4.7 GB per
+    # step and rank over PCIe)
+    host_binding = engine.bind_host_to_gpu(local_rank) if os.environ.get("FPT_BENCH_NO_BIND") != "1" else {"numa_node": None}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -458,7 +461,7 @@ def main():
         except Exception as e:
             consumer = {"unavailable": repr(e)}
         try:
-            c2, _ = synth.make_batch(50000, HW, seed=20242, table=table, fixed_len=300)
+            c2, c2info = synth.make_batch(50000, HW, seed=20242, table=table, fixed_len=300)
             sub = c2.select(engine.shard_intervals(np.diff(c2.out_off), world)[rank]) if world > 1 else c2
             d2 = sub.to_device(dev)
             hist = torch.zeros((200, 1000), dtype=torch.int64, device=dev)
@@ -473,6 +476,7 @@ def main():
 
             lstep()
             barrier()
+            learn_ref = None
             la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             lsteps = 20
             la.record(stream)
@@ -486,10 +490,26 @@ def main():
                 fullh = np.zeros((200, 1000), dtype=np.int64)
                 engine.score_host(ctx, c2, HW, 0, CLIP, (), want=("exp", "obs"), hist=fullh)
                 ok = bool(np.array_equal(fullh, hist.cpu().numpy()))
+                if not args.no_cpu_baseline:
+                    # parity at C2's scale: the histogram of the first 8000 intervals against the reference's C
+                    # (fast_predict without smoothing + the loop of cli/learn_dm.py:276-287), bit for bit
+                    import oracle_lib
+                    orc2, ref2 = oracle_lib.load_oracle(), oracle_lib.load_ref()
+                    k2 = 8000
+                    seq2_, cp2, cm2, ioff2 = synth.oracle_inputs(c2, c2info)
+                    r2 = orc2.score_batch(seq2_, cp2, cm2, ioff2[:k2 + 1], c2.out_off[:k2 + 1], table, mu=synth.MU_PARAMS,
+                                          r=synth.R_PARAMS, hw=HW, shw=0, clip=CLIP, scales=(),
+                                          fn_table=oracle_lib.ref_fn_table(ref2) if ref2 is not None else None,
+                                          nthreads=os.cpu_count() or 1)
+                    href = orc2.hist2d(r2["exp"], r2["obs"])
+                    hdev = np.zeros((200, 1000), dtype=np.int64)
+                    engine.score_host(ctx, c2.select(np.arange(k2)), HW, 0, CLIP, (), want=("exp", "obs"), hist=hdev)
+                    learn_ref = {"intervals": k2, "equal": bool(np.array_equal(href, hdev)),
+                                 "against": "reference C" if ref2 is not None else "oracle port"}
             learn = {"what": "C2: ftd learn_dm histogram, 50 000 x 300 bp, hw=5 shw=0, intervals sharded over %d GPU(s), "
                              "NCCL all-reduce of int64[200,1000] inside the timed region" % world,
                      "value": c2.total / (max(lms) * 1e-3), "unit": "bases/s", "ms_per_pass": max(lms), "per_rank_ms": lms,
-                     "sharded_equals_unsharded": ok}
+                     "sharded_equals_unsharded": ok, "histogram_vs_reference": learn_ref}
         except Exception as e:
             learn = {"unavailable": repr(e)}
 
@@ -537,7 +557,9 @@ def main():
                      "path": {"algorithmic_bytes_per_base": BYTES_PER_BASE, "kernel_ms_per_step": kernel_ms,
                               "achieved": path_gbs, "frac": path_gbs / peak}},
         "e2e": {"value": e2e_val, "unit": "bases/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": args.e2e_steps, "matches_device_path": same, "device_consumer": consumer},
+                "steps": args.e2e_steps, "matches_device_path": same, "device_consumer": consumer,
+                "host": {"cores": os.cpu_count(), "numa_binding_rank0": host_binding,
+                         "counts_cross_pcie_as": "uint32, widened by host threads" if d2h < 44 * total else "float64"}},
         "learn_dm": learn,
         "gpu_launches": launches,
         "clocks": clk,

@@ -296,7 +296,8 @@ __device__ __forceinline__ void ndtr4(const double (&a)[4], const double *s4, do
 __constant__ double kNdK[4] = {FPT_ND_SCALE, FPT_ND_LHI, FPT_ND_LLO, 0.0};
 __constant__ double kNdG[7] = {2.07949308206693863e-02, -6.91185624438261093e-02, 1.65020386126410318e-01, -3.13533160990166759e-01,
                                4.95305615008850841e-01, -6.65382502818922417e-01, 7.69193049757243230e-01};
-#if !FPT_ND_EXP64 && !FPT_ND_G64
+__constant__ double kNdG64[7] = {1.40923486116882261e-05, -5.33751285104347458e-05, -5.88762345240221609e-05, 5.47008438926631780e-04,
+                                 -7.97591746113601187e-04, -2.99395459275425199e-03, 2.07949308206693863e-02};
 __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, double (&res)[4]) {
     double u[4], q[4], r[4], G[4], pe[4];
     int n[4];
@@ -319,6 +320,15 @@ __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, d
         const double qq = fma(nf, kNdK[1], y);
         q[e] = fma(nf, kNdK[2], qq);
     }
+#if FPT_ND_G64
+#pragma unroll
+    for (int e = 0; e < 4; ++e) G[e] = fma(6.15361678962631613e-06, u[e], kNdG64[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) G[e] = fma(G[e], u[e], kNdG64[i]);
+    }
+#else
     {
         float uf[4], Gf[4];
 #pragma unroll
@@ -339,6 +349,15 @@ __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, d
 #pragma unroll
         for (int e = 0; e < 4; ++e) G[e] = fma((double)Gf[e], u[e], kNdG[0]);
     }
+#endif
+#if FPT_ND_EXP64
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pe[e] = fma(1.0 / 120.0, q[e], 1.0 / 24.0);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pe[e] = fma(pe[e], q[e], 1.0 / 6.0);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pe[e] = fma(pe[e], q[e], 0.5);
+#else
     {
         float qf[4], Rf[4];
 #pragma unroll
@@ -353,6 +372,7 @@ __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, d
 #pragma unroll
         for (int e = 0; e < 4; ++e) pe[e] = fma((double)Rf[e], q[e], 0.5);
     }
+#endif
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
@@ -386,9 +406,6 @@ __device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, d
         }
     }
 }
-#else
-__device__ __forceinline__ void ndtr4c(const double (&a)[4], const double *s4, double (&res)[4]) { ndtr4(a, s4, res); }
-#endif
 
 __device__ __forceinline__ int fregion_of(const int *bases, int nreg, int v) {
     int r = 0;

@@ -77,7 +77,8 @@ struct alignas(16) SubStage {
     int xg0, nxg;      // first staged group, number of staged groups
     int sw, mw;        // first staged sequence / mask word
     int nsw, nmw;      // number of them
-    int iv, pad_;
+    int iv;
+    int inside;        // 1: the whole staged range [G0, G0 + 4 nxg) lies inside the track and G0 is a multiple of 4
 };
 // Geometry of a pack, built by prepare_pack one item ahead (two sets per warp, used alternately).
 struct alignas(16) PackGeo {
@@ -196,7 +197,7 @@ FPT_HD ItemGeo item_geometry(const WItem &it, int WH) {
 // The geometry of a pack (executed by lanes 0 .. kWMaxSub - 1, one sub-item each; the others idle): every sub-item's
 // frame is laid into the item's c-space (lane-groups), x-space (staged slots: its groups plus kWHaloG of halo) and
 // staged sequence / mask words one after the other.
-FPT_HD void prepare_pack(const WPack &R, int wh, PackGeo &Q, int lane) {
+FPT_HD void prepare_pack(const WPack &R, int wh, long long n_track, PackGeo &Q, int lane) {
     if (lane >= kWMaxSub) return;
     const int nsub = R.nsub;
     if (lane >= nsub) {
@@ -233,7 +234,8 @@ FPT_HD void prepare_pack(const WPack &R, int wh, PackGeo &Q, int lane) {
     t.xg0 = xgs; t.nxg = G.NXG;
     t.sw = sw; t.mw = mw;
     t.nsw = sub_seq_words(G.NCG); t.nmw = sub_mask_words(G.NCG);
-    t.iv = it.iv; t.pad_ = 0;
+    t.iv = it.iv;
+    t.inside = ((G.G0 & 3) == 0 && G.G0 >= 0 && G.G0 + 4LL * G.NXG <= n_track) ? 1 : 0;
     Q.s[lane] = t;
     Q.cge[lane] = cgs + G.NCG;
     Q.xge[lane] = xgs + G.NXG;
@@ -301,7 +303,7 @@ FPT_HD void stage_issue(const StageSrc P, const PackGeo &Q, WarpSmem &S, int lan
         const int i = sub_of(Q.xge, xg);
         const int x = xg << 2;
         const long long g = Q.s[i].G0 + ((xg - Q.s[i].xg0) << 2);
-        if (P.cuts_vec && (g & 3) == 0 && g >= 0 && g + 4 <= P.n_track) {
+        if (P.cuts_vec && (Q.s[i].inside || ((g & 3) == 0 && g >= 0 && g + 4 <= P.n_track))) {
             env.cp16(rawP + x, P.cuts_p + g);
             env.cp16(rawM + x, P.cuts_m + g);
         } else {
@@ -961,7 +963,7 @@ FPT_HD bool process_item(const ScoreParams &P, bool have_cur, int par, const WPa
     if (next) {
         warp.each([&](int) { env.cp_wait(); });  // the record of `next` (copied asynchronously since the top of the pass)
         PackGeo &Qn = S.pg[par ^ 1];
-        warp.each([&](int lane) { prepare_pack(*next, wh, Qn, lane); });
+        warp.each([&](int lane) { prepare_pack(*next, wh, P.n_track, Qn, lane); });
         warp.each([&](int lane) { env.stage(stage_src(P), Qn, S, lane); });
     }
     if (good && want_win) {

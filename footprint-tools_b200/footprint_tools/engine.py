@@ -367,3 +367,44 @@ def allreduce_histogram(hist, group=None):
         return hist
     dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
     return hist
+
+
+def bind_host_to_gpu(device_index):
+    """Keep this process — its threads, and through first touch its (pinned) host buffers — on the CPUs of the NUMA node
+    the GPU hangs off (one process per GPU: a rank that floats across sockets sends its PCIe traffic through the
+    inter-socket link). Reads /sys/bus/pci/devices/<bdf>/numa_node; does nothing where the platform does not say.
+    Returns {'numa_node': n or None, 'cpus': count, 'pci': bdf}. Call before allocating the host buffers."""
+    import os
+    import subprocess
+
+    bdf = None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    except Exception:
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device_index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = out[-12:].lower() if out else None       # 00000000:1B:00.0 -> 0000:1b:00.0
+        except Exception:
+            bdf = None
+    info = {"numa_node": None, "cpus": 0, "pci": bdf}
+    if not bdf:
+        return info
+    try:
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(numa_node=node, cpus=len(allowed))
+    except Exception:
+        pass
+    return info
+
