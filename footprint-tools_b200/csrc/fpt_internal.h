@@ -40,13 +40,16 @@ struct alignas(16) WItem {
     int ta, tb;
     int iv;
 };
-constexpr int kWMaxSub = 4;
+#ifndef FPT_WARP_MAXSUB
+#define FPT_WARP_MAXSUB 3
+#endif
+constexpr int kWMaxSub = FPT_WARP_MAXSUB;  // 3 or 4
 // Largest cut count the kernel's packed 16-bit format carries (the test is an OR mask, hence 2^k - 1): a 10-wide window
 // sum is then at most 20 470 and the sum of TWO of them still fits a 16-bit half — wider sums are taken in 32 bits.
 constexpr unsigned kWPackedCutLimit = 0x7FFu;
 struct alignas(16) WPack {
     int nsub;
-    int cgs[kWMaxSub - 1];  // first lane-group of sub-items 1 .. 3 in the item
+    int cgs[3];             // first lane-group of sub-items 1 .. kWMaxSub - 1 in the item
     WItem sub[kWMaxSub];
 };
 

@@ -68,24 +68,26 @@ __device__ __forceinline__ double fast_rcp(double d) {
 __device__ __noinline__ double ndtr_slow(double a) { return ndtr_fn(a); }
 
 // ndtr(a) = Phi(a) (reference: hcephes_ndtr, ndtr.c:34-59) as the Stouffer windows of the throughput paths
-// evaluate it: one branch-free path for |a| < 26 instead of Cephes' three ranges, cut so that the FP64 pipe (64
-// lanes per SM, the unit the window arithmetic saturates) carries only the digits that need it:
+// evaluate it: one branch-free path for |a| < 26 instead of Cephes' three ranges:
 //   Q(t) = exp(-t^2/2) * G(u) / (t + 5),   G(u) = (t + 5) * 0.5 * erfcx(t / sqrt 2),  u = 1 - 10/(t + 5)
-//  * G is a degree-13 polynomial (Chebyshev fit against mpmath, tools/fit_ndtr.py --mixed); its seven
-//    highest-order coefficients (|c| <= 3e-3, contribution to G below 4e-3) are summed in FP32, the rest in
-//    FP64 — the FP32 rounding reaches G at 2e-11 relative;
-//  * exp(y) = 2^(n/4) * exp(q), |q| <= ln2/8: q^3/6 .. q^6/720 in FP32 (below 1.1e-4, i.e. 1e-11 of the result),
-//    1 + q + q^2/2 in FP64, 2^(j/4) from a 4-entry shared-memory table (one conflict-free LDS.64);
+//  * G is a degree-13 polynomial (Chebyshev fit against mpmath, tools/fit_ndtr.py);
+//  * exp(y) = 2^(n/16) * exp(q), |q| <= ln2/32, degree 5 in q (truncation 1.4e-13), 2^(j/16) from a 16-entry
+//    shared-memory table;
 //  * range test and sign handling on the high word (integer pipe).
-// Max relative error of Q over [0, 26]: 6e-11 (tools/fit_ndtr.py replays this exact operation order
-// against mpmath), i.e. <= 2.6e-11 absolute on -log10 p; the parity bar is 1e-9 relative. 24 FP64 operations
-// per value instead of 38. |a| >= 26, infinities and NaN go to the Cephes replica as before.
-// s4 = {1, 2^(1/4), 2^(1/2), 2^(3/4)} in shared memory (ndtr4_table_init).
+// Max relative error of Q over [0, 26] below 6e-11 (tools/fit_ndtr.py replays the operation order against mpmath),
+// i.e. <= 2.6e-11 absolute on -log10 p; the parity bar is 1e-9 relative. |a| >= 26 finite goes to the Cephes replica,
+// a non-finite a is NaN as in the reference.
+// Two build variants move part of the arithmetic to FP32 (FPT_ND_G64=0: the seven highest-order coefficients of G,
+// |c| <= 3e-3, in FFMA — 2e-11 relative on G; FPT_ND_EXP64=0: q^3/6 .. q^6/720 in FP32 with a 4-entry table and
+// |q| <= ln2/8): 24 FP64 operations per value instead of 38. They paid while the separate window kernel of round 1 was
+// bound by FP64 dispatch; the fused warp-autonomous kernel is bound by instruction ISSUE, where the two format
+// conversions per detour cost more than the FP64 operations they save (measured on C3: 2.02 against 2.04 ms,
+// profiles/r2/warp_variants.txt), so all-FP64 is the default.
 #ifndef FPT_ND_EXP64
-#define FPT_ND_EXP64 0  // 1: exp(q) entirely in FP64 (16-entry table, |q| <= ln2/32, degree 5) — no FP32 detour
+#define FPT_ND_EXP64 1  // 1: exp(q) entirely in FP64 (16-entry table, |q| <= ln2/32, degree 5) — no FP32 detour
 #endif
 #ifndef FPT_ND_G64
-#define FPT_ND_G64 0    // 1: all 14 coefficients of G in FP64
+#define FPT_ND_G64 1    // 1: all 14 coefficients of G in FP64
 #endif
 constexpr int kNdTab = 16;  // doubles the callers reserve for the 2^(j/N) table
 __constant__ double kPow16[16] = {1.00000000000000000e+00, 1.04427378242741375e+00, 1.09050773266525769e+00, 1.13878863475669156e+00,

@@ -12,7 +12,7 @@ namespace {
 using namespace wk;
 
 #ifndef FPT_WARP_WARPS
-#define FPT_WARP_WARPS 12  // measured on C3: 8 warps 2.52 ms, 12 warps 2.03 ms, 14 warps 2.19 ms, 16 warps 2.10 ms (profiles/r2_warp_variants.txt)
+#define FPT_WARP_WARPS 16  // with 256-position items (fpt_warp_core.cuh); 384-position items fit 12 warps (profiles/r2/warp_variants.txt)
 #endif
 constexpr int kWWarps = FPT_WARP_WARPS;     // warps per CTA (one CTA per SM)
 constexpr int kWThreads = 32 * kWWarps;

@@ -35,8 +35,12 @@
 namespace fpt {
 namespace wk {
 
+// 256 positions (64 lane-groups, two rounds) and 3 sub-items per item keep a warp's shared memory at 10.8 KB, which lets
+// 16 warps share an SM: measured on C3 (profiles/r2/warp_variants.txt) 2.00 ms against 2.04 ms for 384 positions / 4
+// sub-items at 12 warps (14.9 KB each) — four warps per scheduler hide more latency than the smaller items cost (the same
+// item size at 12 warps: 2.13 ms).
 #ifndef FPT_WARP_KWC
-#define FPT_WARP_KWC 384
+#define FPT_WARP_KWC 256
 #endif
 constexpr int kWC = FPT_WARP_KWC;             // c-space capacity of an item (computed positions, rounds of 128)
 constexpr int kWCG = kWC / 4;                 // 96 lane-groups of 4 positions
@@ -47,9 +51,10 @@ constexpr int kWX = 4 * kWXG;                 // 832 staged slots
 constexpr int kWPre = 8;                      // readable slots before / after the packed-cut array
 constexpr int kWZS = kWCG + 4;                // row stride of the transposed z array (2 pad entries each side)
 // An interval's groups weigh at least kWMinW in the planner's stream, which bounds the sub-items of a pack: a run of
-// OG <= kWCG stream units touches at most two whole intervals and two partial ones when 3 kWMinW + 2 > OG.
-constexpr int kWMinW = (kWCG - 2) / 3 + 1;
-static_assert(kWMaxSub == 4 && 3 * kWMinW + 2 > kWCG, "sub-item bound of a pack");
+// OG <= kWCG stream units touches at most two partial intervals and kWMaxSub - 2 whole ones when
+// (kWMaxSub - 1) kWMinW + 2 > OG.
+constexpr int kWMinW = (kWCG - 2) / (kWMaxSub - 1) + 1;
+static_assert((kWMaxSub == 3 || kWMaxSub == 4) && (kWMaxSub - 1) * kWMinW + 2 > kWCG, "sub-item bound of a pack");
 // staged sequence words of a sub-item of n c-groups: its lane windows start at bit position q <= 4 n - 4 + 31 and
 // read words q/16 .. q/16 + 2 (2-bit codes) and q/32, q/32 + 1 (N bits)
 FPT_HD int sub_seq_words(int ncg) { return ((4 * ncg + 27) >> 4) + 3; }
@@ -85,8 +90,8 @@ struct alignas(16) PackGeo {
     int nsub, ncg, nxg, nmw;   // sub-items, c-groups, staged groups, staged mask words of the whole item
     unsigned ndirect, nheads;  // step D2's counters (those of set 0 are the warp's; zero between items)
     int pad_[2];
-    int cge[kWMaxSub];         // c-group where sub-item i ends (INT_MAX beyond the last)
-    int xge[kWMaxSub];         // staged group where sub-item i ends
+    int cge[4];                // c-group where sub-item i ends (INT_MAX beyond the last)
+    int xge[4];                // staged group where sub-item i ends
     SubGeo g[kWMaxSub];
     SubStage s[kWMaxSub];
 };
@@ -198,7 +203,7 @@ FPT_HD ItemGeo item_geometry(const WItem &it, int WH) {
 // frame is laid into the item's c-space (lane-groups), x-space (staged slots: its groups plus kWHaloG of halo) and
 // staged sequence / mask words one after the other.
 FPT_HD void prepare_pack(const WPack &R, int wh, long long n_track, PackGeo &Q, int lane) {
-    if (lane >= kWMaxSub) return;
+    if (lane >= 4) return;
     const int nsub = R.nsub;
     if (lane >= nsub) {
         Q.cge[lane] = 0x7FFFFFFF;
@@ -245,7 +250,7 @@ FPT_HD void prepare_pack(const WPack &R, int wh, long long n_track, PackGeo &Q, 
     }
 }
 // the sub-item of lane-group cg / staged group xg
-FPT_HD int sub_of(const int (&ends)[kWMaxSub], int v) {
+FPT_HD int sub_of(const int (&ends)[4], int v) {
     const int4 e = *reinterpret_cast<const int4 *>(ends);
     return (v >= e.x ? 1 : 0) + (v >= e.y ? 1 : 0) + (v >= e.z ? 1 : 0);
 }
@@ -511,7 +516,7 @@ FPT_HD void store_partial(double *dst, unsigned omask, double v0, double v1, dou
 }
 
 // (shared-memory arrays of step D2, below)
-constexpr int kWDirectCap = 512;
+constexpr int kWDirectCap = kWC <= 128 ? 128 : (kWC <= 256 ? 256 : 512);  // power of two >= kWC
 static_assert(kWC <= kWDirectCap, "one key per item position");
 FPT_HD unsigned long long *direct_keys(WarpSmem &S) { return reinterpret_cast<unsigned long long *>(S.cw_); }
 FPT_HD unsigned *direct_heads(WarpSmem &S) { return reinterpret_cast<unsigned *>(S.cw_) + 2 * kWDirectCap; }

@@ -97,12 +97,20 @@ def oracle_ref(oracle, batch, info, table, shw, scales, uniform=False):
                               r=synth.R_PARAMS, hw=5, shw=shw, clip=0.01, scales=scales, nthreads=4)
 
 
-def planned_items(batch, wh, kwcg=96):
+def _emu_variant():
+    """(lane-groups per item, sub-items per item) of the emulated build (FPT_EMU_FLAGS)."""
+    flags = dict(f.lstrip("-D").split("=") for f in os.environ.get("FPT_EMU_FLAGS", "").split() if "=" in f)
+    return int(flags.get("FPT_WARP_KWC", 256)) // 4, int(flags.get("FPT_WARP_MAXSUB", 3))
+
+
+def planned_items(batch, wh, kwcg=None):
     """Items of the planner (fpt_warp_core.cuh 'planning'): the stream of 4-position output groups of all intervals — an
     interval weighs at least kWMinW = 32 units — divided into runs of OG = 96 - 2 ceil(wh / 4) units."""
+    cg, maxsub = _emu_variant()
+    kwcg = kwcg or cg
     o = np.asarray(batch.out_off, dtype=np.int64)
     ng = np.where(o[1:] > o[:-1], (o[1:] + 3) // 4 - o[:-1] // 4, 0)
-    w = np.where(ng > 0, np.maximum(ng, (kwcg - 2) // 3 + 1), 0)
+    w = np.where(ng > 0, np.maximum(ng, (kwcg - 2) // (maxsub - 1) + 1), 0)
     og = kwcg - 2 * ((wh + 3) // 4)
     return -(-int(w.sum()) // og)
 
@@ -196,7 +204,7 @@ def test_interval_lengths_around_the_edge_rules_and_piece_boundaries(emu, oracle
     check(out, ref, redo, (3, 5, 7), "len %d" % fixed_len)
     assert stats[0] == planned_items(batch, 7) and stats[2] >= batch.n_iv
     if fixed_len >= 381:   # full lane-groups: every item but the last holds 92 output groups
-        assert stats[0] == -(-int(np.sum((batch.out_off[1:] + 3) // 4 - batch.out_off[:-1] // 4)) // 92)
+        assert stats[0] == -(-int(np.sum((batch.out_off[1:] + 3) // 4 - batch.out_off[:-1] // 4)) // (_emu_variant()[0] - 4))
 
 
 def test_one_long_interval_and_misaligned_outputs(emu, oracle, table, lut):
