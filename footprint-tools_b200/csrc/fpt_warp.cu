@@ -1,6 +1,6 @@
 // fpt_warp.cu — device side of the warp-autonomous scoring kernel (steps in fpt_warp_core.cuh): the item planner,
-// the persistent kernel (one 12-warp CTA per SM, every warp fetches work items — packs of interval pieces that fill
-// its 96 lane-groups — from a global counter and runs an item from the packed track to its outputs with no block
+// the persistent kernel (one 16-warp CTA per SM, every warp fetches work items — packs of interval pieces that fill
+// its 64 lane-groups — from a global counter and runs an item from the packed track to its outputs with no block
 // barrier), and the launchers.
 #include "fpt_tile.cuh"
 #include "fpt_warp_core.cuh"

@@ -13,7 +13,7 @@
 //
 // Design: one WARP owns one work item from the packed track to exp / obs / p and the windowed
 // p-values. An item is a PACK of up to kWMaxSub sub-items — whole intervals or pieces of intervals — that together
-// fill the warp's kWC / 4 = 96 lane-groups of 4 positions: the planner divides the stream of 4-position output groups
+// fill the warp's kWC / 4 = 64 lane-groups of 4 positions: the planner divides the stream of 4-position output groups
 // of all intervals into equal runs, so that every round of the scoring and window steps has all 32 lanes at work
 // whatever the interval lengths are (one interval per item left a quarter of the lanes idle on 150-1200 bp DHS
 // intervals). Nothing intermediate touches HBM, no block barrier exists: the five steps of an item are separated by
@@ -43,11 +43,11 @@ namespace wk {
 #define FPT_WARP_KWC 256
 #endif
 constexpr int kWC = FPT_WARP_KWC;             // c-space capacity of an item (computed positions, rounds of 128)
-constexpr int kWCG = kWC / 4;                 // 96 lane-groups of 4 positions
+constexpr int kWCG = kWC / 4;                 // 64 lane-groups of 4 positions
 constexpr int kWPad = 56;                     // slots staged before and after a sub-item's computed range (>= 5 + 50 + 1)
 constexpr int kWHaloG = 2 * kWPad / 4;        // 28 groups of halo per sub-item
-constexpr int kWXG = kWCG + kWMaxSub * kWHaloG;  // 208 groups of 4 staged slots
-constexpr int kWX = 4 * kWXG;                 // 832 staged slots
+constexpr int kWXG = kWCG + kWMaxSub * kWHaloG;  // 148 groups of 4 staged slots
+constexpr int kWX = 4 * kWXG;                 // 592 staged slots
 constexpr int kWPre = 8;                      // readable slots before / after the packed-cut array
 constexpr int kWZS = kWCG + 4;                // row stride of the transposed z array (2 pad entries each side)
 // An interval's groups weigh at least kWMinW in the planner's stream, which bounds the sub-items of a pack: a run of
@@ -96,7 +96,7 @@ struct alignas(16) PackGeo {
     SubStage s[kWMaxSub];
 };
 
-// per-warp shared memory (15 152 bytes)
+// per-warp shared memory (10.8 KB at the default sizes)
 struct alignas(16) WarpSmem {
     uint32_t cw_[kWPre + kWX + kWPre];   // packed cuts, slot x at cw_[kWPre + x]
     uint32_t wcw[kWX + 16];              // packed 10-wide sums

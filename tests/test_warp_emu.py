@@ -105,7 +105,8 @@ def _emu_variant():
 
 def planned_items(batch, wh, kwcg=None):
     """Items of the planner (fpt_warp_core.cuh 'planning'): the stream of 4-position output groups of all intervals — an
-    interval weighs at least kWMinW = 32 units — divided into runs of OG = 96 - 2 ceil(wh / 4) units."""
+    interval weighs at least kWMinW units — divided into runs of OG = kWC / 4 - 2 ceil(wh / 4) units (default build:
+    kWC = 256, at most 3 sub-items per item, kWMinW = 32)."""
     cg, maxsub = _emu_variant()
     kwcg = kwcg or cg
     o = np.asarray(batch.out_off, dtype=np.int64)
