@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
                     if (has1) zcol[jj1 * P.nmax + i1] = d1.z;
                 }
                 __syncthreads();
-                for (int q = tid; q < nj * n; q += kFdrThreads) {
+                auto null_window = [&](int q) {
                     const int jj = q / n, i = q - jj * n;
                     double v = 1.0;  // windowing.pyx:51-54: positions closer than hw to an end
                     if (i >= P.hw && i < n - P.hw) {
@@ -313,7 +313,25 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
                         // (a non-finite sum — a null draw with p < 2^-53 has z = +inf — is NaN in the reference: ndtr.c:34-59)
                         v = fabs(a) < 26.0 ? ndtr_fast1(a, s4) : (fabs(a) <= 1.79769313486231570815e308 ? ndtr_slow(a) : a - a);
                     }
-                    count_null(v);
+                    return v;
+                };
+                // two null values per thread and pass: their searches among the sorted observed values run in lock-step, so
+                // that two chains of dependent shared-memory loads are in flight instead of one
+                for (int q = tid; q < nj * n; q += 2 * kFdrThreads) {
+                    const int q1 = q + kFdrThreads;
+                    const bool has1 = q1 < nj * n;
+                    const double v0 = null_window(q), v1 = has1 ? null_window(q1) : 0.0;
+                    const bool f0 = v0 == v0, f1 = has1 && v1 == v1;
+                    const unsigned long long k0 = order_key(v0), k1 = order_key(v1);
+                    int a0 = 0, b0 = f0 ? n : 0, a1 = 0, b1 = f1 ? n : 0;  // first k in [0, n] with keys[k] >= key
+                    while (a0 < b0 || a1 < b1) {
+                        const int m0 = (a0 + b0) >> 1, m1 = (a1 + b1) >> 1;   // (a finished search sits at <= n: a valid word)
+                        const unsigned long long x0 = keys[min(m0, n - 1)], x1 = keys[min(m1, n - 1)];
+                        if (a0 < b0) { if (x0 >= k0) b0 = m0; else a0 = m0 + 1; }
+                        if (a1 < b1) { if (x1 >= k1) b1 = m1; else a1 = m1 + 1; }
+                    }
+                    if (f0) atomicAdd(&bucket[a0], 1u); else atomicAdd(&nan_count, 1u);
+                    if (has1) { if (f1) atomicAdd(&bucket[a1], 1u); else atomicAdd(&nan_count, 1u); }
                 }
             }
         }

@@ -270,8 +270,16 @@ cudaError_t launch_plan_items(cudaStream_t st, const long long *out_off, const l
     if (blocks > sm_count) blocks = sm_count;   // one block per SM: the grid barrier needs every block resident
     // the same shared-memory carve-out as the scoring kernel that follows: no reconfiguration of the SMs between them
     cudaFuncSetAttribute(plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    plan_kernel<<<(unsigned)blocks, kPlanThreads, 0, st>>>(out_off, iv_start, n_iv, OG, wh, b.pw, b.bsum, b.first_iv, b.head, b.items);
-    return cudaGetLastError();
+    // a COOPERATIVE launch: the runtime starts the grid only when every block can be resident at once, which the grid
+    // barrier relies on (a plain launch interleaved with another context's planner on the same GPU could leave both
+    // spinning for blocks that never get an SM)
+    long long n_iv_arg = n_iv;
+    int og_arg = OG, wh_arg = wh;
+    long long *pw = b.pw, *bsum = b.bsum;
+    int *first_iv = b.first_iv, *head = b.head;
+    WPack *items = b.items;
+    void *args[] = {(void *)&out_off, (void *)&iv_start, &n_iv_arg, &og_arg, &wh_arg, &pw, &bsum, &first_iv, &head, &items};
+    return cudaLaunchCooperativeKernel((const void *)plan_kernel, dim3((unsigned)blocks), dim3(kPlanThreads), args, 0, st);
 }
 
 namespace {

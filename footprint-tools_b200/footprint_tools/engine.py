@@ -278,6 +278,7 @@ def detect_footprints_device(ctx, dbatch, thresholds, hw=5, shw=50, clip=0.01, w
     for t in thresholds:
         rec = ctx.segment_batch(bufs["efdr"], dbatch.out_off, t, 3, True, mem=MEM_DEVICE, n_iv=dbatch.n_iv, total=tot)
         out[t] = tuple(r.cpu().numpy() for r in rec)
+    ctx.check()   # the device status word (a cut count beyond the exact range / beyond the caller's bound): raise, do not return partial columns
     return out, bufs
 
 

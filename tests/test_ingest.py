@@ -718,3 +718,31 @@ def test_gpu_ftd_posterior_from_bedgraph_files(tmp_path):
     assert np.array_equal(np.isnan(got), np.isnan(want))
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)
     assert np.any(got > 0)
+
+
+def test_cutcounts_bamfile_reads_a_packed_track(tmp_path, small_track):
+    """`cutcounts.bamfile(path, min_qual=..., ...)` as cli/detect.py:103-105 constructs it, over a `.fptrk` track:
+    `bamfile[interval]` / `.lookup(interval)` return what the track's read_func returns; anything that is not a packed
+    track is refused (alignment decoding is htslib's job)."""
+    from footprint_tools import cutcounts
+
+    path = str(tmp_path / "t.fptrk")
+    rng, _, track = small_track
+    track.set_cuts("chrA", rng.integers(0, 9, 5000).astype(np.uint32), rng.integers(0, 9, 5000).astype(np.uint32))
+    track.save(path)
+    reader = cutcounts.bamfile(path, min_qual=1, remove_dups=False, remove_qcfail=True, offset=(0, -1))
+    iv = genomic_interval("chrA", 5, 60)
+    got, ref = reader[iv], track.read_func[iv]
+    assert np.array_equal(got["+"], ref["+"]) and np.array_equal(got["-"], ref["-"]) and got["+"].sum() > 0
+    assert np.array_equal(reader.lookup(iv)["+"], ref["+"])
+    assert cutcounts.bamfile(track).track is track
+    with pytest.raises(IOError):
+        cutcounts.bamfile(str(tmp_path / "reads.bam"))
+
+
+def test_host_binding_is_harmless_without_platform_information():
+    """engine.bind_host_to_gpu: where the GPU's NUMA node cannot be read (no GPU, a VM with one node) nothing is bound."""
+    from footprint_tools import engine
+    info = engine.bind_host_to_gpu(0)
+    assert set(info) == {"numa_node", "cpus", "pci"}
+    assert info["numa_node"] is None or info["cpus"] > 0
