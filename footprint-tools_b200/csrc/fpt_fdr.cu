@@ -585,6 +585,8 @@ cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, c
     while (P.np < nmax) P.np <<= 1;
     P.jb = nulls ? 1 : (4096 / nmax < 1 ? 1 : (4096 / nmax > 8 ? 8 : 4096 / nmax));
     if (!nulls && P.jb > times) P.jb = times > 0 ? times : 1;
+    // (fewer null columns per pass would buy a fourth CTA per SM, but measured on C3 it loses: 3 columns 127 ms, 2 columns
+    // 135 ms, 1 column 162 ms per pass — the two block barriers of a pass cost more than the occupancy gives)
     P.nulls = nulls; P.m = m; P.status = status;
     const size_t smem = efdr_smem_bytes(P.np, P.nmax, P.jb);
     cudaError_t e = cudaFuncSetAttribute(efdr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

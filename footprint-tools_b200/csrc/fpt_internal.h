@@ -8,7 +8,10 @@
 namespace fpt {
 
 constexpr int kModelDoubles = 24;
-constexpr int kGuide = 64;         // quantile guide entries per table row (fpt_ops.cu guide_build_kernel, fpt_fdr.cu)  // 9 mu params + 15 r params (dispersion.pyx:117-125)
+#ifndef FPT_GUIDE
+#define FPT_GUIDE 1024  // measured on the C3 FDR step: 64 -> 145 ms, 256 -> 134 ms, 1024 -> 127 ms per pass (same draws, same results)
+#endif
+constexpr int kGuide = FPT_GUIDE;         // quantile guide entries per table row (fpt_ops.cu guide_build_kernel, fpt_fdr.cu)  // 9 mu params + 15 r params (dispersion.pyx:117-125)
 
 // Fused-kernel geometry. One CTA = kThreads threads works on sub-tiles of at
 // most kComputeMax scored positions staged into at most kStageCap shared-memory slots.
