@@ -34,6 +34,7 @@ namespace fpt {
 namespace {
 
 constexpr int kFdrThreads = 256;
+constexpr int kKeyGuide = 1024;  // bins of the guide over an interval's sorted observed values (efdr_kernel)
 
 // ---- Philox4x32-10 (Salmon et al. 2011) ------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
     int *idx = reinterpret_cast<int *>(zcol + (size_t)P.jb * P.nmax);              // np
     int *rank_of = idx + P.np;                                                     // nmax
     unsigned *bucket = reinterpret_cast<unsigned *>(rank_of + P.nmax);             // np + 1
+    unsigned short *kguide = reinterpret_cast<unsigned short *>(bucket + P.np + 1);  // kKeyGuide + 1
     __shared__ double s4[kNdTab];
     __shared__ unsigned part[kFdrThreads];
     __shared__ unsigned nan_count;
@@ -250,8 +252,14 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
         for (int i = tid; i <= np; i += kFdrThreads) bucket[i] = 0;
         if (tid == 0) nan_count = 0;
         __syncthreads();
+        // (a warp's pairs t = 32 w .. 32 w + 31 (+ multiples of kFdrThreads) touch only elements 64 w .. 64 w + 63 (+ ...) while
+        //  the partner distance j is at most 32: those steps need a warp barrier only; the block meets around the others)
+        bool block_level = true;   // the previous step was at block level (the fill above counts as one)
         for (int k = 2; k <= np; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
+                const bool wide = j > 32;
+                if (wide || block_level) __syncthreads(); else __syncwarp();
+                block_level = wide;
                 for (int t = tid; t < (np >> 1); t += kFdrThreads) {
                     const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
                     const int b = a | j;
@@ -262,17 +270,35 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
                         const int ia = idx[a]; idx[a] = idx[b]; idx[b] = ia;
                     }
                 }
-                __syncthreads();
             }
         }
+        __syncthreads();
         for (int k = tid; k < n; k += kFdrThreads) rank_of[idx[k]] = k;
         // (keys[n .. np) are padding: the n real values, NaNs included, sort in front of it)
+        // guide over the sorted observed values: kguide[b] = first k with keys[k] >= b / kKeyGuide, kguide[kKeyGuide] = n — a
+        // null p-value v in [b / kKeyGuide, (b + 1) / kKeyGuide) is located in [kguide[b], kguide[b + 1]], a couple of
+        // entries instead of the whole interval (same result: the bracket holds the answer of the full search)
+        for (int b = tid; b <= kKeyGuide; b += kFdrThreads) {
+            int lo = 0, hi = n;
+            if (b < kKeyGuide) {
+                const unsigned long long kb = order_key((double)b * (1.0 / kKeyGuide));
+                while (lo < hi) {
+                    const int m = (lo + hi) >> 1;
+                    if (keys[m] >= kb) hi = m; else lo = m + 1;
+                }
+            }
+            kguide[b] = (unsigned short)hi;
+        }
 
         // ---- every null value: locate among the sorted observed values, count ----------------------
         auto count_null = [&](double v) {
             if (v != v) { atomicAdd(&nan_count, 1u); return; }
             const unsigned long long kv = order_key(v);
             int a = 0, b = n;  // first k in [0, n] with keys[k] >= kv
+            if (v >= 0.0 && v <= 1.0) {
+                const int g = min((int)(v * (double)kKeyGuide), kKeyGuide - 1);
+                a = kguide[g]; b = kguide[g + 1];
+            }
             while (a < b) {
                 const int m = (a + b) >> 1;
                 if (keys[m] >= kv) b = m; else a = m + 1;
@@ -286,27 +312,34 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
             for (long long q = tid; q < P.m; q += kFdrThreads) count_null(P.nulls[q]);
         } else {
             M = (long long)n * P.times;
-            for (int j0 = 0; j0 < P.times; j0 += P.jb) {
-                const int nj = min(P.jb, P.times - j0);
+            // null columns per pass: as many as fit the z array at THIS interval's length (it is sized for jb columns of
+            // the longest interval) — fewer passes, fewer block barriers, more work per thread between them
+            const int jbi = max(1, min(P.times, (P.jb * P.nmax) / n));
+            for (int j0 = 0; j0 < P.times; j0 += jbi) {
+                const int nj = min(jbi, P.times - j0);
                 __syncthreads();  // zcol free (and, first pass, the sort visible)
+                // (q -> column, position without an integer division: q < 2^15, and (q + 0.5) / n is at least 0.5 / n away
+                //  from an integer, far more than a float product is off)
+                const float inv_n = 1.0f / (float)n;
+                auto column_of = [&](int q) { return (int)(((float)q + 0.5f) * inv_n); };
                 for (int q = tid; q < nj * n; q += 2 * kFdrThreads) {  // two draws per thread and pass (null_draw2)
                     const int q1 = q + kFdrThreads;
                     const bool has1 = q1 < nj * n;
-                    const int jj0 = q / n, i0 = q - jj0 * n;
-                    const int jj1 = has1 ? q1 / n : jj0, i1 = has1 ? q1 - jj1 * n : i0;
+                    const int jj0 = column_of(q), i0 = q - jj0 * n;
+                    const int jj1 = has1 ? column_of(q1) : jj0, i1 = has1 ? q1 - jj1 * n : i0;
                     NullDraw d0, d1;
                     d1.z = 0.0;
                     null_draw2(P.dm, P.lut, P.guide, P.lut_e, P.lut_o, P.ex[o0 + i0], null_uniform(P.seed, o0 + i0, j0 + jj0),
                                P.ex[o0 + i1], null_uniform(P.seed, o0 + i1, j0 + jj1), has1, d0, d1);
-                    zcol[jj0 * P.nmax + i0] = d0.z;
-                    if (has1) zcol[jj1 * P.nmax + i1] = d1.z;
+                    zcol[jj0 * n + i0] = d0.z;
+                    if (has1) zcol[jj1 * n + i1] = d1.z;
                 }
                 __syncthreads();
                 auto null_window = [&](int q) {
-                    const int jj = q / n, i = q - jj * n;
+                    const int jj = column_of(q), i = q - jj * n;
                     double v = 1.0;  // windowing.pyx:51-54: positions closer than hw to an end
                     if (i >= P.hw && i < n - P.hw) {
-                        const double *z = zcol + jj * P.nmax + i;
+                        const double *z = zcol + jj * n + i;
                         double acc = z[0];
                         for (int h = 1; h <= P.hw; ++h) acc += z[-h] + z[h];
                         const double a = acc * (-P.inv_sqrt_k);
@@ -323,7 +356,9 @@ __global__ void __launch_bounds__(kFdrThreads) efdr_kernel(const FdrParams P) {
                     const double v0 = null_window(q), v1 = has1 ? null_window(q1) : 0.0;
                     const bool f0 = v0 == v0, f1 = has1 && v1 == v1;
                     const unsigned long long k0 = order_key(v0), k1 = order_key(v1);
-                    int a0 = 0, b0 = f0 ? n : 0, a1 = 0, b1 = f1 ? n : 0;  // first k in [0, n] with keys[k] >= key
+                    // first k in [0, n] with keys[k] >= key, bracketed by the guide (window p-values lie in [0, 1])
+                    const int g0 = min((int)(v0 * (double)kKeyGuide), kKeyGuide - 1), g1 = min((int)(v1 * (double)kKeyGuide), kKeyGuide - 1);
+                    int a0 = f0 ? kguide[g0] : 0, b0 = f0 ? kguide[g0 + 1] : 0, a1 = f1 ? kguide[g1] : 0, b1 = f1 ? kguide[g1 + 1] : 0;
                     while (a0 < b0 || a1 < b1) {
                         const int m0 = (a0 + b0) >> 1, m1 = (a1 + b1) >> 1;   // (a finished search sits at <= n: a valid word)
                         const unsigned long long x0 = keys[min(m0, n - 1)], x1 = keys[min(m1, n - 1)];
@@ -553,7 +588,8 @@ __global__ void efdr_long_final_kernel(FdrLong L, long long M, long long o0, dou
 }  // namespace
 
 size_t efdr_smem_bytes(int np, int nmax, int jb) {
-    return (size_t)np * 8 + (size_t)jb * nmax * 8 + (size_t)np * 4 + (size_t)nmax * 4 + (size_t)(np + 1) * 4 + 16;
+    return (size_t)np * 8 + (size_t)jb * nmax * 8 + (size_t)np * 4 + (size_t)nmax * 4 + (size_t)(np + 1) * 4 +
+           (size_t)(kKeyGuide + 2) * 2 + 16;
 }
 
 cudaError_t launch_null_sample(cudaStream_t st, const double *dm, const double2 *lut, const unsigned short *guide, int lut_e,
