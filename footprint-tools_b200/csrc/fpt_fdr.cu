@@ -619,7 +619,10 @@ cudaError_t launch_efdr(cudaStream_t st, const double *dm, const double2 *lut, c
     P.nmax = nmax;
     P.np = 1;
     while (P.np < nmax) P.np <<= 1;
-    P.jb = nulls ? 1 : (4096 / nmax < 1 ? 1 : (4096 / nmax > 8 ? 8 : 4096 / nmax));
+#ifndef FPT_FDR_ZCAP
+#define FPT_FDR_ZCAP 4096   // doubles of the z array (null columns x positions generated per pass)
+#endif
+    P.jb = nulls ? 1 : (FPT_FDR_ZCAP / nmax < 1 ? 1 : (FPT_FDR_ZCAP / nmax > 8 ? 8 : FPT_FDR_ZCAP / nmax));
     if (!nulls && P.jb > times) P.jb = times > 0 ? times : 1;
     // (fewer null columns per pass would buy a fourth CTA per SM, but measured on C3 it loses: 3 columns 127 ms, 2 columns
     // 135 ms, 1 column 162 ms per pass — the two block barriers of a pass cost more than the occupancy gives)
