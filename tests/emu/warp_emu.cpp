@@ -27,15 +27,37 @@ namespace {
 using namespace fpt;
 using namespace fpt::wk;
 
+// The lanes of a step run one after the other; FPT_EMU_LANE_ORDER=reverse runs them 31 .. 0 and =shuffle in a fixed
+// pseudo-random order that changes from step to step: a step whose lanes depend on each other's writes (a missing warp
+// barrier) then gives different results from the ascending order.
 struct HostWarp {
+    int mode = 0;          // 0 ascending, 1 reverse, 2 shuffled
+    unsigned state = 12345u;
+    HostWarp() {
+        const char *m = getenv("FPT_EMU_LANE_ORDER");
+        mode = m && !strcmp(m, "reverse") ? 1 : (m && !strcmp(m, "shuffle") ? 2 : 0);
+    }
+    void order(int *o) {
+        for (int i = 0; i < 32; ++i) o[i] = mode == 1 ? 31 - i : i;
+        if (mode == 2)
+            for (int i = 31; i > 0; --i) {
+                state = state * 1664525u + 1013904223u;
+                const int j = (int)((state >> 8) % (unsigned)(i + 1));
+                const int t = o[i]; o[i] = o[j]; o[j] = t;
+            }
+    }
     template <class F>
     void each(F f) {
-        for (int lane = 0; lane < 32; ++lane) f(lane);
+        int o[32];
+        order(o);
+        for (int i = 0; i < 32; ++i) f(o[i]);
     }
     template <class F>
     unsigned or_reduce(F f) {
+        int o[32];
+        order(o);
         unsigned v = 0;
-        for (int lane = 0; lane < 32; ++lane) v |= f(lane);
+        for (int i = 0; i < 32; ++i) v |= f(o[i]);
         return v;
     }
 };

@@ -159,6 +159,21 @@ def test_emulated_kernel_matches_oracle(emu, oracle, table, lut, shw, scales, al
     assert stats[2] >= batch.n_iv and stats[0] == planned_items(batch, max(scales) if scales else 0)
 
 
+@pytest.mark.parametrize("order", ["reverse", "shuffle"])
+def test_lane_order_does_not_matter(emu, oracle, table, lut, order, monkeypatch):
+    """The emulation runs the 32 lanes of a step one after the other; in reverse and in shuffled order the results must be
+    the same bits — a step whose lanes read what other lanes of the same step write (a missing warp barrier) would differ.
+    Deep counts on a small table: the direct evaluation step (sort, heads, runs) is exercised as well."""
+    batch, info = synth.make_batch(120, 55, seed=77, table=table, depth_scale=6.0)
+    monkeypatch.delenv("FPT_EMU_LANE_ORDER", raising=False)
+    base, redo0, _ = run_emu(emu, oracle, batch, table, 50, (3, 5, 7), lut, hist=True)
+    monkeypatch.setenv("FPT_EMU_LANE_ORDER", order)
+    out, redo1, _ = run_emu(emu, oracle, batch, table, 50, (3, 5, 7), lut, hist=True)
+    assert np.array_equal(np.sort(redo0, axis=0), np.sort(redo1, axis=0))
+    for k in ("exp", "obs", "pval", "winp", "hist"):
+        assert np.array_equal(base[k], out[k], equal_nan=True), k
+
+
 def test_deep_counts_hand_items_back_and_leave_the_table(emu, oracle, table, lut):
     """400x depth: cut counts beyond the packed 16-bit format (items handed to the general kernel untouched), expected /
     observed counts outside the (exp, obs) table (evaluated in place), windows over both."""
