@@ -105,7 +105,9 @@ struct ScoreParams {
     // warp-autonomous kernel (fpt_warp.cu)
     int wmode;                 // windows: 0 none, 1 = {3}, 2 = {3, 5, 7}, 3 = win_h[0 .. n_win_h) (ascending, <= 3)
     int win_h[3], n_win_h;
-    int k_row[3];              // first output row of half-width win_h[k]
+    long long k_off[3];        // pass k of the window step (half-width win_h[k]): offset of its first output row in winp_out,
+    unsigned k_vec;            //   bit k: that row is 32-byte aligned,
+    unsigned k_extra[3];       //   further output rows with the same half-width (bit s = row s)
     long long win_row_off[FPT_MAX_SCALES];  // s * total: offset of output row s in winp_out
     const WPack *items;        // built by the planner kernels
     const int *n_items;

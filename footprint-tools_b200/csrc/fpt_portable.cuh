@@ -223,6 +223,20 @@ FPT_HD f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return r;
 }
 
+// v with its high word replaced by `hi` when cond holds (one select on the high word; the low word stays)
+FPT_HD double set_hi_if(double v, unsigned hi, bool cond) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(cond ? (int)hi : __double2hiint(v), __double2loint(v));
+#else
+    if (!cond) return v;
+    unsigned long long b;
+    std::memcpy(&b, &v, 8);
+    b = (b & 0xFFFFFFFFull) | ((unsigned long long)hi << 32);
+    std::memcpy(&v, &b, 8);
+    return v;
+#endif
+}
+
 template <class T>
 FPT_HD T ldg(const T *p) {
 #if defined(__CUDA_ARCH__)

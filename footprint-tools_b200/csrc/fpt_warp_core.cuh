@@ -823,12 +823,20 @@ FPT_HD void step_direct(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, con
 
 // ---- step E: multi-scale Stouffer windows (windowing.h:53-67) of the 4 outputs of group cg from shared-memory z ----
 // z is stored transposed (element index major) so that lane-consecutive groups read consecutive doubles. Sums grow
-// outward from the centre, S_h = S_{h-1} + (z[-h] + z[+h]); the edge rule of windowing.pyx:51-54 sets positions
-// closer than h to an interval end to 1.0. WM selects the half-widths: 1 = {3} (cli/detect.py:84), 2 = {3, 5, 7}
-// (BASELINE.json config C3), both unrolled at compile time; 3 = up to three ascending half-widths given at run time
-// (P.win_h). The normal tails of the up to three sums are evaluated in a ROLLED loop: one copy of the ~270
+// outward from the centre, S_h = S_{h-1} + (z[-h] + z[+h]). WM selects the half-widths: 1 = {3} (cli/detect.py:84),
+// 2 = {3, 5, 7} (BASELINE.json config C3), both unrolled at compile time; 3 = up to three ascending half-widths given at
+// run time (P.win_h). The normal tails of the up to three sums are evaluated in a ROLLED loop: one copy of the ~240
 // instructions of ndtr4 in the kernel instead of one per half-width (16 desynchronised warps share the SM's
-// instruction cache).
+// instruction cache). Everything else is kept out of that loop (it ran 76 instructions of overhead per pass around the
+// 237 of the normal tail):
+//   * the edge rule of windowing.pyx:51-54 — positions closer than h to an interval end are 1.0 — is applied where the
+//     sums are formed, with h a compile-time constant: such an element's ARGUMENT gets the high word of 20.0, and the
+//     normal lower tail of any a in [20, 20.00002) is exactly 1.0 (1 - Phi(-20) = 1 - 2.8e-89 rounds to 1), whatever
+//     the sum was (NaN and infinite sums included: the reference never looks at them there either);
+//   * the output row of pass k is the lane's row-0 address plus P.k_off[k]; P.k_vec / P.k_extra hold its alignment bit
+//     and the (rare) further rows of the same half-width — all prepared by the host (fpt_warp_host.h);
+//   * the three argument sets are not rotated through each other: pass k + 1 takes A1 or A2 by one select.
+constexpr unsigned kWEdgeArgHi = 0x40340000u;  // high word of 20.0
 template <int WM, class Env>
 FPT_HD void step_windows(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, int cg, Env &env) {
     constexpr int HTOP = WM == 1 ? 3 : (WM == 2 ? 7 : kFastMaxScaleHalfWin);
@@ -837,11 +845,11 @@ FPT_HD void step_windows(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, in
     const int a = G.oa - c0 > 0 ? G.oa - c0 : 0, b = G.oz - c0 < 4 ? G.oz - c0 : 4;
     if (b <= a) return;
     const unsigned omask = ((1u << b) - 1u) & ~((1u << a) - 1u);
-    const long long f0 = G.Fb + c0;
+    double *const out0 = P.winp_out + (G.Fb + c0);  // the group's 4 outputs in row 0 of winp_out
     const int dl = G.Tb + c0;  // interval-local index of element 0
     const int glen = G.len;
     const double *zt = S.zsT + 2 + cg;
-    int h0 = WM == 3 ? P.win_h[0] : 3, h1 = WM == 3 ? P.win_h[1] : (WM == 2 ? 5 : -1), h2 = WM == 3 ? P.win_h[2] : (WM == 2 ? 7 : -1);
+    const int h0 = WM == 3 ? P.win_h[0] : 3, h1 = WM == 3 ? P.win_h[1] : (WM == 2 ? 5 : -1), h2 = WM == 3 ? P.win_h[2] : (WM == 2 ? 7 : -1);
     const int ns = WM == 3 ? P.n_win_h : (WM == 2 ? 3 : 1);
     double A0[4] = {0.0, 0.0, 0.0, 0.0}, A1[4] = {0.0, 0.0, 0.0, 0.0}, A2[4] = {0.0, 0.0, 0.0, 0.0};
     {
@@ -860,47 +868,39 @@ FPT_HD void step_windows(const ScoreParams &P, const PackGeo &Q, WarpSmem &S, in
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[e] += Lw[e] + Rw[e];
             }
-            const double cneg = -P.inv_sqrt_k[h];
-            if (h == h0) {
+            if (h == h0 || h == h1 || h == h2) {
+                // valid iff 0 <= t - h and t + h <= len - 1, i.e. (unsigned)(t - h) < len - 2h (none when len <= 2h)
+                const double cneg = -P.inv_sqrt_k[h];
+                const int lim = glen - 2 * h;
+                const unsigned ulim = lim > 0 ? (unsigned)lim : 0u;
+                double v[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) A0[e] = acc[e] * cneg;
-            }
-            if (h == h1) {
+                for (int e = 0; e < 4; ++e) v[e] = pt::set_hi_if(acc[e] * cneg, kWEdgeArgHi, (unsigned)(dl + e - h) >= ulim);
+                if (h == h0) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) A1[e] = acc[e] * cneg;
-            }
-            if (h == h2) {
+                    for (int e = 0; e < 4; ++e) A0[e] = v[e];
+                } else if (h == h1) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) A2[e] = acc[e] * cneg;
+                    for (int e = 0; e < 4; ++e) A1[e] = v[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) A2[e] = v[e];
+                }
             }
         }
     }
+    const unsigned fast = omask == 0xFu ? P.k_vec : 0u;  // bit k: pass k stores its 4 outputs as one 256-bit word
 #pragma unroll 1
     for (int k = 0; k < ns; ++k) {
         double res[4];
         env.ndtr4(A0, res);
-        const int h = h0;
-        {
-            // edge rule: valid iff 0 <= t - h and t + h <= len - 1, i.e. (unsigned)(t - h) < len - 2h (none when len <= 2h)
-            const int lim = glen - 2 * h;
-            const unsigned ulim = lim > 0 ? (unsigned)lim : 0u;
+        double *dst = out0 + P.k_off[k];
+        if ((fast >> k) & 1u) env.st256(dst, res[0], res[1], res[2], res[3]);
+        else store_partial(dst, omask, res[0], res[1], res[2], res[3]);
+        for (unsigned m = P.k_extra[k]; m; m &= m - 1)   // further output rows with the same half-width (rare)
+            store_partial(out0 + P.win_row_off[pt::ffs32(m) - 1], omask, res[0], res[1], res[2], res[3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if ((unsigned)(dl + e - h) >= ulim) res[e] = 1.0;
-        }
-        {   // the output row of this half-width (P.k_row: its first row; further rows with the same half-width are rare)
-            const int s = P.k_row[k];
-            double *dst = P.winp_out + (P.win_row_off[s] + f0);
-            if (omask == 0xFu && ((P.winp_vec >> s) & 1u)) env.st256(dst, res[0], res[1], res[2], res[3]);
-            else store_partial(dst, omask, res[0], res[1], res[2], res[3]);
-        }
-        for (unsigned m = P.h_rows[h] & (P.h_rows[h] - 1); m; m &= m - 1) {
-            const int s = pt::ffs32(m) - 1;
-            store_partial(P.winp_out + (P.win_row_off[s] + f0), omask, res[0], res[1], res[2], res[3]);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { A0[e] = A1[e]; A1[e] = A2[e]; }
-        h0 = h1; h1 = h2;
+        for (int e = 0; e < 4; ++e) A0[e] = k == 0 ? A1[e] : A2[e];
     }
 }
 

@@ -28,7 +28,8 @@ inline bool warp_params_finish(ScoreParams &p, const fpt_score_args *a, int wh_m
     p.wmode = 0;
     p.n_win_h = 0;
     p.win_h[0] = p.win_h[1] = p.win_h[2] = -1;
-    p.k_row[0] = p.k_row[1] = p.k_row[2] = 0;
+    p.k_vec = 0;
+    for (int k = 0; k < 3; ++k) { p.k_off[k] = 0; p.k_extra[k] = 0; }
     if (windows) {
         for (int s = 0; s < a->n_scales; ++s) {
             p.win_row_off[s] = (long long)s * (long long)a->total;
@@ -40,7 +41,9 @@ inline bool warp_params_finish(ScoreParams &p, const fpt_score_args *a, int wh_m
                 if (p.n_win_h == 3) return false;
                 int first = 0;
                 while (!((p.h_rows[h] >> first) & 1u)) ++first;
-                p.k_row[p.n_win_h] = first;
+                p.k_off[p.n_win_h] = p.win_row_off[first];
+                if ((p.winp_vec >> first) & 1u) p.k_vec |= 1u << p.n_win_h;
+                p.k_extra[p.n_win_h] = p.h_rows[h] & (p.h_rows[h] - 1);
                 p.win_h[p.n_win_h++] = h;
             }
         p.wmode = (p.n_win_h == 1 && p.win_h[0] == 3) ? 1
